@@ -30,6 +30,11 @@ extern "C" {
 #endif
 
 #define PQC_ABI_VERSION 1
+#if defined(__GNUC__)
+#define PQC_API __attribute__((visibility("default")))
+#else
+#define PQC_API
+#endif
 #define PQC_MAX_QUBITS 30
 
 typedef struct pqc_program pqc_program;
@@ -58,7 +63,9 @@ enum pqc_opcode {
 
 /* One primitive operation.  angle = scale * angles[s, param] + offset when param >= 0,
  * angle = offset when param < 0 (fixed_R_y/fixed_R_z).  negative_R_z: scale = -1
- * (gates.py:180-187); offset_R_z: offset (gates.py:190-205).
+ * (gates.py:180-187); offset_R_z: offset (gates.py:190-205).  fSim family (full angles,
+ * no half): theta = offset + angles[s, param]; phi = angles[s, param2], or the `scale`
+ * field when param2 < 0 (a frozen fSim).
  * `group` is the index of the reference Gate object in PQC.gates (circuit.py:53-61)
  * this primitive came from: CHAIN / ALLTOALL / shared_parameter / RR_block expand to
  * several primitives sharing one group. */
@@ -82,62 +89,69 @@ typedef struct pqc_pauli_term {
   double re, im;
 } pqc_pauli_term;
 
-const char* pqc_last_error(void);
-int pqc_abi_version(void);
+PQC_API const char* pqc_last_error(void);
+PQC_API int pqc_abi_version(void);
 /* Fails (<0) unless the current CUDA device is compute capability 10.x. */
-int pqc_device_check(int* cc_major, int* cc_minor, int* n_sms);
+PQC_API int pqc_device_check(int* cc_major, int* cc_minor, int* n_sms);
 
 /* ---- gate programs: replaces PQC.set_gates / the per-gate 2^n x 2^n operator rebuild
  * (circuit.py:53-72, gates.py:122-131,469-477) ---------------------------------------- */
-int pqc_program_create(int n_qubits, int n_params, int n_ops, const pqc_op* h_ops,
+PQC_API int pqc_program_create(int n_qubits, int n_params, int n_ops, const pqc_op* h_ops,
                        pqc_program** out);
-int pqc_program_destroy(pqc_program* prog);
+PQC_API int pqc_program_destroy(pqc_program* prog);
 /* out[0]=n_qubits out[1]=n_params out[2]=n_ops out[3]=n_passes (forward plan)
- * out[4]=tile_bits out[5]=n_param_groups out[6]=qfim passes out[7]=reserved */
-int pqc_program_stats(const pqc_program* prog, int64_t* out8);
+ * out[4]=tile_bits out[5]=1 if derivative states are supported out[6]=passes of the
+ * derivative / QFIM plan out[7]=reserved */
+PQC_API int pqc_program_stats(const pqc_program* prog, int64_t* out8);
 
 /* ---- PQC.run for a batch (circuit.py:118-125).  d_init: NULL = |0..0>; otherwise
  * init_stride = 0 broadcasts one [D] vector, init_stride = D gives one per sample
  * (the latter is `Gate * state`, gates.py:63-67).  d_out [S, D]. */
-int pqc_run_batch(const pqc_program* prog, const double* d_angles, int64_t ld_angles,
+PQC_API int pqc_run_batch(const pqc_program* prog, const double* d_angles, int64_t ld_angles,
                   int64_t n_samples, const pqc_c128* d_init, int64_t init_stride,
                   pqc_c128* d_out, void* stream);
 
-/* ---- PQC.get_gradients (circuit.py:149-192): d_out [S, P, D], slot p = derivative
- * state for parameter slot p, i.e. U_G..(D_p U_p)..U_1|init>. */
-int pqc_gradients_batch(const pqc_program* prog, const double* d_angles, int64_t ld_angles,
+/* ---- PQC.get_gradients (circuit.py:149-192): d_out [S, P+1, D]; slot 0 = the final
+ * state, slot 1+p = derivative state for parameter slot p, i.e. U_G..(D_p U_p)..U_1|init>
+ * with D_p the sum of the Pauli generators of the gate's members (gates.py:133-138,
+ * 454-457,519-522).  init_stride must be 0 (one shared initial state). */
+PQC_API int pqc_gradients_batch(const pqc_program* prog, const double* d_angles, int64_t ld_angles,
                         int64_t n_samples, const pqc_c128* d_init, int64_t init_stride,
                         pqc_c128* d_out, void* stream);
 
 /* ---- Measurements.get_QFI (measure.py:33-71) from explicit states:
  * F[s,p,q] = 4 Re(<d_p|d_q> - conj<psi|d_p> <psi|d_q>).  d_states [S,D],
  * d_grads [S,P,D], d_qfim [S,P,P] float64. */
-int pqc_qfim_from_grads(const pqc_c128* d_states, const pqc_c128* d_grads, int n_qubits,
+PQC_API int pqc_qfim_from_grads(const pqc_c128* d_states, const pqc_c128* d_grads, int n_qubits,
                         int n_params, int64_t n_samples, double* d_qfim, void* stream);
 
 /* ---- fused batch path for update_state + get_QFI (circuit.py:127-130, measure.py:33-71)
  * that never materialises the P derivative states of a sample at once outside the
  * caller-provided workspace.  d_states_out may be NULL. */
-int pqc_qfim_workspace_bytes(const pqc_program* prog, int64_t n_samples, int64_t* bytes);
-int pqc_qfim_batch(const pqc_program* prog, const double* d_angles, int64_t ld_angles,
+PQC_API int pqc_qfim_workspace_bytes(const pqc_program* prog, int64_t n_samples, int64_t* bytes);
+PQC_API int pqc_qfim_batch(const pqc_program* prog, const double* d_angles, int64_t ld_angles,
                    int64_t n_samples, const pqc_c128* d_init, void* d_work,
                    int64_t work_bytes, double* d_qfim, pqc_c128* d_states_out, void* stream);
 
 /* ---- scipy.linalg.eigh eigenvalues (measure.py:73-75,84) for S symmetric PxP
  * matrices, ascending; and the `eigvals > cutoff` count (measure.py:85-86). */
-int pqc_eigvalsh_batch(const double* d_mats, int64_t n_mats, int dim, double* d_eig,
+PQC_API int pqc_eigvalsh_batch(const double* d_mats, int64_t n_mats, int dim, double* d_eig,
                        void* stream);
-int pqc_count_greater(const double* d_vals, int64_t rows, int cols, double cutoff,
+/* scipy.linalg.eigh with eigenvectors (measure.py:73-75): d_vecs [S,P,P] row-major,
+ * column k = unit eigenvector of the k-th (ascending) eigenvalue; may be NULL. */
+PQC_API int pqc_eigh_batch(const double* d_mats, int64_t n_mats, int dim, double* d_eig,
+                   double* d_vecs, void* stream);
+PQC_API int pqc_count_greater(const double* d_vals, int64_t rows, int cols, double cutoff,
                       int32_t* d_counts, void* stream);
 
 /* ---- Measurements.single_Q / entanglement (measure.py:226-249): Q[s]. */
-int pqc_meyer_wallach(const pqc_c128* d_states, int64_t n_samples, int n_qubits, double* d_Q,
+PQC_API int pqc_meyer_wallach(const pqc_c128* d_states, int64_t n_samples, int n_qubits, double* d_Q,
                       void* stream);
 /* Qobj.ptrace(k) for one qubit (measure.py:233): d_rho = 2x2 row-major. */
-int pqc_ptrace_1q(const pqc_c128* d_state, int n_qubits, int qubit, pqc_c128* d_rho,
+PQC_API int pqc_ptrace_1q(const pqc_c128* d_state, int n_qubits, int qubit, pqc_c128* d_rho,
                   void* stream);
 /* Qobj.overlap (measure.py:52,58,135; circuit.py:141): out[i] = <a_i|b_i>. */
-int pqc_overlap_batch(const pqc_c128* d_a, int64_t stride_a, const pqc_c128* d_b,
+PQC_API int pqc_overlap_batch(const pqc_c128* d_a, int64_t stride_a, const pqc_c128* d_b,
                       int64_t stride_b, int64_t dim, int64_t count, pqc_c128* d_out,
                       void* stream);
 
@@ -145,28 +159,28 @@ int pqc_overlap_batch(const pqc_c128* d_a, int64_t stride_a, const pqc_c128* d_b
  * triangular != 0: A == B block, only i < j (itertools.combinations).  Counts are ADDED
  * into d_hist[bins] (int64) with np.histogram(range=(0,1)) semantics.  d_F (optional):
  * triangular -> packed combinations order [SA(SA-1)/2]; else row-major [SA,SB]. */
-int pqc_fidelity_hist(const pqc_c128* d_A, int64_t n_a, const pqc_c128* d_B, int64_t n_b,
+PQC_API int pqc_fidelity_hist(const pqc_c128* d_A, int64_t n_a, const pqc_c128* d_B, int64_t n_b,
                       int n_qubits, int triangular, int64_t bins, long long* d_hist,
                       double* d_F, void* stream);
 /* np.histogram(F, bins, range=(0,1)) for caller-supplied samples (expr(F_samples, N)). */
-int pqc_hist_f64(const double* d_F, int64_t count, int64_t bins, long long* d_hist,
+PQC_API int pqc_hist_f64(const double* d_F, int64_t count, int64_t bins, long long* d_hist,
                  void* stream);
 /* Measurements.expr on histogram counts (measure.py:161-180): KL(P_pqc || P_haar(N)).
  * d_scratch: 4 doubles. */
-int pqc_kl_haar(const long long* d_hist, int64_t bins, double hilbert_dim, double* d_out,
+PQC_API int pqc_kl_haar(const long long* d_hist, int64_t bins, double hilbert_dim, double* d_out,
                 double* d_scratch, void* stream);
 
 /* ---- renyi_entropy_fast / gkp_fast (measure.py:318-368) via Walsh-Hadamard over
  * Z-masks for every X-mask.  d_out [n_alpha, S]: 1/(1-a) ln(sum |2^{-n/2} W|^{2a}) - n ln 2. */
-int pqc_magic_batch(const pqc_c128* d_states, int64_t n_samples, int n_qubits, int n_alpha,
+PQC_API int pqc_magic_batch(const pqc_c128* d_states, int64_t n_samples, int n_qubits, int n_alpha,
                     const double* h_alphas, double* d_out, void* stream);
 
 /* ---- qt.expect(H, psi) with H a Pauli sum (circuit.py:28-31,132-137): out[s] = <psi_s|H|psi_s>
  * and H|psi> itself (measure.py:468). */
-int pqc_pauli_expect_batch(const pqc_c128* d_states, int64_t n_samples, int n_qubits,
+PQC_API int pqc_pauli_expect_batch(const pqc_c128* d_states, int64_t n_samples, int n_qubits,
                            int n_terms, const pqc_pauli_term* h_terms, pqc_c128* d_out,
                            void* stream);
-int pqc_pauli_apply_batch(const pqc_c128* d_states, int64_t n_samples, int n_qubits,
+PQC_API int pqc_pauli_apply_batch(const pqc_c128* d_states, int64_t n_samples, int n_qubits,
                           int n_terms, const pqc_pauli_term* h_terms, pqc_c128* d_out,
                           void* stream);
 

@@ -1,0 +1,257 @@
+// pqc_api.cu -- C-ABI entry points for programs, state generation, derivative states and
+// the fused QFIM pipeline (include/pqc_b200.h).
+#include <algorithm>
+#include <cstring>
+
+#include "pqc_common.cuh"
+
+static thread_local std::string g_last_error;
+void pqc_set_error(const std::string& msg) { g_last_error = msg; }
+
+extern "C" const char* pqc_last_error(void) { return g_last_error.c_str(); }
+extern "C" int pqc_abi_version(void) { return PQC_ABI_VERSION; }
+
+extern "C" int pqc_device_check(int* cc_major, int* cc_minor, int* n_sms) {
+  int dev = 0;
+  PQC_CUDA(cudaGetDevice(&dev));
+  int maj = 0, min = 0, sms = 0;
+  PQC_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  PQC_CUDA(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+  PQC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major) *cc_major = maj;
+  if (cc_minor) *cc_minor = min;
+  if (n_sms) *n_sms = sms;
+  if (maj != 10) PQC_FAIL(-3, "this library is built for sm_100a (B200) only");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// programs
+// ---------------------------------------------------------------------------------
+extern "C" int pqc_program_create(int n_qubits, int n_params, int n_ops, const pqc_op* h_ops,
+                                  pqc_program** out) {
+  if (!out) PQC_FAIL(-1, "null output handle");
+  *out = nullptr;
+  if (n_qubits < 1 || n_qubits > PQC_MAX_QUBITS) PQC_FAIL(-1, "n_qubits must be in [1, 30]");
+  if (n_params < 0 || n_ops < 0) PQC_FAIL(-1, "negative counts");
+  for (int i = 0; i < n_ops; ++i) {
+    const pqc_op& op = h_ops[i];
+    if (op.kind < 0 || op.kind >= PQC_OP__COUNT) PQC_FAIL(-1, "unknown opcode");
+    const bool two = op.kind == PQC_OP_CNOT || op.kind == PQC_OP_CZ ||
+                     op.kind == PQC_OP_SQRTISWAP || op.kind == PQC_OP_RXX ||
+                     op.kind == PQC_OP_RYY || op.kind == PQC_OP_RZZ || op.kind == PQC_OP_FSIM ||
+                     op.kind == PQC_OP_FIXED_FSIM;
+    if (op.q0 < 0 || op.q0 >= n_qubits) PQC_FAIL(-1, "qubit index out of range");
+    if (two && (op.q1 < 0 || op.q1 >= n_qubits || op.q1 == op.q0))
+      PQC_FAIL(-1, "two-qubit op needs two distinct qubits in range");
+    if (op.param >= n_params || op.param2 >= n_params) PQC_FAIL(-1, "parameter slot out of range");
+  }
+  pqc_program* p = new pqc_program();
+  p->n = n_qubits;
+  p->P = n_params;
+  p->ops.assign(h_ops, h_ops + n_ops);
+  for (auto& op : p->ops) {
+    const bool two = op.kind == PQC_OP_CNOT || op.kind == PQC_OP_CZ ||
+                     op.kind == PQC_OP_SQRTISWAP || op.kind == PQC_OP_RXX ||
+                     op.kind == PQC_OP_RYY || op.kind == PQC_OP_RZZ || op.kind == PQC_OP_FSIM ||
+                     op.kind == PQC_OP_FIXED_FSIM;
+    if (!two) op.q1 = -1;
+  }
+  const int rc = pqc_plan_program(p);
+  if (rc) {
+    pqc_program_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return 0;
+}
+
+extern "C" int pqc_program_destroy(pqc_program* prog) {
+  if (!prog) return 0;
+  if (prog->d_ops) cudaFree(prog->d_ops);
+  if (prog->d_gens) cudaFree(prog->d_gens);
+  delete prog;
+  return 0;
+}
+
+extern "C" int pqc_program_stats(const pqc_program* prog, int64_t* out8) {
+  if (!prog || !out8) PQC_FAIL(-1, "null argument");
+  out8[0] = prog->n;
+  out8[1] = prog->P;
+  out8[2] = (int64_t)prog->ops.size();
+  out8[3] = (int64_t)prog->run_passes.size();
+  out8[4] = prog->tile_bits;
+  out8[5] = prog->grad_supported ? 1 : 0;
+  int64_t q = 0;
+  for (auto& v : prog->seg_passes) q += (int64_t)v.size();
+  out8[6] = q;
+  out8[7] = 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// PQC.run (circuit.py:118-125)
+// ---------------------------------------------------------------------------------
+static int init_mode_of(const pqc_c128* d_init, int64_t init_stride) {
+  if (!d_init) return 1;
+  return init_stride == 0 ? 2 : 3;
+}
+
+extern "C" int pqc_run_batch(const pqc_program* prog, const double* d_angles, int64_t ld,
+                             int64_t S, const pqc_c128* d_init, int64_t init_stride,
+                             pqc_c128* d_out, void* stream) {
+  if (!prog || !d_out) PQC_FAIL(-1, "null argument");
+  if (S <= 0) return 0;
+  if (prog->P > 0 && (!d_angles || ld < prog->P)) PQC_FAIL(-1, "No parameters supplied!");
+  cudaStream_t st = (cudaStream_t)stream;
+  int mode = init_mode_of(d_init, init_stride);
+  for (const Pass& ps : prog->run_passes) {
+    const int rc = pqc_launch_pass(prog, ps, (c128*)d_out, (const c128*)d_init, init_stride, mode,
+                                   d_angles, ld, S, 1, 1, 0, st);
+    if (rc) return rc;
+    mode = 0;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// PQC.get_gradients (circuit.py:149-192), forward form: the state and every already
+// spawned derivative vector advance together; derivative p is spawned as
+// (sum of generators) * psi right after parameter p's gate (gates.py:133-138,454-457).
+// d_out [S][P+1][D]: slot 0 = final state, slot 1+p = derivative state p.
+// ---------------------------------------------------------------------------------
+static int forward_derivatives(const pqc_program* prog, const double* d_angles, int64_t ld,
+                               int64_t S, const pqc_c128* d_init, int64_t init_stride, c128* buf,
+                               c128* d_G, bool trailing_all, bool trailing_state_only,
+                               cudaStream_t st);
+
+extern "C" int pqc_gradients_batch(const pqc_program* prog, const double* d_angles, int64_t ld,
+                                   int64_t S, const pqc_c128* d_init, int64_t init_stride,
+                                   pqc_c128* d_out, void* stream) {
+  if (!prog || !d_out) PQC_FAIL(-1, "null argument");
+  if (S <= 0) return 0;
+  if (!prog->grad_supported) PQC_FAIL(-4, "derivative states unsupported: " + prog->grad_reason);
+  if (prog->P > 0 && (!d_angles || ld < prog->P)) PQC_FAIL(-1, "No parameters supplied!");
+  return forward_derivatives(prog, d_angles, ld, S, d_init, init_stride, (c128*)d_out, nullptr,
+                             true, false, (cudaStream_t)stream);
+}
+
+// <slot j | slot k> for j = 0..k-1... written into G[(s*(P+1)+j)*P + p]; one CTA per (s, j)
+__global__ void __launch_bounds__(256) k_slot_dots(const c128* __restrict__ buf, int n,
+                                                   int slots_total, int new_slot, int P, int p,
+                                                   c128* __restrict__ G) {
+  __shared__ double red[32];
+  const long long D = 1ll << n;
+  const int rows = new_slot + 1;
+  const long long s = blockIdx.x / rows;
+  const int j = blockIdx.x % rows;
+  const c128* a = buf + ((s * slots_total + j) << n);
+  const c128* b = buf + ((s * slots_total + new_slot) << n);
+  double re = 0.0, im = 0.0;
+  for (long long i = threadIdx.x; i < D; i += 256) {
+    const c128 x = a[i], y = b[i];
+    re += x.x * y.x + x.y * y.y;
+    im += x.x * y.y - x.y * y.x;
+  }
+  re = block_sum<256>(re, red);
+  im = block_sum<256>(im, red);
+  if (threadIdx.x == 0) G[(s * (P + 1) + j) * P + p] = make_double2(re, im);
+}
+
+static int forward_derivatives(const pqc_program* prog, const double* d_angles, int64_t ld,
+                               int64_t S, const pqc_c128* d_init, int64_t init_stride, c128* buf,
+                               c128* d_G, bool trailing_all, bool trailing_state_only,
+                               cudaStream_t st) {
+  const int P = prog->P, n = prog->n;
+  const int slots_total = P + 1;
+  int mode = init_mode_of(d_init, init_stride);
+  if (P == 0) {
+    for (const Pass& ps : prog->run_passes) {
+      const int rc = pqc_launch_pass(prog, ps, buf, (const c128*)d_init, init_stride, mode,
+                                     d_angles, ld, S, 1, 1, 0, st);
+      if (rc) return rc;
+      mode = 0;
+    }
+    return 0;
+  }
+  for (int p = 0; p < P; ++p) {
+    for (const Pass& ps : prog->seg_passes[p]) {
+      const int active = mode != 0 ? 1 : p + 1;
+      int rc = pqc_launch_pass(prog, ps, buf, (const c128*)d_init, init_stride, mode, d_angles,
+                               ld, S * active, active, slots_total, 0, st);
+      if (rc) return rc;
+      mode = 0;
+    }
+    const int g0 = prog->gen_off[p], g1 = prog->gen_off[p + 1];
+    int rc = pqc_pauli_apply_slots(buf, buf, n, S, slots_total, 0, p + 1, prog->d_gens + g0,
+                                   g1 - g0, st);
+    if (rc) return rc;
+    if (d_G) {
+      const long long grid = S * (p + 2);
+      if (grid > 0x7fffffffLL) PQC_FAIL(-1, "dot grid too large");
+      k_slot_dots<<<(unsigned)grid, 256, 0, st>>>(buf, n, slots_total, p + 1, P, p, d_G);
+      PQC_LAUNCH_CHECK();
+    }
+  }
+  if (trailing_all || trailing_state_only) {
+    const int active = trailing_all ? P + 1 : 1;
+    for (const Pass& ps : prog->seg_passes[P]) {
+      const int rc = pqc_launch_pass(prog, ps, buf, nullptr, 0, 0, d_angles, ld, S * active,
+                                     active, slots_total, 0, st);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// fused update_state + get_QFI over a batch (circuit.py:127-130, measure.py:33-71).
+// Overlaps are taken at spawn time: every later gate is a unitary applied to both
+// vectors, so <d_p|d_q> and <psi|d_p> do not change afterwards.
+// ---------------------------------------------------------------------------------
+static int64_t qfim_bytes_per_sample(const pqc_program* prog) {
+  const int64_t D = 1ll << prog->n;
+  return (int64_t)(prog->P + 1) * D * (int64_t)sizeof(c128) +
+         (int64_t)(prog->P + 1) * std::max(1, prog->P) * (int64_t)sizeof(c128);
+}
+
+extern "C" int pqc_qfim_workspace_bytes(const pqc_program* prog, int64_t S, int64_t* bytes) {
+  if (!prog || !bytes) PQC_FAIL(-1, "null argument");
+  *bytes = qfim_bytes_per_sample(prog) * std::max<int64_t>(1, S) + 256;
+  return 0;
+}
+
+extern "C" int pqc_qfim_batch(const pqc_program* prog, const double* d_angles, int64_t ld,
+                              int64_t S, const pqc_c128* d_init, void* d_work, int64_t work_bytes,
+                              double* d_qfim, pqc_c128* d_states_out, void* stream) {
+  if (!prog || !d_work || !d_qfim) PQC_FAIL(-1, "null argument");
+  if (S <= 0) return 0;
+  if (!prog->grad_supported) PQC_FAIL(-4, "QFIM unsupported: " + prog->grad_reason);
+  if (prog->P > 0 && (!d_angles || ld < prog->P)) PQC_FAIL(-1, "No parameters supplied!");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = prog->P, n = prog->n;
+  const int64_t D = 1ll << n;
+  const int64_t per = qfim_bytes_per_sample(prog);
+  // 256 B aligned start
+  uintptr_t w0 = ((uintptr_t)d_work + 255) & ~(uintptr_t)255;
+  const int64_t usable = work_bytes - (int64_t)(w0 - (uintptr_t)d_work);
+  int64_t C = usable / per;
+  if (C < 1) PQC_FAIL(-1, "QFIM workspace too small for one sample");
+  C = std::min<int64_t>(C, S);
+  for (int64_t c0 = 0; c0 < S; c0 += C) {
+    const int64_t c = std::min<int64_t>(C, S - c0);
+    c128* buf = (c128*)w0;
+    c128* G = buf + c * (int64_t)(P + 1) * D;
+    int rc = forward_derivatives(prog, d_angles + c0 * ld, ld, c, d_init, 0, buf, G, false,
+                                 d_states_out != nullptr, st);
+    if (rc) return rc;
+    rc = pqc_qfim_finalize(G, c, P, d_qfim + c0 * (int64_t)P * P, st);
+    if (rc) return rc;
+    if (d_states_out) {
+      PQC_CUDA(cudaMemcpy2DAsync((c128*)d_states_out + c0 * D, D * sizeof(c128), buf,
+                                 (size_t)(P + 1) * D * sizeof(c128), D * sizeof(c128), c,
+                                 cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,842 @@
+// pqc_measure.cu -- capacity-measure kernels over batches of statevectors.
+// Each entry point cites the reference lines it replaces (/root/reference/pyramaterised/).
+#include <algorithm>
+#include <cmath>
+
+#include "pqc_common.cuh"
+
+// ---------------------------------------------------------------------------------
+// Qobj.overlap: out[i] = <a_i|b_i>   (measure.py:52,58,135; circuit.py:141)
+// One CTA per pair -> fixed summation order -> bitwise reproducible run to run.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_overlap(const c128* __restrict__ A, long long sa,
+                                                 const c128* __restrict__ B, long long sb,
+                                                 long long dim, c128* __restrict__ out) {
+  __shared__ double red[32];
+  const c128* a = A + (long long)blockIdx.x * sa;
+  const c128* b = B + (long long)blockIdx.x * sb;
+  double re = 0.0, im = 0.0;
+  for (long long i = threadIdx.x; i < dim; i += 256) {
+    const c128 x = a[i], y = b[i];
+    re += x.x * y.x + x.y * y.y;
+    im += x.x * y.y - x.y * y.x;
+  }
+  re = block_sum<256>(re, red);
+  im = block_sum<256>(im, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = make_double2(re, im);
+}
+
+extern "C" int pqc_overlap_batch(const pqc_c128* d_a, int64_t stride_a, const pqc_c128* d_b,
+                                 int64_t stride_b, int64_t dim, int64_t count, pqc_c128* d_out,
+                                 void* stream) {
+  if (count <= 0) return 0;
+  if (count > 0x7fffffffLL) PQC_FAIL(-1, "too many overlaps in one call");
+  k_overlap<<<(unsigned)count, 256, 0, (cudaStream_t)stream>>>(
+      (const c128*)d_a, stride_a, (const c128*)d_b, stride_b, dim, (c128*)d_out);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Meyer-Wallach (measure.py:226-249): per qubit k the 1-qubit reduced density matrix
+// rho_k = [[r00, r01],[conj r01, r11]] and Q = 2 (1 - 1/n sum_k Tr rho_k^2),
+// Tr rho^2 = r00^2 + r11^2 + 2|r01|^2.
+// acc layout [S][n][4] = (r00, r11, Re r01, Im r01).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mw_accumulate(const c128* __restrict__ states, int n,
+                                                       int chunk_log2, double* __restrict__ acc) {
+  __shared__ double red[32];
+  const long long D = 1ll << n;
+  const int chunks_log2 = n - chunk_log2;
+  const long long s = blockIdx.x >> chunks_log2;
+  const long long c0 = ((long long)blockIdx.x & ((1ll << chunks_log2) - 1)) << chunk_log2;
+  const c128* psi = states + s * D;
+  const long long csize = 1ll << chunk_log2;
+  for (int b = 0; b < n; ++b) {
+    const long long bit = 1ll << b;
+    double r00 = 0, r11 = 0, xr = 0, xi = 0;
+    for (long long i = threadIdx.x; i < csize; i += 256) {
+      const long long x = c0 + i;
+      if (x & bit) continue;
+      const c128 a0 = psi[x], a1 = psi[x | bit];
+      r00 += a0.x * a0.x + a0.y * a0.y;
+      r11 += a1.x * a1.x + a1.y * a1.y;
+      xr += a0.x * a1.x + a0.y * a1.y;      // a0 * conj(a1)
+      xi += a0.y * a1.x - a0.x * a1.y;
+    }
+    r00 = block_sum<256>(r00, red);
+    r11 = block_sum<256>(r11, red);
+    xr = block_sum<256>(xr, red);
+    xi = block_sum<256>(xi, red);
+    if (threadIdx.x == 0) {
+      double* o = acc + (s * n + (n - 1 - b)) * 4;   // store by QUBIT index
+      if (chunks_log2 == 0) {
+        o[0] = r00; o[1] = r11; o[2] = xr; o[3] = xi;
+      } else {
+        atomicAdd(o + 0, r00); atomicAdd(o + 1, r11); atomicAdd(o + 2, xr); atomicAdd(o + 3, xi);
+      }
+    }
+  }
+}
+
+__global__ void k_mw_finalize(const double* __restrict__ acc, long long S, int n,
+                              double* __restrict__ Q) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double tot = 0.0;
+  for (int k = 0; k < n; ++k) {
+    const double* o = acc + (s * n + k) * 4;
+    tot += o[0] * o[0] + o[1] * o[1] + 2.0 * (o[2] * o[2] + o[3] * o[3]);
+  }
+  Q[s] = 2.0 * (1.0 - (1.0 / n) * tot);
+}
+
+static int mw_accumulate(const c128* d_states, long long S, int n, double* d_acc, cudaStream_t st) {
+  const int chunk_log2 = std::min(n, 14);
+  const long long grid = S << (n - chunk_log2);
+  if (grid > 0x7fffffffLL) PQC_FAIL(-1, "Meyer-Wallach grid too large; split the batch");
+  if (n > chunk_log2) PQC_CUDA(cudaMemsetAsync(d_acc, 0, sizeof(double) * 4 * n * S, st));
+  k_mw_accumulate<<<(unsigned)grid, 256, 0, st>>>(d_states, n, chunk_log2, d_acc);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pqc_meyer_wallach(const pqc_c128* d_states, int64_t S, int n, double* d_Q,
+                                 void* stream) {
+  if (S <= 0) return 0;
+  if (n < 1 || n > PQC_MAX_QUBITS) PQC_FAIL(-1, "bad qubit count");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* acc = nullptr;
+  PQC_CUDA(cudaMallocAsync(&acc, sizeof(double) * 4 * n * S, st));
+  int rc = mw_accumulate((const c128*)d_states, S, n, acc, st);
+  if (rc == 0) {
+    k_mw_finalize<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(acc, S, n, d_Q);
+    if (cudaGetLastError() != cudaSuccess) rc = -2;
+  }
+  cudaFreeAsync(acc, st);
+  return rc;
+}
+
+__global__ void k_rho_from_acc(const double* __restrict__ acc, int n, int qubit,
+                               c128* __restrict__ rho) {
+  const double* o = acc + qubit * 4;
+  rho[0] = make_double2(o[0], 0.0);
+  rho[1] = make_double2(o[2], o[3]);
+  rho[2] = make_double2(o[2], -o[3]);
+  rho[3] = make_double2(o[1], 0.0);
+}
+
+extern "C" int pqc_ptrace_1q(const pqc_c128* d_state, int n, int qubit, pqc_c128* d_rho,
+                             void* stream) {
+  if (qubit < 0 || qubit >= n) PQC_FAIL(-1, "ptrace qubit out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* acc = nullptr;
+  PQC_CUDA(cudaMallocAsync(&acc, sizeof(double) * 4 * n, st));
+  int rc = mw_accumulate((const c128*)d_state, 1, n, acc, st);
+  if (rc == 0) {
+    k_rho_from_acc<<<1, 1, 0, st>>>(acc, n, qubit, (c128*)d_rho);
+    if (cudaGetLastError() != cudaSuccess) rc = -2;
+  }
+  cudaFreeAsync(acc, st);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------
+// Pauli sums: H|psi> and <psi|H|psi>  (circuit.py:28-31,132-137; measure.py:468; and the
+// generator sums of gates.py:454-457 used for derivative states).
+// (P psi)[y] = i^{ny} (-1)^{popcount((y^xm) & zm)} psi[y ^ xm]
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ c128 pauli_sum_at(const c128* __restrict__ psi, long long y,
+                                             const GenTerm* __restrict__ terms, int nterms) {
+  double re = 0.0, im = 0.0;
+  for (int t = 0; t < nterms; ++t) {
+    const GenTerm g = terms[t];
+    const long long x = y ^ (long long)g.xmask;
+    const c128 v = psi[x];
+    int ph = __popc(g.xmask & g.zmask) + 2 * __popc((uint32_t)x & g.zmask);   // power of i
+    ph &= 3;
+    c128 w;
+    if (ph == 0) w = v;
+    else if (ph == 1) w = make_double2(-v.y, v.x);
+    else if (ph == 2) w = make_double2(-v.x, -v.y);
+    else w = make_double2(v.y, -v.x);
+    re += g.re * w.x - g.im * w.y;
+    im += g.re * w.y + g.im * w.x;
+  }
+  return make_double2(re, im);
+}
+
+// dst item i <- sum_t coef_t P_t src item i.  Items are (sample, slot) pairs addressed
+// like the tile kernel: offset = (sample*slots_total + slot) << n.
+__global__ void __launch_bounds__(256) k_pauli_apply(const c128* __restrict__ src, c128* __restrict__ dst,
+                                                     int n, long long n_samples, int slots_total,
+                                                     int src_slot, int dst_slot,
+                                                     const GenTerm* __restrict__ terms, int nterms) {
+  const long long D = 1ll << n;
+  const long long total = n_samples * D;
+  for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < total;
+       g += (long long)gridDim.x * 256) {
+    const long long s = g >> n, y = g & (D - 1);
+    const c128* psi = src + ((s * slots_total + src_slot) << n);
+    dst[((s * slots_total + dst_slot) << n) + y] = pauli_sum_at(psi, y, terms, nterms);
+  }
+}
+
+int pqc_pauli_apply_slots(const c128* src, c128* dst, int n, long long S, int slots_total,
+                          int src_slot, int dst_slot, const GenTerm* d_terms, int nterms,
+                          cudaStream_t st) {
+  if (S <= 0) return 0;
+  const long long total = S << n;
+  const long long grid = std::min<long long>((total + 255) / 256, 148 * 32);
+  k_pauli_apply<<<(unsigned)grid, 256, 0, st>>>(src, dst, n, S, slots_total, src_slot, dst_slot,
+                                                d_terms, nterms);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) k_pauli_expect(const c128* __restrict__ states, int n,
+                                                      const GenTerm* __restrict__ terms, int nterms,
+                                                      c128* __restrict__ out) {
+  __shared__ double red[32];
+  const long long D = 1ll << n;
+  const c128* psi = states + (long long)blockIdx.x * D;
+  double re = 0.0, im = 0.0;
+  for (long long y = threadIdx.x; y < D; y += 256) {
+    const c128 h = pauli_sum_at(psi, y, terms, nterms);
+    const c128 a = psi[y];
+    re += a.x * h.x + a.y * h.y;
+    im += a.x * h.y - a.y * h.x;
+  }
+  re = block_sum<256>(re, red);
+  im = block_sum<256>(im, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = make_double2(re, im);
+}
+
+static int upload_terms(const pqc_pauli_term* h_terms, int n_terms, GenTerm** d_terms,
+                        cudaStream_t st) {
+  std::vector<GenTerm> t(n_terms);
+  for (int i = 0; i < n_terms; ++i) {
+    t[i].xmask = h_terms[i].xmask;
+    t[i].zmask = h_terms[i].zmask;
+    t[i].re = h_terms[i].re;
+    t[i].im = h_terms[i].im;
+  }
+  PQC_CUDA(cudaMallocAsync(d_terms, sizeof(GenTerm) * std::max(1, n_terms), st));
+  // pageable source: the copy is staged before the call returns, so `t` may die here
+  PQC_CUDA(cudaMemcpyAsync(*d_terms, t.data(), sizeof(GenTerm) * n_terms, cudaMemcpyHostToDevice,
+                           st));
+  return 0;
+}
+
+extern "C" int pqc_pauli_expect_batch(const pqc_c128* d_states, int64_t S, int n, int n_terms,
+                                      const pqc_pauli_term* h_terms, pqc_c128* d_out,
+                                      void* stream) {
+  if (S <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  GenTerm* d_terms = nullptr;
+  int rc = upload_terms(h_terms, n_terms, &d_terms, st);
+  if (rc) return rc;
+  k_pauli_expect<<<(unsigned)S, 256, 0, st>>>((const c128*)d_states, n, d_terms, n_terms,
+                                              (c128*)d_out);
+  if (cudaGetLastError() != cudaSuccess) rc = -2;
+  cudaFreeAsync(d_terms, st);
+  return rc;
+}
+
+extern "C" int pqc_pauli_apply_batch(const pqc_c128* d_states, int64_t S, int n, int n_terms,
+                                     const pqc_pauli_term* h_terms, pqc_c128* d_out,
+                                     void* stream) {
+  if (S <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  GenTerm* d_terms = nullptr;
+  int rc = upload_terms(h_terms, n_terms, &d_terms, st);
+  if (rc) return rc;
+  rc = pqc_pauli_apply_slots((const c128*)d_states, (c128*)d_out, n, S, 1, 0, 0, d_terms,
+                             n_terms, st);
+  cudaFreeAsync(d_terms, st);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------
+// np.histogram(F, bins=B, range=(0,1)) binning (measure.py:153-155), restated exactly:
+// idx = int(F*B); idx==B -> B-1; then the two edge corrections numpy applies against
+// edges = linspace(0,1,B+1) (edge_i = i*(1/B), edge_B = 1); values outside [0,1] dropped.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ long long np_hist_bin(double f, long long B, double step) {
+  if (!(f >= 0.0) || !(f <= 1.0)) return -1;
+  long long idx = (long long)(f * (double)B);
+  if (idx == B) idx = B - 1;
+  const double lo = __dmul_rn((double)idx, step);
+  if (f < lo) {
+    idx -= 1;
+  } else if (idx != B - 1) {
+    const double hi = (idx + 1 == B) ? 1.0 : __dmul_rn((double)(idx + 1), step);
+    if (f >= hi) idx += 1;
+  }
+  return idx;
+}
+
+__global__ void k_hist_f64(const double* __restrict__ F, long long count, long long B,
+                           double step, unsigned long long* __restrict__ hist) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = np_hist_bin(F[i], B, step);
+    if (b >= 0) atomicAdd(hist + b, 1ull);
+  }
+}
+
+extern "C" int pqc_hist_f64(const double* d_F, int64_t count, int64_t bins, long long* d_hist,
+                            void* stream) {
+  if (bins <= 0) PQC_FAIL(-1, "`bins` must be positive, when an integer");
+  if (count <= 0) return 0;
+  const long long grid = std::min<long long>((count + 255) / 256, 148 * 16);
+  k_hist_f64<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      d_F, count, bins, 1.0 / (double)bins, (unsigned long long*)d_hist);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// pairwise fidelities + histogram (measure.py:123-159).  v0: FP64 CUDA-core tiled
+// ZHERK-style kernel, 64x64 pair tile per CTA, 4x4 complex accumulators per thread,
+// K staged through shared memory 16 amplitudes at a time.
+// ---------------------------------------------------------------------------------
+#define FT 64
+#define FK 16
+__global__ void __launch_bounds__(256) k_fidelity(const c128* __restrict__ A, long long SA,
+                                                  const c128* __restrict__ Bm, long long SB,
+                                                  int n, int triangular, long long bins,
+                                                  double step, unsigned long long* __restrict__ hist,
+                                                  double* __restrict__ Fout) {
+  // block -> (bi, bj) tile coordinates
+  long long bi, bj;
+  const long long nbj = (SB + FT - 1) / FT;
+  if (triangular) {
+    // linear index over the upper triangle of the tile grid (bj >= bi)
+    long long t = blockIdx.x;
+    const long long nb = nbj;
+    // row bi has (nb - bi) tiles; solve by search (few iterations in double then fix up)
+    double disc = (2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t;
+    bi = (long long)(((2.0 * nb + 1.0) - sqrt(disc)) * 0.5);
+    if (bi < 0) bi = 0;
+    while (bi > 0 && bi * nb - bi * (bi - 1) / 2 > t) --bi;
+    while ((bi + 1) * nb - (bi + 1) * bi / 2 <= t) ++bi;
+    bj = bi + (t - (bi * nb - bi * (bi - 1) / 2));
+  } else {
+    bi = blockIdx.x / nbj;
+    bj = blockIdx.x % nbj;
+  }
+  __shared__ c128 sa[FK][FT + 1];
+  __shared__ c128 sb[FK][FT + 1];
+  const long long D = 1ll << n;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double are[4][4], aim[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) are[r][c] = aim[r][c] = 0.0;
+
+  for (long long k0 = 0; k0 < D; k0 += FK) {
+    // each thread loads 4 elements of each operand tile: FT rows x FK cols = 1024 elements
+    for (int e = threadIdx.x; e < FT * FK; e += 256) {
+      const int r = e / FK, kk = e % FK;
+      const long long ia = bi * FT + r, ib = bj * FT + r;
+      const long long k = k0 + kk;
+      c128 va = make_double2(0, 0), vb = make_double2(0, 0);
+      if (k < D) {
+        if (ia < SA) va = A[ia * D + k];
+        if (ib < SB) vb = Bm[ib * D + k];
+      }
+      sa[kk][r] = va;
+      sb[kk][r] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < FK; ++kk) {
+      c128 ra[4], rb[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) ra[r] = sa[kk][ty * 4 + r];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rb[c] = sb[kk][tx * 4 + c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          // conj(a) * b
+          are[r][c] += ra[r].x * rb[c].x + ra[r].y * rb[c].y;
+          aim[r][c] += ra[r].x * rb[c].y - ra[r].y * rb[c].x;
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const long long i = bi * FT + ty * 4 + r, j = bj * FT + tx * 4 + c;
+      if (i >= SA || j >= SB) continue;
+      if (triangular && j <= i) continue;
+      const double re = are[r][c], im = aim[r][c];
+      const double mag = hypot(re, im);               // np.abs(z) ** 2 (measure.py:135)
+      const double f = mag * mag;
+      if (hist) {
+        const long long b = np_hist_bin(f, bins, step);
+        if (b >= 0) atomicAdd(hist + b, 1ull);
+      }
+      if (Fout) {
+        const long long idx = triangular ? (i * (2 * SA - i - 1) / 2 + (j - i - 1)) : (i * SB + j);
+        Fout[idx] = f;
+      }
+    }
+}
+
+extern "C" int pqc_fidelity_hist(const pqc_c128* d_A, int64_t n_a, const pqc_c128* d_B,
+                                 int64_t n_b, int n, int triangular, int64_t bins,
+                                 long long* d_hist, double* d_F, void* stream) {
+  if (n_a <= 0 || n_b <= 0) return 0;
+  if (d_hist && bins <= 0) PQC_FAIL(-1, "`bins` must be positive, when an integer");
+  if (triangular && (d_A != d_B || n_a != n_b))
+    PQC_FAIL(-1, "triangular mode needs the same block on both sides");
+  const long long nbi = (n_a + FT - 1) / FT, nbj = (n_b + FT - 1) / FT;
+  const long long grid = triangular ? nbi * (nbi + 1) / 2 : nbi * nbj;
+  if (grid > 0x7fffffffLL) PQC_FAIL(-1, "fidelity grid too large; split the block");
+  k_fidelity<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      (const c128*)d_A, n_a, (const c128*)d_B, n_b, n, triangular, bins,
+      bins > 0 ? 1.0 / (double)bins : 0.0, (unsigned long long*)d_hist, d_F);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Measurements.expr on histogram counts (measure.py:161-180):
+//   P_pqc = counts / sum(counts); F_mid = bin midpoints; haar = (N-1)(1-F)^(N-2);
+//   P_haar = haar / sum(haar); KL = sum kl_div(P_pqc, P_haar)   (scipy.special.kl_div)
+// scratch[0] = sum counts, scratch[1] = sum haar, scratch[2] = KL
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double bin_mid(long long i, long long B, double step) {
+  const double lo = __dmul_rn((double)i, step);
+  const double hi = (i + 1 == B) ? 1.0 : __dmul_rn((double)(i + 1), step);
+  return (lo + hi) / 2.0;
+}
+
+__global__ void __launch_bounds__(256) k_kl_sums(const long long* __restrict__ hist, long long B,
+                                                 double step, double N, double* __restrict__ scratch) {
+  __shared__ double red[32];
+  double sc = 0.0, sh = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < B; i += (long long)gridDim.x * 256) {
+    sc += (double)hist[i];
+    sh += (N - 1.0) * pow(1.0 - bin_mid(i, B, step), N - 2.0);
+  }
+  sc = block_sum<256>(sc, red);
+  sh = block_sum<256>(sh, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(scratch + 0, sc);
+    atomicAdd(scratch + 1, sh);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_kl_terms(const long long* __restrict__ hist, long long B,
+                                                  double step, double N, double* __restrict__ scratch) {
+  __shared__ double red[32];
+  const double tc = scratch[0], th = scratch[1];
+  double kl = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < B; i += (long long)gridDim.x * 256) {
+    const double x = (double)hist[i] / tc;
+    const double y = (N - 1.0) * pow(1.0 - bin_mid(i, B, step), N - 2.0) / th;
+    double t;
+    if (x > 0.0 && y > 0.0) t = x * log(x / y) - x + y;
+    else if (x == 0.0 && y >= 0.0) t = y;
+    else t = INFINITY;
+    kl += t;
+  }
+  kl = block_sum<256>(kl, red);
+  if (threadIdx.x == 0) atomicAdd(scratch + 2, kl);
+}
+
+__global__ void k_copy1(const double* src, double* dst) { *dst = *src; }
+
+extern "C" int pqc_kl_haar(const long long* d_hist, int64_t bins, double N, double* d_out,
+                           double* d_scratch, void* stream) {
+  if (bins <= 0) PQC_FAIL(-1, "`bins` must be positive, when an integer");
+  cudaStream_t st = (cudaStream_t)stream;
+  PQC_CUDA(cudaMemsetAsync(d_scratch, 0, 4 * sizeof(double), st));
+  const long long grid = std::min<long long>((bins + 255) / 256, 148 * 8);
+  const double step = 1.0 / (double)bins;
+  k_kl_sums<<<(unsigned)grid, 256, 0, st>>>(d_hist, bins, step, N, d_scratch);
+  k_kl_terms<<<(unsigned)grid, 256, 0, st>>>(d_hist, bins, step, N, d_scratch);
+  k_copy1<<<1, 1, 0, st>>>(d_scratch + 2, d_out);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Renyi / GKP magic (measure.py:318-368).  For X-mask k the reference's column M[:,k] is
+// the Walsh-Hadamard transform over j of v_j = conj(c_j) c_{j^k}.  Because
+// v_{j^k} = conj(v_j), WHT(Re v)_i vanishes when i.k is odd and WHT(Im v)_i when it is
+// even, so |M[i,k]| = |WHT(Re v + Im v)_i|: one REAL in-shared-memory FWHT per mask
+// instead of the reference's 2^n x 2^n x 2^n complex GEMM.
+// One CTA per (sample, slice of masks); state cached in shared memory.
+// out[a][s] accumulates sum_{i,k} |W|^{2 alpha_a}; finalised by k_magic_finalize.
+// ---------------------------------------------------------------------------------
+#define MAGIC_MAX_ALPHA 4
+struct MagicArgs {
+  const c128* states;
+  int n;
+  int masks_per_cta;
+  int n_alpha;
+  double alpha[MAGIC_MAX_ALPHA];
+  double* sums;      // [n_alpha][S]
+  long long S;
+};
+
+__global__ void __launch_bounds__(256) k_magic(const MagicArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int n = a.n;
+  const uint32_t D = 1u << n;
+  double* cr = reinterpret_cast<double*>(smraw);   // [D] real parts
+  double* ci = cr + D;                             // [D] imaginary parts
+  double* u = ci + D;                              // [D] FWHT buffer
+  __shared__ double red[32];
+  const int slices = (int)((D + a.masks_per_cta - 1) / a.masks_per_cta);
+  const long long s = blockIdx.x / slices;
+  const int slice = blockIdx.x % slices;
+  const c128* psi = a.states + s * (long long)D;
+  for (uint32_t i = threadIdx.x; i < D; i += 256) {
+    const c128 v = psi[i];
+    cr[i] = v.x;
+    ci[i] = v.y;
+  }
+  __syncthreads();
+  double acc[MAGIC_MAX_ALPHA];
+#pragma unroll
+  for (int q = 0; q < MAGIC_MAX_ALPHA; ++q) acc[q] = 0.0;
+  const uint32_t k_begin = (uint32_t)slice * a.masks_per_cta;
+  const uint32_t k_end = min(D, k_begin + (uint32_t)a.masks_per_cta);
+  for (uint32_t k = k_begin; k < k_end; ++k) {
+    for (uint32_t j = threadIdx.x; j < D; j += 256) {
+      const double xr = cr[j], xi = ci[j], yr = cr[j ^ k], yi = ci[j ^ k];
+      // v = conj(c_j) c_{j^k};  u = Re v + Im v
+      u[j] = (xr * yr + xi * yi) + (xr * yi - xi * yr);
+    }
+    __syncthreads();
+    for (uint32_t h = 1; h < D; h <<= 1) {
+      for (uint32_t p = threadIdx.x; p < (D >> 1); p += 256) {
+        const uint32_t i0 = ((p & ~(h - 1)) << 1) | (p & (h - 1));
+        const double x = u[i0], y = u[i0 + h];
+        u[i0] = x + y;
+        u[i0 + h] = x - y;
+      }
+      __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < D; i += 256) {
+      const double w = fabs(u[i]);
+#pragma unroll
+      for (int q = 0; q < MAGIC_MAX_ALPHA; ++q) {
+        if (q < a.n_alpha) {
+          const double al = a.alpha[q];
+          double t;
+          if (al == 2.0) { const double w2 = w * w; t = w2 * w2; }
+          else if (al == 0.5) t = w;
+          else if (al == 1.0) t = w * w;
+          else t = (w == 0.0) ? 0.0 : pow(w, 2.0 * al);
+          acc[q] += t;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int q = 0; q < a.n_alpha; ++q) {
+    const double t = block_sum<256>(acc[q], red);
+    if (threadIdx.x == 0) atomicAdd(a.sums + (long long)q * a.S + s, t);
+  }
+}
+
+__global__ void k_magic_finalize(double* __restrict__ out, long long S, int n, int n_alpha,
+                                 MagicArgs a) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S * n_alpha) return;
+  const int q = (int)(e / S);
+  const double al = a.alpha[q];
+  // sum |2^{-n/2} W|^{2 alpha} = 2^{-n alpha} sum |W|^{2 alpha}
+  const double tot = out[e] * exp2(-(double)n * al);
+  out[e] = 1.0 / (1.0 - al) * log(tot) - (double)n * 0.69314718055994530942;
+}
+
+extern "C" int pqc_magic_batch(const pqc_c128* d_states, int64_t S, int n, int n_alpha,
+                               const double* h_alphas, double* d_out, void* stream) {
+  if (S <= 0 || n_alpha <= 0) return 0;
+  if (n_alpha > MAGIC_MAX_ALPHA) PQC_FAIL(-1, "at most 4 alphas per call");
+  if (n < 1 || n > 13) PQC_FAIL(-1, "magic kernel keeps the state in shared memory: n <= 13");
+  cudaStream_t st = (cudaStream_t)stream;
+  MagicArgs a;
+  a.states = (const c128*)d_states;
+  a.n = n;
+  a.n_alpha = n_alpha;
+  for (int q = 0; q < n_alpha; ++q) {
+    if (h_alphas[q] == 1.0) PQC_FAIL(-1, "alpha = 1 is singular (1/(1-alpha))");
+    a.alpha[q] = h_alphas[q];
+  }
+  a.sums = d_out;
+  a.S = S;
+  const long long D = 1ll << n;
+  // enough CTAs to fill the machine: >= 4 * 148 CTAs when the batch is small
+  long long slices = std::max<long long>(1, std::min<long long>(D, (148 * 4 + S - 1) / S));
+  a.masks_per_cta = (int)((D + slices - 1) / slices);
+  slices = (D + a.masks_per_cta - 1) / a.masks_per_cta;
+  const size_t smem = 3 * D * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PQC_CUDA(cudaFuncSetAttribute(k_magic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  if (S * slices > 0x7fffffffLL) PQC_FAIL(-1, "magic grid too large; split the batch");
+  PQC_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * S * n_alpha, st));
+  k_magic<<<(unsigned)(S * slices), 256, smem, st>>>(a);
+  PQC_LAUNCH_CHECK();
+  k_magic_finalize<<<(unsigned)((S * n_alpha + 127) / 128), 128, 0, st>>>(d_out, S, n, n_alpha, a);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// get_QFI (measure.py:33-71) from explicit states + derivative states.
+// One CTA per (sample, p, q>=p) would be wasteful; use one CTA per (sample, p) row and
+// loop q, after first computing s_p = <psi|d_p>.  Deterministic summation order.
+// G scratch: [S][P+1][P] complex: row 0 = s_q, row 1+p = <d_p|d_q>.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gram_rows(const c128* __restrict__ states,
+                                                   const c128* __restrict__ grads, int n, int P,
+                                                   c128* __restrict__ G) {
+  __shared__ double red[32];
+  const long long D = 1ll << n;
+  const long long s = blockIdx.x / (P + 1);
+  const int row = blockIdx.x % (P + 1);
+  const c128* a = row == 0 ? states + s * D : grads + (s * P + (row - 1)) * D;
+  const int q0 = row == 0 ? 0 : row - 1;
+  for (int q = q0; q < P; ++q) {
+    const c128* b = grads + (s * P + q) * D;
+    double re = 0.0, im = 0.0;
+    for (long long i = threadIdx.x; i < D; i += 256) {
+      const c128 x = a[i], y = b[i];
+      re += x.x * y.x + x.y * y.y;
+      im += x.x * y.y - x.y * y.x;
+    }
+    re = block_sum<256>(re, red);
+    im = block_sum<256>(im, red);
+    if (threadIdx.x == 0) G[(s * (P + 1) + row) * P + q] = make_double2(re, im);
+  }
+}
+
+// F_pq = 4 Re(G_pq - conj(s_p) s_q), p <= q, mirrored (measure.py:55-70)
+__global__ void k_qfim_finalize(const c128* __restrict__ G, long long S, int P,
+                                double* __restrict__ F) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S * P * P) return;
+  const long long s = e / ((long long)P * P);
+  const int r = (int)((e / P) % P), c = (int)(e % P);
+  const int p = r < c ? r : c, q = r < c ? c : r;
+  const c128* g = G + s * (long long)(P + 1) * P;
+  const c128 sp = g[p], sq = g[q], d = g[(long long)(1 + p) * P + q];
+  // np.conjugate(s_p) * s_q, real part
+  const double rhs = sp.x * sq.x + sp.y * sq.y;
+  F[e] = 4.0 * (d.x - rhs);
+}
+
+int pqc_qfim_finalize(const c128* d_G, long long S, int P, double* d_F, cudaStream_t st) {
+  const long long tot = S * P * P;
+  if (tot <= 0) return 0;
+  k_qfim_finalize<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_G, S, P, d_F);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pqc_qfim_from_grads(const pqc_c128* d_states, const pqc_c128* d_grads, int n,
+                                   int P, int64_t S, double* d_qfim, void* stream) {
+  if (S <= 0 || P <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  c128* G = nullptr;
+  PQC_CUDA(cudaMallocAsync(&G, sizeof(c128) * S * (P + 1) * P, st));
+  int rc = 0;
+  if (S * (P + 1) > 0x7fffffffLL) {
+    pqc_set_error("qfim grid too large");
+    rc = -1;
+  } else {
+    k_gram_rows<<<(unsigned)(S * (P + 1)), 256, 0, st>>>((const c128*)d_states,
+                                                        (const c128*)d_grads, n, P, G);
+    if (cudaGetLastError() != cudaSuccess) rc = -2;
+    if (rc == 0) rc = pqc_qfim_finalize(G, S, P, d_qfim, st);
+  }
+  cudaFreeAsync(G, st);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------
+// eigenvalues of S symmetric PxP matrices (scipy.linalg.eigh, measure.py:73-75,84):
+// parallel cyclic Jacobi in shared memory, one CTA per matrix, round-robin pairing so
+// P/2 disjoint rotations run concurrently; ascending output.
+// ---------------------------------------------------------------------------------
+template <bool WITH_V>
+__global__ void __launch_bounds__(128) k_jacobi_eigvals(const double* __restrict__ mats, int P,
+                                                        int Pp, double* __restrict__ eig,
+                                                        double* __restrict__ vecs) {
+  extern __shared__ double smd[];
+  double* A = smd;                        // [Pp][Pp+1]
+  const int ld = Pp + 1;
+  double* cs = A + (size_t)Pp * ld;       // [Pp/2][2]
+  int* pr = reinterpret_cast<int*>(cs + Pp);   // [Pp] current pairing
+  double* V = reinterpret_cast<double*>(pr + Pp + (Pp & 1));   // [Pp][Pp+1] accumulated rotations
+  __shared__ double red[32];
+  __shared__ double s_off, s_norm;
+  double prev_off = 1e300;
+  const double* M = mats + (long long)blockIdx.x * P * P;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < Pp * Pp; e += 128) {
+    const int r = e / Pp, c = e % Pp;
+    double v = 0.0;
+    if (r < P && c < P) v = 0.5 * (M[(long long)r * P + c] + M[(long long)c * P + r]);
+    else if (r == c) v = 1e300;            // padding: decoupled sentinel, dropped at the end
+    A[r * ld + c] = v;
+  }
+  for (int i = tid; i < Pp; i += 128) pr[i] = i;
+  if (WITH_V)
+    for (int e = tid; e < Pp * Pp; e += 128) V[(e / Pp) * ld + (e % Pp)] = (e / Pp == e % Pp) ? 1.0 : 0.0;
+  __syncthreads();
+  const int half = Pp / 2;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    // convergence test: off-diagonal Frobenius norm vs diagonal
+    double off = 0.0, nrm = 0.0;
+    for (int e = tid; e < P * P; e += 128) {
+      const int r = e / P, c = e % P;
+      const double v = A[r * ld + c];
+      if (r == c) nrm += v * v; else off += v * v;
+    }
+    off = block_sum<128>(off, red);
+    nrm = block_sum<128>(nrm, red);
+    if (tid == 0) { s_off = off; s_norm = nrm; }
+    __syncthreads();
+    // stop at the rounding floor: either negligible, or small and no longer shrinking
+    const double cur_off = s_off;
+    if (cur_off == 0.0 || cur_off <= 1e-33 * s_norm ||
+        (cur_off <= 1e-26 * s_norm && cur_off >= 0.25 * prev_off))
+      break;
+    prev_off = cur_off;
+    for (int round = 0; round < Pp - 1; ++round) {
+      // rotation angles for the `half` disjoint pairs (p = pr[i], q = pr[Pp-1-i])
+      for (int i = tid; i < half; i += 128) {
+        int p = pr[i], q = pr[Pp - 1 - i];
+        if (p > q) { const int t = p; p = q; q = t; }
+        const double apq = A[p * ld + q];
+        double c = 1.0, s = 0.0;
+        if (apq != 0.0 && p < P && q < P) {
+          const double tau = (A[q * ld + q] - A[p * ld + p]) / (2.0 * apq);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + t * t);
+          s = t * c;
+        }
+        cs[2 * i] = c;
+        cs[2 * i + 1] = s;
+      }
+      __syncthreads();
+      // rows: A <- J^T A
+      for (int e = tid; e < half * Pp; e += 128) {
+        const int i = e / Pp, col = e % Pp;
+        int p = pr[i], q = pr[Pp - 1 - i];
+        if (p > q) { const int t = p; p = q; q = t; }
+        const double c = cs[2 * i], s = cs[2 * i + 1];
+        const double x = A[p * ld + col], y = A[q * ld + col];
+        A[p * ld + col] = c * x - s * y;
+        A[q * ld + col] = s * x + c * y;
+      }
+      __syncthreads();
+      // columns: A <- A J
+      for (int e = tid; e < half * Pp; e += 128) {
+        const int i = e / Pp, row = e % Pp;
+        int p = pr[i], q = pr[Pp - 1 - i];
+        if (p > q) { const int t = p; p = q; q = t; }
+        const double c = cs[2 * i], s = cs[2 * i + 1];
+        const double x = A[row * ld + p], y = A[row * ld + q];
+        A[row * ld + p] = c * x - s * y;
+        A[row * ld + q] = s * x + c * y;
+        if (WITH_V) {
+          const double vx = V[row * ld + p], vy = V[row * ld + q];
+          V[row * ld + p] = c * vx - s * vy;
+          V[row * ld + q] = s * vx + c * vy;
+        }
+      }
+      __syncthreads();
+      // round-robin tournament: keep pr[0], rotate the rest
+      if (tid == 0) {
+        const int last = pr[Pp - 1];
+        for (int i = Pp - 1; i > 1; --i) pr[i] = pr[i - 1];
+        pr[1] = last;
+      }
+      __syncthreads();
+    }
+  }
+  // rank sort of the P real diagonal entries (ties broken by index)
+  for (int i = tid; i < P; i += 128) {
+    const double v = A[i * ld + i];
+    int rank = 0;
+    for (int j = 0; j < P; ++j) {
+      const double w = A[j * ld + j];
+      rank += (w < v) || (w == v && j < i);
+    }
+    eig[(long long)blockIdx.x * P + rank] = v;
+    if (WITH_V)     // column `rank` of the output = eigenvector of the rank-th eigenvalue
+      for (int r = 0; r < P; ++r)
+        vecs[((long long)blockIdx.x * P + r) * P + rank] = V[r * ld + i];
+  }
+}
+
+static int eigh_launch(const double* d_mats, int64_t n_mats, int dim, double* d_eig,
+                       double* d_vecs, cudaStream_t st) {
+  if (n_mats <= 0 || dim <= 0) return 0;
+  const int Pp = (dim + 1) & ~1;
+  size_t smem = ((size_t)Pp * (Pp + 1) + Pp) * sizeof(double) + (Pp + (Pp & 1)) * sizeof(int);
+  if (d_vecs) smem += (size_t)Pp * (Pp + 1) * sizeof(double);
+  if (smem > 200 * 1024)
+    PQC_FAIL(-1, "eigh: matrix too large for the shared-memory Jacobi (dim <= 158, or 110 with vectors)");
+  if (n_mats > 0x7fffffffLL) PQC_FAIL(-1, "too many matrices");
+  static bool attr_set = false;
+  if (!attr_set) {
+    PQC_CUDA(cudaFuncSetAttribute(k_jacobi_eigvals<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PQC_CUDA(cudaFuncSetAttribute(k_jacobi_eigvals<true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  if (d_vecs)
+    k_jacobi_eigvals<true><<<(unsigned)n_mats, 128, smem, st>>>(d_mats, dim, Pp, d_eig, d_vecs);
+  else
+    k_jacobi_eigvals<false><<<(unsigned)n_mats, 128, smem, st>>>(d_mats, dim, Pp, d_eig, nullptr);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pqc_eigvalsh_batch(const double* d_mats, int64_t n_mats, int dim, double* d_eig,
+                                  void* stream) {
+  return eigh_launch(d_mats, n_mats, dim, d_eig, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int pqc_eigh_batch(const double* d_mats, int64_t n_mats, int dim, double* d_eig,
+                              double* d_vecs, void* stream) {
+  return eigh_launch(d_mats, n_mats, dim, d_eig, d_vecs, (cudaStream_t)stream);
+}
+
+__global__ void k_count_greater(const double* __restrict__ v, long long rows, int cols,
+                                double cutoff, int* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  int c = 0;
+  for (int j = 0; j < cols; ++j) c += v[r * cols + j] > cutoff;
+  out[r] = c;
+}
+
+extern "C" int pqc_count_greater(const double* d_vals, int64_t rows, int cols, double cutoff,
+                                 int32_t* d_counts, void* stream) {
+  if (rows <= 0) return 0;
+  k_count_greater<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      d_vals, rows, cols, cutoff, d_counts);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,311 @@
+"""GPU parity: the CUDA engine (through the reference-facing API and the C ABI) against
+the reference-generated goldens and the numpy oracle.  Tolerances are BASELINE.json's:
+amplitudes / fidelities 1e-10 absolute, QFIM / magic 1e-8 relative, KL 1e-6."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import pyramaterised_b200 as pyqc
+from helpers import oracle_case, specs_from_circuit
+from oracle import pqc_oracle as orc
+from pyramaterised_b200 import engine
+
+pytestmark = pytest.mark.gpu
+
+ALL = sorted(cases.CASES)
+ATOL = 1e-10
+RTOL = 1e-8
+GRAD_OK = [c for c in ALL if cases.CASES[c][2] > 0 and "fsim" not in c]
+
+
+def reseed():
+    pyqc.gates.rng.bit_generator.state = np.random.default_rng(1).bit_generator.state
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(1.0, np.abs(np.asarray(b)).max())
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_states_and_measures_vs_golden(golden, name):
+    qc = cases.CASES[name][0](pyqc)
+    ang = golden[f"{name}/angles"]
+    m = pyqc.measure.Measurements(qc)
+    st = qc.run_batch(ang)
+    assert np.abs(st.cpu().numpy() - golden[f"{name}/states"]).max() < ATOL
+    # single-sample API path (PQC.run / cost / single_Q), as the reference is called
+    s0 = qc.run(list(ang[0]))
+    assert np.abs(s0.numpy() - golden[f"{name}/states"][0]).max() < ATOL
+    assert abs(qc.cost(list(ang[1])) - golden[f"{name}/cost"][1]) < ATOL
+    assert abs(m.single_Q(s0, qc.n_qubits) - golden[f"{name}/Q"][0]) < ATOL
+    assert np.abs(engine.meyer_wallach(st).cpu().numpy() - golden[f"{name}/Q"]).max() < ATOL
+    _, F = engine.fidelity_hist(st, want_F=True)
+    assert np.abs(F.cpu().numpy() - golden[f"{name}/F"]).max() < ATOL
+    if cases.CASES[name][3]:
+        mg = engine.magic(st, (2.0, 0.5)).cpu().numpy()
+        assert rel(mg[0], golden[f"{name}/renyi2"]) < RTOL
+        assert rel(mg[1] / (2 * np.log(2)), golden[f"{name}/gkp"]) < RTOL
+        assert abs(m.renyi_entropy_fast(s0) - golden[f"{name}/renyi2"][0]) < RTOL
+        assert abs(m.gkp_fast(s0) - golden[f"{name}/gkp"][0]) < RTOL
+
+
+@pytest.mark.parametrize("name", GRAD_OK)
+def test_gradients_qfi_eqd_vs_golden(golden, name):
+    qc = cases.CASES[name][0](pyqc)
+    G = cases.CASES[name][2]
+    m = pyqc.measure.Measurements(qc)
+    for s in range(G):
+        a = list(golden[f"{name}/angles"][s])
+        qc.update_state(a)
+        grads = qc.get_gradients()
+        got = np.stack([g.numpy() for g in grads])
+        assert np.abs(got - golden[f"{name}/grads"][s]).max() < ATOL
+        F = m.get_QFI(grad_list=grads)
+        ref = golden[f"{name}/qfi"][s]
+        assert rel(F, ref) < RTOL
+        assert m.get_effective_quantum_dimension(1e-12) == int(golden[f"{name}/eqd"][s])
+        assert abs(m.new_measure(F) - golden[f"{name}/new_measure"][s]) < 1e-8
+        gv = m.get_gradient_vector(a)
+        assert np.abs(np.array(gv) - golden[f"{name}/gradvec"][s]).max() < 1e-9
+    # fused batch path agrees with the reference-shaped path
+    Fb, eq = m.qfim_batch(golden[f"{name}/angles"][:G], cutoff_eigvals=1e-12)
+    assert rel(Fb.cpu().numpy(), golden[f"{name}/qfi"]) < RTOL
+    assert list(eq.cpu().numpy()) == list(golden[f"{name}/eqd"])
+
+
+@pytest.mark.parametrize("name", [c for c in ALL if "fsim" in c])
+def test_fsim_family_fails_loudly_on_derivatives(name):
+    qc = cases.CASES[name][0](pyqc)
+    with pytest.raises(NotImplementedError):
+        qc.get_gradients()
+
+
+def test_reference_known_answers(golden):
+    """Ports of /root/reference/tests.py hard asserts."""
+    from math import isclose
+    c = pyqc.PQC(1)
+    c.add_layer([pyqc.fixed_R_y(0, 1, np.pi / 2)])
+    out = c.run("random")
+    assert isclose(np.real(out[1][0][0]), 1 / np.sqrt(2))                 # tests.py:64-76
+    c = pyqc.PQC(1)
+    c.add_layer([pyqc.H(0, 1)], n=2)
+    assert c.run("random") == pyqc.qt.basis(2, 0)                          # tests.py:81-86
+    qg = cases.build_qg4(pyqc)
+    assert isclose(qg.cost(cases.QG_ANGLES), cases.QG_ENERGY, abs_tol=1e-5)   # tests.py:207-209
+    m = pyqc.measure.Measurements(qg)
+    assert m.get_effective_quantum_dimension(10 ** -12) == cases.QG_EQD       # tests.py:211-212
+    for N in (4, 6, 8):                                                       # tests.py:114-128
+        for P in (1, 2, 2 ** (N // 2)):
+            layers, th = pyqc.templates.NPQC_layers(P, N)
+            npqc = pyqc.PQC(N)
+            for l in layers:
+                npqc.add_layer(l)
+            npqc.state = npqc.run(angles=th)
+            Q = pyqc.measure.Measurements(npqc).get_QFI()
+            assert np.abs(Q - np.eye(len(Q))).max() < 1e-12
+    bell = pyqc.State(golden["bell/state"])                                   # tests.py:284-295
+
+    class Bell:
+        n_qubits = 2
+        state = bell
+
+        def run(self, a):
+            return bell
+
+    bm = pyqc.measure.Measurements(Bell())
+    assert isclose(bm.renyi_entropy_fast(bell), 0, abs_tol=1e-10)
+    assert isclose(bm.gkp_fast(bell), 0, abs_tol=1e-10)
+    assert isclose(bm.single_Q(bell, 2), 1, abs_tol=1e-10)
+
+
+def test_config1_expressibility_entanglement(golden):
+    """BASELINE config 1 through the reference API on the module RNG (quirk Q13)."""
+    qc = pyqc.templates.generate_circuit("NPQC", 4, 4)
+    m = pyqc.measure.Measurements(qc)
+    reseed()
+    e = m.expressibility(1000)
+    ent = m.entanglement(1000)
+    assert abs(e - float(golden["c1/expr"])) < 1e-6
+    assert np.abs(np.array(ent) - golden["c1/ent"]).max() < ATOL
+    reseed()
+    F = np.array(m._gen_f_samples(1000))
+    assert np.abs(F[:4096] - golden["c1/F_head"]).max() < ATOL
+    assert abs(F.sum() - float(golden["c1/F_sum"])) < 1e-8
+    # histogram kernel == np.histogram on the very same samples (bit exact integer counts)
+    bins = engine.n_bins(len(F))
+    assert bins == 3746
+    ours = engine.hist_f64(torch.as_tensor(F, device="cuda"), bins).cpu().numpy()
+    assert np.array_equal(ours, np.histogram(F, bins=bins, range=(0, 1))[0])
+    assert np.abs(ours - golden["c1/hist"]).sum() <= 4
+    for N, ref in zip((4, 8.5, 16, 64), golden["c1/expr_altN"]):
+        assert abs(m.expr(list(F), N) - ref) < 1e-6 * max(1, abs(ref))
+    prob, mid = m._gen_histo(list(F))
+    assert abs(prob.sum() - 1) < 1e-12 and len(mid) == bins
+
+
+def test_histogram_edge_semantics():
+    """np.histogram(range=(0,1)): right-closed last bin, out-of-range dropped."""
+    rng = np.random.default_rng(5)
+    for bins in (1, 7, 83, 3746, 100003):
+        edges = np.linspace(0, 1, bins + 1)
+        F = np.concatenate([rng.random(5000), edges[:: max(1, bins // 500)],
+                            np.nextafter(edges[1:-1:max(1, bins // 300)], 0),
+                            np.nextafter(edges[1:-1:max(1, bins // 300)], 1),
+                            [0.0, 1.0, 1.0 + 2e-16, -1e-18, 1.5, np.nan]])
+        ours = engine.hist_f64(torch.as_tensor(F, device="cuda"), bins).cpu().numpy()
+        assert np.array_equal(ours, np.histogram(F[~np.isnan(F)], bins=bins, range=(0, 1))[0]), bins
+    with pytest.raises(ValueError):
+        engine.hist_f64(torch.zeros(4, dtype=torch.float64, device="cuda"), 0)
+
+
+def test_efficient_measurements(golden):
+    qc = pyqc.templates.generate_circuit("generic_HE", 4, 2)
+    m = pyqc.measure.Measurements(qc)
+    reseed()
+    d = m.efficient_measurements(40)
+    assert abs(d["Expr"] - float(golden["effm/expr"])) < 1e-6
+    assert np.abs(np.array(d["Ent"]) - golden["effm/ent"]).max() < ATOL
+    assert np.abs(np.array(d["Magic"]) - golden["effm/magic"]).max() < 1e-8
+    assert np.abs(np.array(d["GKP"]) - golden["effm/gkp"]).max() < 1e-8
+    reseed()
+    f = m.efficient_measurements(40, full_data=True)
+    assert np.abs(np.array(f["Expr"]) - golden["effm/full_expr"]).max() < ATOL
+    assert np.abs(np.array(f["Ent"]) - golden["effm/full_ent"]).max() < ATOL
+    assert np.abs(np.array(f["Magic"]) - golden["effm/full_magic"]).max() < 1e-8
+    assert np.abs(np.array(f["GKP"]) - golden["effm/full_gkp"]).max() < 1e-8
+    import random
+    random.seed(7)
+    with pytest.raises(ValueError):
+        m.efficient_measurements(12, angles="clifford")       # zero bins, as the reference
+    random.seed(7)
+    c = m.efficient_measurements(20, angles="clifford")
+    assert np.abs(np.array(c["Magic"]) - golden["effm/cliff_magic"]).max() < 1e-8
+    assert np.abs(np.array(c["Ent"]) - golden["effm/cliff_ent"]).max() < ATOL
+    assert abs(c["Expr"] - float(golden["effm/cliff_expr"])) < 1e-6
+    qc7 = pyqc.templates.generate_circuit("generic_HE", 7, 1)
+    reseed()
+    d7 = pyqc.measure.Measurements(qc7).efficient_measurements(5, measure_eom=False,
+                                                                measure_GKP=False)
+    assert d7["Expr"] == -1 and d7["Magic"] == [-1, -1] and d7["GKP"] == [-1, -1]
+    assert np.abs(np.array(d7["Ent"]) - golden["effm/n7_ent"]).max() < ATOL
+    z = m.efficient_measurements(0)
+    assert z == {"Expr": -1, "Ent": [-1, -1], "Magic": [-1, -1], "GKP": [-1, -1]}
+
+
+def test_example_script_values(golden):
+    ex = cases.build_example4(pyqc)
+    m = pyqc.measure.Measurements(ex)
+    reseed()
+    assert abs(m.expressibility(150) - float(golden["example/expr150"])) < 1e-6
+    assert abs(m.entropy_of_magic(150) - float(golden["example/eom150"])) < 1e-8
+
+
+def test_magic_12q_config4(golden):
+    qc = pyqc.templates.generate_circuit("NPQC", 12, 3)
+    st = qc.run_batch(golden["magic12/angles"])
+    assert np.abs(st[0].cpu().numpy() - golden["magic12/state"]).max() < ATOL
+    mg = engine.magic(st, (2.0, 0.5)).cpu().numpy()
+    assert abs(mg[0, 0] - float(golden["magic12/renyi2"])) < RTOL * 4
+    assert abs(mg[1, 0] / (2 * np.log(2)) - float(golden["magic12/gkp"])) < RTOL * 5
+    assert abs(engine.meyer_wallach(st)[0].item() - float(golden["magic12/Q"])) < ATOL
+    # a batch of random 12-qubit NPQC states against the FWHT oracle
+    specs, _ = orc.generate_circuit("NPQC", 12, 3)
+    ang = np.random.default_rng(3).random((3, orc.n_params(specs))) * 2 * np.pi
+    st = qc.run_batch(ang)
+    ref = orc.run(specs, 12, ang)
+    assert np.abs(st.cpu().numpy() - ref).max() < ATOL
+    mg = engine.magic(st, (2.0, 0.5)).cpu().numpy()
+    for s in range(3):
+        assert abs(mg[0, s] - orc.renyi_fwht(ref[s], 2.0)) < RTOL * 4
+        assert abs(mg[1, s] - orc.renyi_fwht(ref[s], 0.5)) < RTOL * 10
+
+
+@pytest.mark.parametrize("kind,n,p", [("generic_HE", 13, 2), ("NPQC", 14, 3), ("TFIM", 16, 2),
+                                      ("XXZ", 16, 1), ("qg_circuit", 15, 1), ("Circuit_2", 17, 1)])
+def test_multi_pass_states_vs_oracle(kind, n, p):
+    """n > tile bits: several HBM passes per circuit; amplitudes vs the numpy oracle."""
+    qc = pyqc.templates.generate_circuit(kind, n, p, shuffle=False)
+    specs, init = orc.generate_circuit(kind, n, p)
+    assert specs_from_circuit(qc) == specs
+    ang = np.random.default_rng(n * 100 + p).random((2, orc.n_params(specs))) * 2 * np.pi
+    got = qc.run_batch(ang).cpu().numpy()
+    ref = orc.run(specs, n, ang, init)
+    assert np.abs(got - ref).max() < ATOL
+    Q = engine.meyer_wallach(torch.as_tensor(ref, device="cuda")).cpu().numpy()
+    assert np.abs(Q - [orc.single_Q(r, n) for r in ref]).max() < ATOL
+
+
+@pytest.mark.parametrize("kind,n,p", [("TFIM", 13, 2), ("XXZ", 14, 1), ("TFIM", 16, 1)])
+def test_multi_pass_qfim_vs_oracle(kind, n, p):
+    qc = pyqc.templates.generate_circuit(kind, n, p, shuffle=False)
+    specs, init = orc.generate_circuit(kind, n, p)
+    ang = np.random.default_rng(n + p).random((2, orc.n_params(specs))) * 2 * np.pi
+    F, st = qc.qfim_batch(ang, want_states=True)
+    ref_st = orc.run(specs, n, ang, init)
+    assert np.abs(st.cpu().numpy() - ref_st).max() < ATOL
+    gr = orc.gradients(specs, n, ang, init)
+    for s in range(2):
+        assert rel(F[s].cpu().numpy(), orc.qfi(ref_st[s], gr[s])) < RTOL
+
+
+def test_eigvalsh_vs_lapack():
+    rng = np.random.default_rng(11)
+    for P in (1, 2, 5, 12, 32, 33, 64):
+        A = rng.normal(size=(6, P, P))
+        A = A + A.transpose(0, 2, 1)
+        A[1] = A[1] @ A[1].T                                   # PSD
+        v = rng.normal(size=(P, max(1, P // 3)))
+        A[2] = v @ v.T                                         # rank deficient (zeros)
+        w = engine.eigvalsh(torch.as_tensor(A, device="cuda")).cpu().numpy()
+        ref = np.linalg.eigvalsh(A)
+        scale = np.abs(ref).max(axis=1, keepdims=True)
+        assert (np.abs(w - ref) / scale).max() < 1e-13, P
+        ww, vv = engine.eigh(torch.as_tensor(A, device="cuda"))
+        ww, vv = ww.cpu().numpy(), vv.cpu().numpy()
+        for k in range(6):
+            assert np.abs(A[k] @ vv[k] - vv[k] * ww[k]).max() < 1e-11 * max(1, scale[k, 0])
+            assert np.abs(vv[k].T @ vv[k] - np.eye(P)).max() < 1e-12
+        cnt = engine.count_greater(torch.as_tensor(ref, device="cuda"), 1e-12).cpu().numpy()
+        assert np.array_equal(cnt, (ref > 1e-12).sum(axis=1))
+
+
+def test_size_independent_properties_16q():
+    """At BASELINE config 3 size: unit norm, QFIM symmetric PSD, gauge invariance of F,
+    and F(theta) of TFIM bounded by 4 Var <= (2 * #generators)^2."""
+    qc = pyqc.templates.generate_circuit("TFIM", 16, 16)
+    ang = np.random.default_rng(1).random((3, 32)) * 2 * np.pi
+    F, st = qc.qfim_batch(ang, want_states=True)
+    nrm = engine.overlap(st, st).cpu().numpy()
+    assert np.abs(nrm - 1).max() < 1e-12
+    Fn = F.cpu().numpy()
+    assert np.abs(Fn - Fn.transpose(0, 2, 1)).max() == 0
+    w = engine.eigvalsh(F).cpu().numpy()
+    assert w.min() > -1e-9 and np.diagonal(Fn, axis1=1, axis2=2).max() <= 4 * 8 ** 2 + 1e-9
+    eq = engine.count_greater(torch.as_tensor(w, device="cuda"), 1e-12).cpu().numpy()
+    assert np.array_equal(eq, (np.linalg.eigvalsh(Fn) > 1e-12).sum(axis=1))
+
+
+def test_operator_algebra_and_state_surface(golden):
+    """`Gate * state`, prod(), conj(), overlap, ptrace, == (gates.py:30-31,63-85)."""
+    N = 3
+    psi = pyqc.qt.tensor([pyqc.qt.basis(2, 0)] * N)
+    g = pyqc.R_y(1, N)
+    g.set_theta(0.7)
+    chain = pyqc.CHAIN(pyqc.CNOT, N)
+    out = chain * (g * psi)
+    ref = orc.run([("R_y", 1), ("CHAIN", "CNOT")], N, [[0.7]])[0]
+    assert np.abs(out.numpy() - ref).max() < ATOL
+    out2 = pyqc.prod([g, chain][::-1]) * psi
+    assert out2 == out
+    U = g.operation.full()
+    assert np.abs(U - np.kron(np.kron(np.eye(2), orc.rot_matrix("y", 0.7)), np.eye(2))).max() < 1e-15
+    rx = pyqc.R_x(0, N)
+    rx.set_theta(1.3)
+    assert np.abs(rx.operation.conj().full() - rx.operation.full().conj()).max() < 1e-15
+    assert abs(out.overlap(out) - 1) < 1e-14
+    rho = out.ptrace(1)
+    assert abs((rho * rho).tr() - np.trace(rho.full() @ rho.full()).real) < 1e-15
+    assert out.dims == [[2] * N, [1] * N] and out.data.toarray().shape == (8, 1)
+    d = g.derivative() * out
+    assert np.abs(d.numpy() - orc.apply_1q(out.numpy()[None], N, 1, -0.5j * orc.SY)[0]).max() < ATOL

@@ -1,0 +1,138 @@
+"""CPU-only checks of the host side: reference-API bookkeeping, templates, lowering, the
+C-ABI surface, and that the product fails loudly instead of falling back to a CPU path."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+import pyramaterised_b200 as pyqc
+from helpers import oracle_case, specs_from_circuit
+from oracle import pqc_oracle as orc
+from pyramaterised_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ALL = sorted(cases.CASES)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_templates_match_oracle_specs(golden, name):
+    """The same builder calls as the golden generator produce the gate list the oracle
+    restates from templates.py, and the quirk-Q1 bookkeeping of circuit.py:62-72."""
+    qc = cases.CASES[name][0](pyqc)
+    specs, n, init = oracle_case(name)
+    assert qc.n_qubits == n
+    assert specs_from_circuit(qc) == specs
+    assert qc.n_true_params == int(golden[f"{name}/P"]) == cases.n_true_params(qc)
+    assert qc.n_params == int(golden[f"{name}/n_params_attr"])
+    assert qc.parameterised == list(golden[f"{name}/parameterised"])
+    if init is not None:
+        assert int(np.argmax(np.abs(init))) == qc._init_index
+
+
+def test_lowering_slots_and_groups():
+    qc = pyqc.templates.generate_circuit("TFIM", 16, 16)
+    ops = qc.lower()
+    assert len(ops) == 16 + 16 * 32 and qc.n_true_params == 32
+    slots = [o[3] for o in ops if o[3] >= 0]
+    assert slots == sorted(slots) and set(slots) == set(range(32))
+    assert [o[5] for o in ops] == sorted(o[5] for o in ops)          # gate index is monotone
+    fer = pyqc.templates.generate_circuit("fermionic", 4, 1, shuffle=False).lower()
+    neg = [o for o in fer if o[0] == _lib.OP_RZ and o[6] == -1.0]
+    off = [o for o in fer if o[0] == _lib.OP_RZ and o[3] >= 0 and o[7] == np.pi]
+    assert neg and off and neg[0][3] == off[0][3]                     # shared slot
+    fs = pyqc.templates.generate_circuit("fsim", 5, 2, shuffle=False).lower()
+    two = [o for o in fs if o[0] == _lib.OP_FSIM]
+    assert all(o[4] == o[3] + 1 for o in two)
+
+
+def test_random_stream_matches_reference_rng():
+    """gates.py:10 + circuit.py:100-112: one rng.random(1) per parameter, sample-major."""
+    qc = pyqc.templates.generate_circuit("NPQC", 4, 4)
+    st = pyqc.gates.rng.bit_generator.state
+    try:
+        pyqc.gates.rng.bit_generator.state = np.random.default_rng(1).bit_generator.state
+        batch = qc.draw_random(3)
+        pyqc.gates.rng.bit_generator.state = np.random.default_rng(1).bit_generator.state
+        single = [qc.set_params("random").copy() for _ in range(3)]
+    finally:
+        pyqc.gates.rng.bit_generator.state = st
+    ref = np.random.default_rng(1).random(3 * 20) * 2 * np.pi
+    assert np.array_equal(batch.ravel(), ref) and np.array_equal(np.concatenate(single), ref)
+
+
+def test_set_params_errors_like_reference():
+    qc = pyqc.templates.generate_circuit("generic_HE", 3, 1)
+    with pytest.raises(Exception, match="No parameters supplied!"):
+        qc.set_params("nonsense")
+    with pytest.raises(IndexError):
+        qc.set_params([0.1, 0.2])
+    with pytest.raises(Exception, match="Must supply a valid entangler!"):
+        pyqc.templates.string_to_entangler("swap")
+    qc.set_params(list(range(6)))
+    assert qc.get_params() == list(range(6))
+
+
+def test_pauli_sum_algebra():
+    qt = pyqc.qt
+    X, Y, Z = qt.sigmax(), qt.sigmay(), qt.sigmaz()
+    assert X * Y == 1j * Z and Y * Z == 1j * X and Z * X == 1j * Y
+    H = pyqc.templates.TFIM_hamiltonian(4, g=1.0, h=0.5)
+    M = H.full()
+    assert np.allclose(M, M.conj().T) and H.isherm
+    ref = np.zeros((16, 16), complex)
+    P = {"x": orc.SX, "z": orc.SZ}
+
+    def emb(op, q):
+        m = np.array([[1.0]])
+        for k in range(4):
+            m = np.kron(m, op if k == q else np.eye(2))
+        return m
+    for i in range(4):
+        ref -= emb(P["z"], i) @ emb(P["z"], (i + 1) % 4) + emb(P["x"], i) + 0.5 * emb(P["z"], i)
+    assert np.allclose(M, ref)
+    zz = pyqc.PQC(3).H
+    assert np.allclose(zz.full(), emb(orc.SZ, 0)[:8, :8] * 0 + np.kron(np.kron(orc.SZ, orc.SZ), np.eye(2)))
+    assert (Y.conj() == -1 * Y) and (qt.tensor([X, Z]).n == 2)
+
+
+def test_shared_parameter_derivative_shortcut_conditions():
+    N = 4
+    xxz = pyqc.templates.XXZ_layers(1, N)[0]
+    assert all(g._sum_of_generators_is_exact() for g in xxz)
+    bad = pyqc.shared_parameter([pyqc.R_x(0, N), pyqc.R_z(0, N)], N, commute=False)
+    assert not bad._sum_of_generators_is_exact()
+    bad2 = pyqc.shared_parameter([pyqc.R_y(0, N), pyqc.R_y(1, N)], N, commute=False)
+    assert not bad2._sum_of_generators_is_exact()
+    d = pyqc.RR_block(pyqc.R_zz, N).derivative()
+    assert len(d.terms) == N and all(abs(c + 0.5j) < 1e-15 for c in d.terms.values())
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pqc_b200.h")).read()
+    declared = set(re.findall(r"PQC_API\s+(?:const\s+char\*|int)\s+(pqc_\w+)\s*\(", hdr))
+    assert len(declared) >= 23
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared - {"pqc_last_error"} == set(_lib.SIGNATURES)
+    assert lib.pqc_abi_version() == 1
+    # error path without touching the device
+    import ctypes as C
+    h = C.c_void_p()
+    assert lib.pqc_program_create(0, 0, 0, None, C.byref(h)) < 0
+    assert b"n_qubits" in lib.pqc_last_error()
+
+
+def test_no_cpu_fallback_and_no_oracle_import():
+    import torch
+    pkg = os.path.join(ROOT, "pyramaterised_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src and "qutip_lite" not in src, fn
+    if not torch.cuda.is_available():
+        qc = pyqc.templates.generate_circuit("generic_HE", 3, 1)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            qc.run("random")
