@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the PQC hot path on B200.
+
+Workload (BASELINE.json configs[2], the 16-qubit configuration the metric is quoted on):
+TFIM Hamiltonian-variational circuit, 16 qubits x 16 layers (P = 32 parameters),
+QFIM + effective quantum dimension (cutoff 1e-12) for S parameter sets per GPU.
+One *step* = one pass of that path over the S x 32 synthetic angle batch
+(np.random.default_rng(1), the stream the reference itself consumes).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
+  python bench.py --impl reference [...]                       reference algorithm on host cores
+
+Prints ONE JSON line (see DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "PQC samples/sec (statevector+measures) at 16q, 1/8 B200; % HBM roofline"
+CUTOFF = 1e-12
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--circuit", default="TFIM", choices=["TFIM", "XXZ"])
+    ap.add_argument("--qubits", type=int, default=16)
+    ap.add_argument("--layers", type=int, default=16)
+    ap.add_argument("--samples", type=int, default=10000, help="parameter sets per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"{a.circuit} {a.qubits}q x {a.layers} layers: QFIM + effective quantum dimension "
+            f"(cutoff {CUTOFF:g}) over {a.samples} parameter sets per GPU")
+
+
+def angles_for(a, n_params, rank):
+    """rows [rank*S, (rank+1)*S) of the one global stream default_rng(1).random((G*S, P))."""
+    rng = np.random.default_rng(1)
+    skip = rank * a.samples * n_params
+    if skip:
+        rng.random(skip)
+    return rng.random((a.samples, n_params)) * 2 * np.pi
+
+
+# ---------------------------------------------------------------------------------------
+# CPU side: the oracle's literal restatement of update_state + get_QFI + EQD
+# (circuit.py:127-130,149-192; measure.py:33-87): P full re-simulations per sample.
+# ---------------------------------------------------------------------------------------
+def _cpu_one_derivative(job):
+    from oracle import pqc_oracle as orc
+    specs, n, ang, init, idx = job
+    if idx < 0:
+        return orc.run(specs, n, ang, init)[0]
+    return orc.gradients(specs, n, ang, init, only=[idx])[0, 0]
+
+
+def cpu_qfim_eqd(specs, n, ang_row, init, pool=None):
+    from oracle import pqc_oracle as orc
+    P = orc.n_params(specs)
+    jobs = [(specs, n, ang_row[None, :], init, i) for i in range(-1, P)]
+    res = pool.map(_cpu_one_derivative, jobs) if pool is not None else \
+        [_cpu_one_derivative(j) for j in jobs]
+    F = orc.qfi(res[0], np.stack(res[1:]))
+    return orc.eqd(F, CUTOFF)
+
+
+def cpu_baseline(a):
+    """Single host thread, one parameter set of the very same workload."""
+    from oracle import pqc_oracle as orc
+    specs, init = orc.generate_circuit(a.circuit, a.qubits, a.layers)
+    ang = angles_for(a, orc.n_params(specs), 0)
+    t0 = time.perf_counter()
+    cpu_qfim_eqd(specs, a.qubits, ang[0], init)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "samples/s", "cores": 1, "kind": "port",
+            "sample": f"1 of the {a.samples} parameter sets (row 0), full {a.qubits}q x "
+                      f"{a.layers} layers, literal {orc.n_params(specs)} re-simulations + QFIM "
+                      f"+ eigh; {dt:.1f} s of numpy on one core; QuTiP itself is not "
+                      f"installable offline so the restated reference is timed"}
+
+
+def run_reference(a):
+    """--impl reference: the reference algorithm (oracle port) on all host cores; one
+    step = one parameter set, its P+1 independent simulations spread over a process pool."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import pqc_oracle as orc
+    specs, init = orc.generate_circuit(a.circuit, a.qubits, a.layers)
+    P = orc.n_params(specs)
+    ang = angles_for(a, P, 0)
+    cores = max(1, min(os.cpu_count() or 1, P + 1))
+    with mp.get_context("fork").Pool(cores) as pool:
+        for i in range(a.warmup):
+            cpu_qfim_eqd(specs, a.qubits, ang[i % a.samples], init, pool)
+        t0 = time.perf_counter()
+        for i in range(a.steps):
+            cpu_qfim_eqd(specs, a.qubits, ang[(a.warmup + i) % a.samples], init, pool)
+        dt = time.perf_counter() - t0
+    value = a.steps / dt
+    base = {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"each step = 1 parameter set of the workload; its {P}+1 independent "
+                      f"simulations run on a {cores}-process pool (numpy oracle; QuTiP not "
+                      f"installable offline)"}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
+        "config": {"workload": workload_name(a), "step_unit": "1 parameter set"},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0}}))
+
+
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(index)], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, mx, reasons, power = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import pyramaterised_b200 as pyqc
+    from pyramaterised_b200 import engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_baseline(a)          # before the GPU run, on this box's host cores
+
+    qc = pyqc.templates.generate_circuit(a.circuit, a.qubits, a.layers, shuffle=False)
+    P = qc.n_true_params
+    m = pyqc.measure.Measurements(qc)
+    ang_host = torch.from_numpy(angles_for(a, P, rank)).pin_memory()
+    ang_dev = ang_host.to(dev)
+    eq_host = torch.empty((a.samples,), dtype=torch.int32).pin_memory()
+    ev_host = torch.empty((a.samples, P), dtype=torch.float64).pin_memory()
+
+    def step_resident():
+        F = qc.qfim_batch(ang_dev)
+        w = engine.eigvalsh(F)
+        return engine.count_greater(w, CUTOFF), w
+
+    def step_e2e():
+        """Public API call with HOST buffers: pinned angles in, EQD + spectrum out."""
+        F, eq = m.qfim_batch(ang_host, cutoff_eigvals=CUTOFF)     # H2D inside
+        w = engine.eigvalsh(F)
+        eq_host.copy_(eq, non_blocking=True)
+        ev_host.copy_(w, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return eq_host
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    for _ in range(max(3, a.warmup)):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = engine.launch_count()
+    engine.profile_begin()
+    ms, (eq, w) = timed(step_resident, a.steps)
+    prof = engine.profile_end()
+    launches = engine.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+
+    step_e2e()
+    ms_e2e, eq_h = timed(step_e2e, a.steps)
+    assert np.array_equal(eq_h.numpy(), eq.cpu().numpy())
+
+    lt = torch.tensor([launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(lt)
+    total = a.samples * world
+    value = total * a.steps / (ms / 1e3)
+    e2e = total * a.steps / (ms_e2e / 1e3)
+    peak, peak_src = measured_peak_gbs()
+    achieved = prof["bytes"] / (prof["ms"] / 1e3) / 1e9 if prof["ms"] > 0 else 0.0
+    kern = "k_apply_pass"
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "complex128 (f64)", "data": "synthetic",
+        "config": {"workload": workload_name(a), "circuit": a.circuit, "n_qubits": a.qubits,
+                   "layers": a.layers, "n_params": P, "samples_per_gpu": a.samples,
+                   "sharding": f"samples x{world}, no data-path collective",
+                   "l2": "no flush needed: each chunk's live vectors (33 MB per parameter "
+                         "set x thousands of sets) exceed the 126 MB L2 many times over",
+                   "eqd_histogram": np.bincount(eq.cpu().numpy()).tolist()},
+        "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / a.steps,
+                "h2d_bytes_per_step": int(ang_host.numel() * 8),
+                "d2h_bytes_per_step": int(eq_host.numel() * 4 + ev_host.numel() * 8)},
+        "gpu_launches": int(lt.item()),
+        "roofline": {"kernel": kern, "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                     "launches": prof["launches"],
+                     "avg_launch_ms": prof["ms"] / max(1, prof["launches"]),
+                     "kernel_share_of_step": prof["ms"] / ms,
+                     "algorithmic_bytes_per_launch": prof["bytes"] / max(1, prof["launches"]),
+                     "traffic": ncu_traffic(kern)},
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -91,6 +91,14 @@ typedef struct pqc_pauli_term {
 
 PQC_API const char* pqc_last_error(void);
 PQC_API int pqc_abi_version(void);
+/* Number of CUDA kernels this library has launched in the calling process. */
+PQC_API long long pqc_launch_count(void);
+/* Bracket a region in which every launch of the gate-apply tile kernel is timed with a
+ * CUDA event pair on its own stream.  pqc_profile_end synchronises those events and
+ * returns out[0] = summed kernel ms, out[1] = launches, out[2] = algorithmic bytes
+ * (vectors x 2 x 16 x 2^n per launch), out[3] = reserved. */
+PQC_API int pqc_profile_begin(void);
+PQC_API int pqc_profile_end(double* out4);
 /* Fails (<0) unless the current CUDA device is compute capability 10.x. */
 PQC_API int pqc_device_check(int* cc_major, int* cc_minor, int* n_sms);
 

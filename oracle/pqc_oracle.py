@@ -375,9 +375,11 @@ def run(specs, n, angles, init=None):
     return psi
 
 
-def gradients(specs, n, angles, init=None):
+def gradients(specs, n, angles, init=None, only=None):
     """PQC.get_gradients for a batch: [S,P,2^n] (circuit.py:149-192), including the
-    quirk-Q2 gate lookup for two-parameter gates."""
+    quirk-Q2 gate lookup for two-parameter gates.  `only`: optional iterable of parameter
+    indices to compute (each is an independent full re-simulation, circuit.py:167-169);
+    the result then has len(only) derivative states."""
     angles = np.atleast_2d(np.asarray(angles, dtype=np.float64))
     S = angles.shape[0]
     init = zero_state(n) if init is None else np.asarray(init, dtype=np.complex128)
@@ -395,18 +397,20 @@ def gradients(specs, n, angles, init=None):
                 psi = apply_gate(psi, n, s, th, ph)
         return psi
 
-    out = []
+    jobs = []
     param_locs = [j for j, s in enumerate(specs) if param_count(s) > 0]
     for count, loc in enumerate(param_locs):
         if param_count(specs[loc]) == 1:
-            out.append(resim(loc, 0))
+            jobs.append((loc, 0))
         else:
-            out.append(resim(loc, 1))
+            jobs.append((loc, 1))
             # circuit.py:188: g_prime = self.gates[count] -- count indexes the parameterised
             # list, so this is the intended gate only if every earlier gate is parameterised
             loc2 = count
-            which2 = 2 if specs[loc2][0] == "fSim" else 0
-            out.append(resim(loc2, which2))
+            jobs.append((loc2, 2 if specs[loc2][0] == "fSim" else 0))
+    if only is not None:
+        jobs = [jobs[i] for i in only]
+    out = [resim(loc, which) for loc, which in jobs]
     return np.stack(out, axis=1) if out else np.zeros((S, 0, 2 ** n), np.complex128)
 
 

@@ -35,6 +35,8 @@ _DBL = C.c_double
 # name -> argtypes; every function returns int except pqc_last_error
 SIGNATURES = {
     "pqc_abi_version": [],
+    "pqc_profile_begin": [],
+    "pqc_profile_end": [C.POINTER(_DBL)],
     "pqc_device_check": [C.POINTER(_INT), C.POINTER(_INT), C.POINTER(_INT)],
     "pqc_program_create": [_INT, _INT, _INT, C.POINTER(PqcOp), C.POINTER(_P)],
     "pqc_program_destroy": [_P],
@@ -81,6 +83,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch
         fn.restype = C.c_int
         fn.argtypes = args
+    lib.pqc_launch_count.restype = C.c_longlong
+    lib.pqc_launch_count.argtypes = []
     if lib.pqc_abi_version() != 1:
         raise ImportError("libpqc_b200.so ABI version mismatch")
     _lib = lib

@@ -8,7 +8,10 @@
 static thread_local std::string g_last_error;
 void pqc_set_error(const std::string& msg) { g_last_error = msg; }
 
+long long g_pqc_launches = 0;
+
 extern "C" const char* pqc_last_error(void) { return g_last_error.c_str(); }
+extern "C" long long pqc_launch_count(void) { return g_pqc_launches; }
 extern "C" int pqc_abi_version(void) { return PQC_ABI_VERSION; }
 
 extern "C" int pqc_device_check(int* cc_major, int* cc_minor, int* n_sms) {

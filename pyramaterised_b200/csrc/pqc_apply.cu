@@ -412,6 +412,51 @@ __global__ void __launch_bounds__(NT) k_apply_pass(const PassArgs a) {
   }
 }
 
+// ---- optional per-launch timing of the gate-apply kernel (bench.py roofline) ------------
+struct ProfRec { cudaEvent_t e0, e1; double bytes; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+extern "C" int pqc_profile_begin(void) {
+  for (auto& r : g_prof) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
+  g_prof.clear();
+  g_prof_on = true;
+  return 0;
+}
+
+extern "C" int pqc_profile_end(double* out4) {
+  g_prof_on = false;
+  double ms = 0.0, bytes = 0.0;
+  for (auto& r : g_prof) {
+    PQC_CUDA(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    PQC_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t;
+    bytes += r.bytes;
+  }
+  if (out4) {
+    out4[0] = ms;
+    out4[1] = (double)g_prof.size();
+    out4[2] = bytes;
+    out4[3] = 0.0;
+  }
+  for (auto& r : g_prof) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
+  g_prof.clear();
+  return 0;
+}
+
 template <int NT>
 static int launch_nt(const PassArgs& a, long long grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
@@ -420,7 +465,19 @@ static int launch_nt(const PassArgs& a, long long grid, size_t smem, cudaStream_
                                   200 * 1024));
     attr_set = true;
   }
+  ProfRec rec;
+  if (g_prof_on) {
+    rec.e0 = prof_event();
+    rec.e1 = prof_event();
+    // algorithmic traffic of one pass: every vector read once and written once
+    rec.bytes = (double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n);
+    cudaEventRecord(rec.e0, st);
+  }
   k_apply_pass<NT><<<(unsigned)grid, NT, smem, st>>>(a);
+  if (g_prof_on) {
+    cudaEventRecord(rec.e1, st);
+    g_prof.push_back(rec);
+  }
   PQC_LAUNCH_CHECK();
   return 0;
 }

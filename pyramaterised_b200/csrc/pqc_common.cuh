@@ -25,8 +25,10 @@ void pqc_set_error(const std::string& msg);
       return -2;                                                                    \
     }                                                                               \
   } while (0)
+extern long long g_pqc_launches;      // kernels launched by this library (pqc_launch_count)
 #define PQC_LAUNCH_CHECK()                                                          \
   do {                                                                              \
+    ++g_pqc_launches;                                                               \
     cudaError_t _e = cudaGetLastError();                                            \
     if (_e != cudaSuccess) {                                                        \
       pqc_set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));       \

@@ -111,6 +111,7 @@ extern "C" int pqc_meyer_wallach(const pqc_c128* d_states, int64_t S, int n, dou
   int rc = mw_accumulate((const c128*)d_states, S, n, acc, st);
   if (rc == 0) {
     k_mw_finalize<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(acc, S, n, d_Q);
+    ++g_pqc_launches;
     if (cudaGetLastError() != cudaSuccess) rc = -2;
   }
   cudaFreeAsync(acc, st);
@@ -135,6 +136,7 @@ extern "C" int pqc_ptrace_1q(const pqc_c128* d_state, int n, int qubit, pqc_c128
   int rc = mw_accumulate((const c128*)d_state, 1, n, acc, st);
   if (rc == 0) {
     k_rho_from_acc<<<1, 1, 0, st>>>(acc, n, qubit, (c128*)d_rho);
+    ++g_pqc_launches;
     if (cudaGetLastError() != cudaSuccess) rc = -2;
   }
   cudaFreeAsync(acc, st);
@@ -238,6 +240,7 @@ extern "C" int pqc_pauli_expect_batch(const pqc_c128* d_states, int64_t S, int n
   if (rc) return rc;
   k_pauli_expect<<<(unsigned)S, 256, 0, st>>>((const c128*)d_states, n, d_terms, n_terms,
                                               (c128*)d_out);
+  ++g_pqc_launches;
   if (cudaGetLastError() != cudaSuccess) rc = -2;
   cudaFreeAsync(d_terms, st);
   return rc;
@@ -464,6 +467,7 @@ extern "C" int pqc_kl_haar(const long long* d_hist, int64_t bins, double N, doub
   const double step = 1.0 / (double)bins;
   k_kl_sums<<<(unsigned)grid, 256, 0, st>>>(d_hist, bins, step, N, d_scratch);
   k_kl_terms<<<(unsigned)grid, 256, 0, st>>>(d_hist, bins, step, N, d_scratch);
+  g_pqc_launches += 2;
   k_copy1<<<1, 1, 0, st>>>(d_scratch + 2, d_out);
   PQC_LAUNCH_CHECK();
   return 0;
@@ -663,6 +667,7 @@ extern "C" int pqc_qfim_from_grads(const pqc_c128* d_states, const pqc_c128* d_g
   } else {
     k_gram_rows<<<(unsigned)(S * (P + 1)), 256, 0, st>>>((const c128*)d_states,
                                                         (const c128*)d_grads, n, P, G);
+    ++g_pqc_launches;
     if (cudaGetLastError() != cudaSuccess) rc = -2;
     if (rc == 0) rc = pqc_qfim_finalize(G, S, P, d_qfim, st);
   }

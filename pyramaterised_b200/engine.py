@@ -12,6 +12,7 @@ import torch
 from . import _lib
 
 _device_ok = False
+QFIM_WORK_BYTES = 32 << 30   # default cap of the live-vector workspace of Program.qfim
 gpu_launches = 0          # kernels enqueued through this module (bench.py reports it)
 
 
@@ -30,6 +31,22 @@ def device():
         _lib.check(lib.pqc_device_check(C.byref(maj), C.byref(mnr), C.byref(sms)))
         _device_ok = True
     return dev
+
+
+def launch_count():
+    """Kernels launched by libpqc_b200.so in this process (counted inside the library)."""
+    return int(_lib.load().pqc_launch_count())
+
+
+def profile_begin():
+    _lib.check(_lib.load().pqc_profile_begin())
+
+
+def profile_end():
+    """-> dict(ms, launches, bytes) for the gate-apply kernel since profile_begin()."""
+    out = (C.c_double * 4)()
+    _lib.check(_lib.load().pqc_profile_end(out))
+    return {"ms": out[0], "launches": int(out[1]), "bytes": out[2]}
 
 
 def _stream():
@@ -155,10 +172,13 @@ class Program:
         _lib.check(lib.pqc_qfim_workspace_bytes(self._h, S, C.byref(need)))
         per = (need.value - 256) // max(1, S)
         if max_work_bytes is None:
-            free, _total = torch.cuda.mem_get_info()
-            max_work_bytes = int(free * 0.6)
+            max_work_bytes = QFIM_WORK_BYTES
         nbytes = min(need.value, max(per + 256, (max_work_bytes // per) * per + 256))
-        work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        work = getattr(self, "_work", None)
+        if work is None or work.numel() < nbytes or work.device != dev:
+            self._work = work = None           # drop the old block before asking for a bigger one
+            self._work = work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        nbytes = work.numel()
         F = torch.empty((S, self.P, self.P), dtype=torch.float64, device=dev)
         states = torch.empty((S, self.dim), dtype=torch.complex128, device=dev) if want_states else None
         if init is not None:

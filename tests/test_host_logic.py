@@ -111,12 +111,12 @@ def test_shared_parameter_derivative_shortcut_conditions():
 
 def test_c_abi_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "pqc_b200.h")).read()
-    declared = set(re.findall(r"PQC_API\s+(?:const\s+char\*|int)\s+(pqc_\w+)\s*\(", hdr))
+    declared = set(re.findall(r"PQC_API\s+(?:const\s+char\*|int|long long)\s+(pqc_\w+)\s*\(", hdr))
     assert len(declared) >= 23
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert declared - {"pqc_last_error"} == set(_lib.SIGNATURES)
+    assert declared - {"pqc_last_error", "pqc_launch_count"} == set(_lib.SIGNATURES)
     assert lib.pqc_abi_version() == 1
     # error path without touching the device
     import ctypes as C
