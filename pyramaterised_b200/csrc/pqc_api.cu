@@ -1,6 +1,7 @@
 // pqc_api.cu -- C-ABI entry points for programs, state generation, derivative states and
 // the fused QFIM pipeline (include/pqc_b200.h).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "pqc_common.cuh"
@@ -60,7 +61,8 @@ extern "C" int pqc_program_create(int n_qubits, int n_params, int n_ops, const p
                      op.kind == PQC_OP_FIXED_FSIM;
     if (!two) op.q1 = -1;
   }
-  const int rc = pqc_plan_program(p);
+  int rc = pqc_plan_program(p);
+  if (rc == 0) rc = pqc_plan_v1(p);
   if (rc) {
     pqc_program_destroy(p);
     return rc;
@@ -73,6 +75,10 @@ extern "C" int pqc_program_destroy(pqc_program* prog) {
   if (!prog) return 0;
   if (prog->d_ops) cudaFree(prog->d_ops);
   if (prog->d_gens) cudaFree(prog->d_gens);
+  if (prog->d_mops) cudaFree(prog->d_mops);
+  if (prog->d_sweeps) cudaFree(prog->d_sweeps);
+  if (prog->d_tjobs) cudaFree(prog->d_tjobs);
+  if (prog->d_zz) cudaFree(prog->d_zz);
   delete prog;
   return 0;
 }
@@ -82,13 +88,16 @@ extern "C" int pqc_program_stats(const pqc_program* prog, int64_t* out8) {
   out8[0] = prog->n;
   out8[1] = prog->P;
   out8[2] = (int64_t)prog->ops.size();
-  out8[3] = (int64_t)prog->run_passes.size();
-  out8[4] = prog->tile_bits;
+  const bool v1r = prog->v1_ok && !pqc_use_v0();
+  const bool v1g = prog->v1_grad_ok && !pqc_use_v0();
+  out8[3] = v1r ? (int64_t)prog->v1_run.size() : (int64_t)prog->run_passes.size();
+  out8[4] = v1r ? V1_LOCAL_BITS : prog->tile_bits;
   out8[5] = prog->grad_supported ? 1 : 0;
   int64_t q = 0;
-  for (auto& v : prog->seg_passes) q += (int64_t)v.size();
+  if (v1g) q = pqc_v1_n_passes(prog, false);
+  else for (auto& v : prog->seg_passes) q += (int64_t)v.size();
   out8[6] = q;
-  out8[7] = 0;
+  out8[7] = (v1r ? 1 : 0) | (v1g ? 2 : 0);
   return 0;
 }
 
@@ -107,6 +116,8 @@ extern "C" int pqc_run_batch(const pqc_program* prog, const double* d_angles, in
   if (S <= 0) return 0;
   if (prog->P > 0 && (!d_angles || ld < prog->P)) PQC_FAIL(-1, "No parameters supplied!");
   cudaStream_t st = (cudaStream_t)stream;
+  if (prog->v1_ok && !pqc_use_v0())
+    return pqc_v1_run(prog, d_angles, ld, S, (const c128*)d_init, init_stride, (c128*)d_out, st);
   int mode = init_mode_of(d_init, init_stride);
   for (const Pass& ps : prog->run_passes) {
     const int rc = pqc_launch_pass(prog, ps, (c128*)d_out, (const c128*)d_init, init_stride, mode,
@@ -135,8 +146,25 @@ extern "C" int pqc_gradients_batch(const pqc_program* prog, const double* d_angl
   if (S <= 0) return 0;
   if (!prog->grad_supported) PQC_FAIL(-4, "derivative states unsupported: " + prog->grad_reason);
   if (prog->P > 0 && (!d_angles || ld < prog->P)) PQC_FAIL(-1, "No parameters supplied!");
+  if (init_stride != 0) PQC_FAIL(-1, "derivative states take one shared initial state");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prog->v1_grad_ok && !pqc_use_v0()) {
+    // second ping-pong copy; ordered so that the last pass lands in the caller's buffer
+    const size_t bytes = sizeof(c128) * (size_t)S * (prog->P + 1) * ((size_t)1 << prog->n);
+    c128* scratch = nullptr;
+    PQC_CUDA(cudaMallocAsync(&scratch, bytes, st));
+    const bool even = (pqc_v1_n_passes(prog, true) % 2) == 0;
+    c128* fin = nullptr;
+    int rc = pqc_v1_derivatives(prog, d_angles, ld, S, (const c128*)d_init,
+                                even ? (c128*)d_out : scratch, even ? scratch : (c128*)d_out,
+                                nullptr, false, true, &fin, st);
+    if (rc == 0 && fin != (c128*)d_out)
+      if (cudaMemcpyAsync(d_out, fin, bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = -2;
+    cudaFreeAsync(scratch, st);
+    return rc;
+  }
   return forward_derivatives(prog, d_angles, ld, S, d_init, init_stride, (c128*)d_out, nullptr,
-                             true, false, (cudaStream_t)stream);
+                             true, false, st);
 }
 
 // <slot j | slot k> for j = 0..k-1... written into G[(s*(P+1)+j)*P + p]; one CTA per (s, j)
@@ -214,8 +242,23 @@ static int forward_derivatives(const pqc_program* prog, const double* d_angles, 
 // ---------------------------------------------------------------------------------
 static int64_t qfim_bytes_per_sample(const pqc_program* prog) {
   const int64_t D = 1ll << prog->n;
+  if (prog->v1_grad_ok && !pqc_use_v0())   // two ping-pong copies + per-tile Gram partials
+    return 2 * (int64_t)(prog->P + 1) * D * (int64_t)sizeof(c128) +
+           pqc_v1_gpart_elems(prog, 1) * (int64_t)sizeof(c128);
   return (int64_t)(prog->P + 1) * D * (int64_t)sizeof(c128) +
          (int64_t)(prog->P + 1) * std::max(1, prog->P) * (int64_t)sizeof(c128);
+}
+
+// samples processed together: small enough that the freshly spawned vectors (the Gram
+// partners every CTA re-reads) stay L2 resident, large enough to fill 148 SMs
+static int64_t qfim_chunk_target() {
+  static int64_t v = -1;
+  if (v < 0) {
+    const char* e = getenv("PQC_QFIM_CHUNK");
+    v = e ? atoll(e) : 64;
+    if (v < 1) v = 64;
+  }
+  return v;
 }
 
 extern "C" int pqc_qfim_workspace_bytes(const pqc_program* prog, int64_t S, int64_t* bytes) {
@@ -241,6 +284,27 @@ extern "C" int pqc_qfim_batch(const pqc_program* prog, const double* d_angles, i
   int64_t C = usable / per;
   if (C < 1) PQC_FAIL(-1, "QFIM workspace too small for one sample");
   C = std::min<int64_t>(C, S);
+  if (prog->v1_grad_ok && !pqc_use_v0()) {
+    C = std::min<int64_t>(C, qfim_chunk_target());
+    for (int64_t c0 = 0; c0 < S; c0 += C) {
+      const int64_t c = std::min<int64_t>(C, S - c0);
+      c128* buf_a = (c128*)w0;
+      c128* buf_b = buf_a + c * (int64_t)(P + 1) * D;
+      c128* G = buf_b + c * (int64_t)(P + 1) * D;
+      c128* fin = nullptr;
+      int rc = pqc_v1_derivatives(prog, d_angles + c0 * ld, ld, c, (const c128*)d_init, buf_a,
+                                  buf_b, G, true, d_states_out != nullptr, &fin, st);
+      if (rc) return rc;
+      rc = pqc_v1_qfim_reduce(prog, G, c, d_qfim + c0 * (int64_t)P * P, st);
+      if (rc) return rc;
+      if (d_states_out) {
+        PQC_CUDA(cudaMemcpy2DAsync((c128*)d_states_out + c0 * D, D * sizeof(c128), fin,
+                                   (size_t)(P + 1) * D * sizeof(c128), D * sizeof(c128), c,
+                                   cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    return 0;
+  }
   for (int64_t c0 = 0; c0 < S; c0 += C) {
     const int64_t c = std::min<int64_t>(C, S - c0);
     c128* buf = (c128*)w0;

@@ -457,6 +457,21 @@ extern "C" int pqc_profile_end(double* out4) {
   return 0;
 }
 
+int pqc_prof_launch_begin(double bytes, cudaStream_t st) {
+  if (!g_prof_on) return -1;
+  ProfRec rec;
+  rec.e0 = prof_event();
+  rec.e1 = prof_event();
+  rec.bytes = bytes;
+  cudaEventRecord(rec.e0, st);
+  g_prof.push_back(rec);
+  return (int)g_prof.size() - 1;
+}
+
+void pqc_prof_launch_end(int h, cudaStream_t st) {
+  if (h >= 0) cudaEventRecord(g_prof[h].e1, st);
+}
+
 template <int NT>
 static int launch_nt(const PassArgs& a, long long grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
@@ -465,19 +480,11 @@ static int launch_nt(const PassArgs& a, long long grid, size_t smem, cudaStream_
                                   200 * 1024));
     attr_set = true;
   }
-  ProfRec rec;
-  if (g_prof_on) {
-    rec.e0 = prof_event();
-    rec.e1 = prof_event();
-    // algorithmic traffic of one pass: every vector read once and written once
-    rec.bytes = (double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n);
-    cudaEventRecord(rec.e0, st);
-  }
+  // algorithmic traffic of one pass: every vector read once and written once
+  const int h = pqc_prof_launch_begin(
+      (double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st);
   k_apply_pass<NT><<<(unsigned)grid, NT, smem, st>>>(a);
-  if (g_prof_on) {
-    cudaEventRecord(rec.e1, st);
-    g_prof.push_back(rec);
-  }
+  pqc_prof_launch_end(h, st);
   PQC_LAUNCH_CHECK();
   return 0;
 }

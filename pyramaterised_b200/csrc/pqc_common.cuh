@@ -84,10 +84,75 @@ struct GenTerm {             // one Pauli term of a parameter's generator sum
   double re, im;             // coefficient (already includes -i/2 * scale)
 };
 
+// ------------------------------------------------------------------ v1 (sweep engine)
+// internal opcodes produced by the planner's fusion step
+#define PQC_K_ZZSUM 32   // product of same-angle R_zz over a pair set: one table-lookup phase
+#define PQC_K_RXY 33     // R_yy * R_xx on one pair, same angle: rotation of the odd-parity pair
+#define PQC_K_GEN 34     // multiply by a diagonal generator sum (spawn items only)
+#define PQC_K_LAYER_RX4 35    // rx-type gate on each of the 4 register bits (identity = c 1, s 0)
+#define PQC_K_LAYER_REAL4 36  // real 2x2 on each register bit: RY, H or identity
+
+#define V1_LOCAL_BITS 12          // 4096 amplitudes per CTA = 256 threads x 16 registers
+#define V1_MAX_SPAWN 32
+#define V1_MAX_PART 64
+
+struct MOp {               // one micro-op inside a sweep
+  int kind;
+  int k0, k1;              // register-bit index (0..3) if the bit is a register bit, else -1
+  int l0, l1;              // local tile position of the bit, -1 if outside the tile
+  int b0, b1;              // global bit positions
+  int trig;                // first trig slot
+  int aux0, aux1;          // ZZSUM: zz-term offset / count;  GEN: in-pass spawn index
+  int npairs;              // ZZSUM: number of pairs
+  int subk;                // LAYER_*4: gate on register bit K in byte K: 0 none, else opcode+1
+  int subt[4];             // LAYER_*4: trig slot of the gate on register bit K
+};
+struct SweepD {
+  int rb[4];               // local positions held in registers, ascending
+  int mop_begin, mop_end;
+  int io;                  // bit0: load straight from global, bit1: store straight to global
+  int pad;
+};
+struct TrigJob {           // per-item trig table entry (or run of entries) to fill
+  int kind, param, param2, slot, npairs, pad;
+  double scale, offset;
+};
+struct ZZTerm { uint32_t mask; int shift; };   // count += popc((x ^ (x >> shift)) & mask)
+
+struct V1Pass {
+  int tb, low_run;
+  int lbit[V1_LOCAL_BITS];
+  int obit[PQC_MAX_QUBITS];
+  int sweep_off, nsweeps;  // into the program's device arrays
+  int mop_off, nmops;
+  int tj_off, ntjobs, ntrig;
+  // in-pass diagonal spawns, in order of their K_GEN micro-ops
+  std::vector<int> spawn_param;
+  bool direct_ok;
+  int io_first, io_last;
+};
+struct V1Stage {
+  int type;                      // 0 = pass, 1 = gather spawn
+  int pass = -1;                 // index into v1_passes
+  std::vector<int> gather_params;
+  std::vector<int> partners;     // parameters whose Gram column is taken on this pass' load
+};
+
 struct pqc_program {
   int n = 0, P = 0;
   std::vector<pqc_op> ops;
   int tile_bits = 12;
+  // ---- v1 plans
+  bool v1_ok = false;            // run plan usable
+  bool v1_grad_ok = false;       // derivative / QFIM plan usable
+  std::vector<V1Pass> v1_passes;
+  std::vector<int> v1_run;                   // pass indices of the plain run plan
+  std::vector<V1Stage> v1_grad;              // stages of the derivative / QFIM plan
+  std::vector<int> v1_gen_diag_off;          // per parameter: offset/count of diagonal terms
+  MOp* d_mops = nullptr;
+  SweepD* d_sweeps = nullptr;
+  TrigJob* d_tjobs = nullptr;
+  ZZTerm* d_zz = nullptr;
   // forward plan over the whole op list (PQC.run)
   std::vector<Pass> run_passes;
   // QFIM / gradient plan: one segment of passes per parameter, plus the trailing ops
@@ -133,6 +198,19 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 // ------------------------------------------------------------------ cross-file host API
 int pqc_plan_program(pqc_program* prog);
+int pqc_plan_v1(pqc_program* prog);
+int pqc_v1_run(const pqc_program* prog, const double* d_angles, long long ld, long long S,
+               const c128* d_init, long long init_stride, c128* d_out, cudaStream_t st);
+int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long long ld, long long S,
+                       const c128* d_init, c128* buf_a, c128* buf_b, c128* d_gpart,
+                       bool want_dots, bool need_final, c128** final_buf, cudaStream_t st);
+int pqc_v1_n_passes(const pqc_program* prog, bool need_final);
+long long pqc_v1_gpart_elems(const pqc_program* prog, long long S);
+int pqc_v1_qfim_reduce(const pqc_program* prog, const c128* d_gpart, long long S, double* d_F,
+                       cudaStream_t st);
+bool pqc_use_v0();
+int pqc_prof_launch_begin(double bytes, cudaStream_t st);
+void pqc_prof_launch_end(int h, cudaStream_t st);
 int pqc_pauli_apply_slots(const c128* src, c128* dst, int n, long long S, int slots_total,
                           int src_slot, int dst_slot, const GenTerm* d_terms, int nterms,
                           cudaStream_t st);

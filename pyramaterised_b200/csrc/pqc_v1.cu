@@ -1,0 +1,1463 @@
+// pqc_v1.cu -- the register-blocked "sweep" engine (v1) and its planner.
+//
+// Same job as pqc_apply.cu (circuit.py:123-124 gate application, circuit.py:149-192
+// derivative states, measure.py:33-71 Gram entries) but organised for the B200 memory
+// system:
+//   * a PASS stages a 4096-amplitude tile (12 tile bits, the low 4 always included so
+//     every global access is a full 256 B run) and visits it in SWEEPS;
+//   * a SWEEP pulls 16 amplitudes per thread into registers (4 "register bits") and
+//     applies every pending op on those bits plus every pending diagonal op -- one
+//     shared-memory round trip and one barrier per sweep instead of one per gate;
+//     the first / last sweep of a pass talk to global memory directly;
+//   * shared memory is XOR-swizzled so the three aligned nibble sweeps are conflict free;
+//   * the planner groups the op list into mutually commuting BLOCKS, fuses same-angle
+//     R_zz sets into one table-lookup phase (ZZSUM) and R_yy*R_xx pairs into one XY
+//     rotation, lets passes run across parameter boundaries, spawns derivative vectors
+//     where the generator commutes with the rest of its block, multiplies diagonal
+//     generators inside the pass (recomputing psi's tile), and takes the Gram dot
+//     products while the next pass loads its tile (ping-pong buffers keep that race free).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "pqc_common.cuh"
+
+bool pqc_use_v0() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PQC_ENGINE");
+    v = (e && strcmp(e, "v0") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// =====================================================================================
+// planner
+// =====================================================================================
+namespace {
+
+struct COp {
+  int kind = 0, b0 = -1, b1 = -1, param = -1, param2 = -1, group = -1;
+  double scale = 1.0, offset = 0.0;
+  uint32_t support = 0, mix = 0;
+  bool diag = false, pauli = false, two = false;
+  uint32_t px = 0, pz = 0, px2 = 0, pz2 = 0;
+  std::vector<std::pair<int, int>> pairs;   // ZZSUM
+};
+
+bool pauli_comm(uint32_t x1, uint32_t z1, uint32_t x2, uint32_t z2) {
+  return ((__builtin_popcount(x1 & z2) + __builtin_popcount(z1 & x2)) & 1) == 0;
+}
+
+bool commute(const COp& a, const COp& b) {
+  if (!(a.support & b.support)) return true;
+  if (a.diag && b.diag) return true;
+  if (a.pauli && b.pauli) {
+    bool ok = pauli_comm(a.px, a.pz, b.px, b.pz);
+    if (a.two) ok = ok && pauli_comm(a.px2, a.pz2, b.px, b.pz);
+    if (b.two) ok = ok && pauli_comm(a.px, a.pz, b.px2, b.pz2);
+    if (a.two && b.two) ok = ok && pauli_comm(a.px2, a.pz2, b.px2, b.pz2);
+    return ok;
+  }
+  return false;
+}
+
+COp make_cop(const pqc_op& op, int n) {
+  COp c;
+  c.kind = op.kind;
+  c.b0 = n - 1 - op.q0;
+  c.b1 = op.q1 >= 0 ? n - 1 - op.q1 : -1;
+  c.param = op.param;
+  c.param2 = op.param2;
+  c.scale = op.scale;
+  c.offset = op.offset;
+  c.group = op.group;
+  const uint32_t m0 = 1u << c.b0, m1 = c.b1 >= 0 ? 1u << c.b1 : 0u;
+  c.support = m0 | m1;
+  switch (op.kind) {
+    case PQC_OP_RX: c.mix = m0; c.pauli = true; c.px = m0; break;
+    case PQC_OP_RY: c.mix = m0; c.pauli = true; c.px = m0; c.pz = m0; break;
+    case PQC_OP_RZ: c.diag = true; c.pauli = true; c.pz = m0; break;
+    case PQC_OP_H: case PQC_OP_X: c.mix = m0; break;
+    case PQC_OP_S: case PQC_OP_T: case PQC_OP_IDENT: c.diag = true; break;
+    case PQC_OP_CNOT: c.mix = m1; break;
+    case PQC_OP_CZ: c.diag = true; break;
+    case PQC_OP_RXX: c.mix = m0 | m1; c.pauli = true; c.px = m0 | m1; break;
+    case PQC_OP_RYY: c.mix = m0 | m1; c.pauli = true; c.px = m0 | m1; c.pz = m0 | m1; break;
+    case PQC_OP_RZZ: c.diag = true; c.pauli = true; c.pz = m0 | m1; break;
+    default: c.mix = m0 | m1; break;   // SQRTISWAP, FSIM, FIXED_FSIM
+  }
+  return c;
+}
+
+bool same_angle(const COp& a, const COp& b) {
+  return a.param == b.param && a.scale == b.scale && a.offset == b.offset;
+}
+
+// fuse inside one reference gate (same `group`) when all its members commute
+void fuse_group(std::vector<COp>& run) {
+  if (run.size() < 2) return;
+  for (auto& a : run)
+    if (!a.pauli) return;
+  for (size_t i = 0; i < run.size(); ++i)
+    for (size_t j = i + 1; j < run.size(); ++j)
+      if (!commute(run[i], run[j])) return;
+  std::vector<bool> dead(run.size(), false);
+  // same-angle R_zz sets -> ZZSUM
+  for (size_t i = 0; i < run.size(); ++i) {
+    if (dead[i] || run[i].kind != PQC_OP_RZZ) continue;
+    std::vector<size_t> mem;
+    for (size_t j = i; j < run.size(); ++j)
+      if (!dead[j] && run[j].kind == PQC_OP_RZZ && same_angle(run[i], run[j])) mem.push_back(j);
+    if (mem.size() < 2 || mem.size() > 48) continue;
+    bool dup = false;                      // RR_block on 2 qubits lists its pair twice (quirk Q9)
+    for (size_t u = 0; u < mem.size(); ++u)
+      for (size_t v = u + 1; v < mem.size(); ++v)
+        if (run[mem[u]].support == run[mem[v]].support) dup = true;
+    if (dup) continue;
+    COp z = run[i];
+    z.kind = PQC_K_ZZSUM;
+    z.pauli = false;
+    z.diag = true;
+    z.mix = 0;
+    z.support = 0;
+    for (size_t j : mem) {
+      z.pairs.push_back({run[j].b0, run[j].b1});
+      z.support |= run[j].support;
+      if (j != i) dead[j] = true;
+    }
+    run[i] = z;
+  }
+  // R_yy * R_xx on the same pair with the same angle -> RXY
+  for (size_t i = 0; i < run.size(); ++i) {
+    if (dead[i] || run[i].kind != PQC_OP_RYY) continue;
+    for (size_t j = 0; j < run.size(); ++j) {
+      if (dead[j] || run[j].kind != PQC_OP_RXX || !same_angle(run[i], run[j])) continue;
+      if (run[i].support != run[j].support) continue;
+      run[i].kind = PQC_K_RXY;
+      run[i].two = true;
+      run[i].px2 = run[j].px;
+      run[i].pz2 = run[j].pz;
+      dead[j] = true;
+      break;
+    }
+  }
+  std::vector<COp> out;
+  for (size_t i = 0; i < run.size(); ++i)
+    if (!dead[i]) out.push_back(run[i]);
+  run.swap(out);
+}
+
+int trig_entries(const COp& c) {
+  switch (c.kind) {
+    case PQC_OP_RX: case PQC_OP_RY: case PQC_OP_RZ: case PQC_OP_RXX: case PQC_OP_RYY:
+    case PQC_OP_RZZ: case PQC_K_RXY: return 1;
+    case PQC_OP_FSIM: case PQC_OP_FIXED_FSIM: return 2;
+    case PQC_K_ZZSUM: return (int)c.pairs.size() + 1;
+    default: return 0;
+  }
+}
+
+struct Builder {
+  const pqc_program* prog;
+  int n, cap, ipc;                         // qubits, tile amplitude bits, items per CTA
+  std::vector<MOp>& mops;
+  std::vector<SweepD>& sweeps;
+  std::vector<TrigJob>& tjobs;
+  std::vector<ZZTerm>& zz;
+  std::vector<V1Pass>& passes;
+
+  // current pass
+  uint32_t tile = 0;
+  std::vector<int> grp[3];
+  int grp_of[32];
+  // pre/post: index permutations (X, CNOT) folded into the sweep's load / store addresses
+  struct SW { int g; std::vector<MOp> pre, ops, post; };
+  std::vector<SW> sws;
+  std::vector<TrigJob> tj;
+  int ntrig = 0;
+  std::vector<int> spawn_param;
+  bool open = false;
+  int nmops_cur = 0;
+
+  uint32_t lowmask() const { return n >= 4 ? 0xfu : ((1u << n) - 1u); }
+
+  void begin() {
+    tile = 0;
+    for (auto& g : grp) g.clear();
+    for (int& g : grp_of) g = -1;
+    sws.clear();
+    tj.clear();
+    ntrig = 0;
+    spawn_param.clear();
+    open = true;
+    nmops_cur = 0;
+  }
+  int unassigned_low() const {
+    int c = 0;
+    for (int b = 0; b < 4 && b < n; ++b) c += grp_of[b] < 0;
+    return c;
+  }
+  int room(int g, uint32_t need) const {   // free slots of group g for bits of `need`
+    int r = 4 - (int)grp[g].size();
+    if (g == 0) {                          // keep space for low bits that are still unplaced
+      int res = 0;
+      for (int b = 0; b < 4 && b < n; ++b) res += (grp_of[b] < 0) && !((need >> b) & 1u);
+      r -= res;
+    }
+    return r;
+  }
+  // group an op with mixing bits `need` would go to; -1 if it does not fit this pass
+  int target_group(uint32_t need) const {
+    if (__builtin_popcount(tile | need | lowmask()) > cap) return -1;
+    int g = -1, fresh = 0;
+    for (int b = 0; b < n; ++b)
+      if ((need >> b) & 1u) {
+        if (grp_of[b] >= 0) {
+          if (g >= 0 && g != grp_of[b]) return -1;
+          g = grp_of[b];
+        } else {
+          ++fresh;
+        }
+      }
+    if (g >= 0) return room(g, need) >= fresh ? g : -1;
+    const int cur = sws.empty() ? -1 : sws.back().g;
+    if (cur >= 0 && room(cur, need) >= fresh) return cur;
+    const bool all_low = (need & ~lowmask()) == 0;
+    const int order_low[3] = {0, 1, 2}, order_hi[3] = {2, 1, 0};
+    for (int i = 0; i < 3; ++i) {
+      const int c = all_low ? order_low[i] : order_hi[i];
+      if (room(c, need) >= fresh) return c;
+    }
+    return -1;
+  }
+  bool trig_fits(const COp& c) const { return (ntrig + trig_entries(c)) * ipc <= 2048; }
+
+  int priority(const COp& c) const {       // lower is better; 99 = cannot take now
+    if (!trig_fits(c) || sws.size() >= 30 || nmops_cur >= 150) return 99;
+    if (!c.mix) return 0;
+    const int g = target_group(c.mix);
+    if (g < 0) return 99;
+    const bool perm = c.kind == PQC_OP_X || c.kind == PQC_OP_CNOT;
+    if (!sws.empty() && (sws.back().g == g || sws.back().g < 0) &&
+        (perm || sws.back().post.empty()))
+      return 1;
+    bool assigned = false;
+    for (int b = 0; b < n; ++b)
+      if (((c.mix >> b) & 1u) && grp_of[b] >= 0) assigned = true;
+    return assigned ? 2 : 3;
+  }
+
+  MOp proto(const COp& c) {
+    MOp m;
+    memset(&m, 0, sizeof(m));
+    m.kind = c.kind;
+    m.b0 = c.b0;
+    m.b1 = c.b1;
+    m.k0 = m.k1 = m.l0 = m.l1 = -1;
+    m.trig = -1;
+    const int te = trig_entries(c);
+    if (te) {
+      m.trig = ntrig;
+      TrigJob j;
+      memset(&j, 0, sizeof(j));
+      j.kind = c.kind;
+      j.param = c.param;
+      j.param2 = c.param2;
+      j.slot = ntrig;
+      j.npairs = (int)c.pairs.size();
+      j.scale = c.scale;
+      j.offset = c.offset;
+      tj.push_back(j);
+      ntrig += te;
+    }
+    if (c.kind == PQC_K_ZZSUM) {
+      m.npairs = (int)c.pairs.size();
+      m.aux0 = (int)zz.size();
+      // group the pairs by bit distance: count += popc((x ^ (x >> d)) & mask_d)
+      std::vector<std::pair<int, uint32_t>> terms;
+      for (auto& pr : c.pairs) {
+        const int lo = std::min(pr.first, pr.second), d = std::abs(pr.first - pr.second);
+        bool found = false;
+        for (auto& t : terms)
+          if (t.first == d) { t.second |= 1u << lo; found = true; }
+        if (!found) terms.push_back({d, 1u << lo});
+      }
+      for (auto& t : terms) zz.push_back(ZZTerm{t.second, t.first});
+      m.aux1 = (int)terms.size();
+    }
+    return m;
+  }
+
+  void take(const COp& c) {
+    MOp m = proto(c);
+    ++nmops_cur;
+    if (!c.mix) {
+      if (sws.empty() || !sws.back().post.empty()) sws.push_back(SW{-1, {}, {}, {}});
+      sws.back().ops.push_back(m);
+      return;
+    }
+    const bool perm = c.kind == PQC_OP_X || c.kind == PQC_OP_CNOT;
+    const int g = target_group(c.mix);
+    for (int b = 0; b < n; ++b)
+      if (((c.mix >> b) & 1u) && grp_of[b] < 0) {
+        grp_of[b] = g;
+        grp[g].push_back(b);
+      }
+    tile |= c.mix;
+    if (!sws.empty() && sws.back().g < 0) sws.back().g = g;
+    if (sws.empty() || sws.back().g != g || (!perm && !sws.back().post.empty()))
+      sws.push_back(SW{g, {}, {}, {}});
+    SW& sw = sws.back();
+    if (!perm) sw.ops.push_back(m);
+    else if (sw.ops.empty() && sw.post.empty()) sw.pre.push_back(m);
+    else sw.post.push_back(m);
+  }
+
+  void take_gen(int param) {               // in-pass diagonal generator multiply
+    MOp m;
+    memset(&m, 0, sizeof(m));
+    m.kind = PQC_K_GEN;
+    m.k0 = m.k1 = m.l0 = m.l1 = m.b0 = m.b1 = -1;
+    m.trig = -1;
+    m.aux0 = (int)spawn_param.size();
+    spawn_param.push_back(param);
+    ++nmops_cur;
+    if (sws.empty() || !sws.back().post.empty()) sws.push_back(SW{-1, {}, {}, {}});
+    sws.back().ops.push_back(m);
+  }
+
+  int close() {                            // -> index of the finished pass
+    // place the low bits, then fill the tile with the lowest unused global bits
+    auto place = [&](int b) {
+      const int pref[3] = {0, 1, 2};
+      for (int i = 0; i < 3; ++i)
+        if ((int)grp[pref[i]].size() < 4) {
+          grp_of[b] = pref[i];
+          grp[pref[i]].push_back(b);
+          tile |= 1u << b;
+          return;
+        }
+    };
+    for (int b = 0; b < 4 && b < n; ++b)
+      if (grp_of[b] < 0) place(b);
+    for (int b = 0; b < n && __builtin_popcount(tile) < cap; ++b)
+      if (grp_of[b] < 0) place(b);
+    V1Pass ps;
+    memset(ps.lbit, 0, sizeof(ps.lbit));
+    memset(ps.obit, 0, sizeof(ps.obit));
+    ps.tb = cap;
+    int lpos[32];
+    for (int& v : lpos) v = -1;
+    int pos = 0;
+    int gfirst[3], gcount[3];
+    for (int g = 0; g < 3; ++g) {
+      std::sort(grp[g].begin(), grp[g].end());
+      gfirst[g] = pos;
+      gcount[g] = (int)grp[g].size();
+      for (int b : grp[g]) {
+        lpos[b] = pos;
+        ps.lbit[pos++] = b;
+      }
+    }
+    int o = 0;
+    for (int b = 0; b < n; ++b)
+      if (lpos[b] < 0) ps.obit[o++] = b;
+    ps.low_run = 0;
+    while (ps.low_run < cap && ps.lbit[ps.low_run] == ps.low_run) ps.low_run++;
+    ps.direct_ok = (n >= V1_LOCAL_BITS) && gcount[0] == 4 && ps.low_run >= 4;
+    if (sws.empty()) sws.push_back(SW{-1, {}, {}, {}});
+    ps.sweep_off = (int)sweeps.size();
+    ps.mop_off = (int)mops.size();
+    for (size_t si = 0; si < sws.size(); ++si) {
+      SW& sw = sws[si];
+      if (sw.g < 0) sw.g = gcount[2] ? 2 : (gcount[1] ? 1 : 0);
+      SweepD d;
+      memset(&d, 0, sizeof(d));
+      std::vector<int> rb;
+      for (int b : grp[sw.g]) rb.push_back(lpos[b]);
+      // fewer than 4 bits in the group (n < 12): borrow neighbouring amplitude positions
+      for (int g2 = 1; g2 <= 2 && rb.size() < 4; ++g2) {
+        const int gg = (sw.g + g2) % 3;
+        for (int i = gcount[gg] - 1; i >= 0 && rb.size() < 4; --i) rb.push_back(gfirst[gg] + i);
+      }
+      std::sort(rb.begin(), rb.end());
+      for (int k = 0; k < 4; ++k) d.rb[k] = rb[k];
+      d.mop_begin = (int)mops.size() - ps.mop_off;
+      auto emit = [&](std::vector<MOp>& list) {
+        for (MOp m : list) {
+          auto fill = [&](int b, int& k, int& l) {
+            if (b < 0) return;
+            l = lpos[b];
+            k = -1;
+            for (int q = 0; q < 4; ++q)
+              if (l >= 0 && d.rb[q] == l) k = q;
+          };
+          fill(m.b0, m.k0, m.l0);
+          fill(m.b1, m.k1, m.l1);
+          mops.push_back(m);
+        }
+      };
+      emit(sw.pre);
+      {
+        // resolve register-bit indices, then pack runs of RX / RY / H into LAYER1Q macro-ops
+        const size_t at = mops.size();
+        emit(sw.ops);
+        std::vector<MOp> packed;
+        for (size_t q = at; q < mops.size(); ++q) {
+          const MOp& m = mops[q];
+          const bool oneq = m.kind == PQC_OP_RX || m.kind == PQC_OP_RY || m.kind == PQC_OP_H;
+          if (!oneq) { packed.push_back(m); continue; }
+          const int lk = m.kind == PQC_OP_RX ? PQC_K_LAYER_RX4 : PQC_K_LAYER_REAL4;
+          if (packed.empty() || packed.back().kind != lk ||
+              ((packed.back().subk >> (8 * m.k0)) & 0xff)) {
+            MOp L;
+            memset(&L, 0, sizeof(L));
+            L.kind = lk;
+            L.k0 = L.k1 = L.l0 = L.l1 = L.b0 = L.b1 = -1;
+            L.trig = -1;
+            packed.push_back(L);
+          }
+          packed.back().subk |= (m.kind + 1) << (8 * m.k0);
+          packed.back().subt[m.k0] = m.trig < 0 ? 0 : m.trig;
+        }
+        mops.resize(at);
+        for (auto& m : packed) mops.push_back(m);
+      }
+      emit(sw.post);
+      d.mop_end = (int)mops.size() - ps.mop_off;
+      d.pad = (int)sw.pre.size() | ((int)sw.post.size() << 16);
+      const bool touches_low = d.rb[0] < 4;
+      if (ps.direct_ok && !touches_low) {
+        if (si == 0) d.io |= 1;
+        if (si + 1 == sws.size()) d.io |= 2;
+      }
+      sweeps.push_back(d);
+    }
+    ps.nsweeps = (int)sws.size();
+    ps.nmops = (int)mops.size() - ps.mop_off;
+    ps.io_first = sweeps[ps.sweep_off].io;
+    ps.io_last = sweeps[ps.sweep_off + ps.nsweeps - 1].io;
+    ps.tj_off = (int)tjobs.size();
+    for (auto& j : tj) tjobs.push_back(j);
+    ps.ntjobs = (int)tj.size();
+    ps.ntrig = std::max(1, ntrig);
+    ps.spawn_param = spawn_param;
+    passes.push_back(ps);
+    open = false;
+    return (int)passes.size() - 1;
+  }
+};
+
+}  // namespace
+
+int pqc_plan_v1(pqc_program* prog) {
+  const int n = prog->n, P = prog->P;
+  prog->v1_ok = prog->v1_grad_ok = false;
+  if (n < 8) return 0;                      // tiny circuits stay on the v0 tile kernel
+  // ---- canonical ops: per-gate fusion --------------------------------------------------
+  std::vector<COp> cops;
+  {
+    std::vector<COp> run;
+    int cur = -2;
+    auto flush = [&]() {
+      fuse_group(run);
+      for (auto& c : run) cops.push_back(c);
+      run.clear();
+    };
+    for (const pqc_op& op : prog->ops) {
+      if (op.group != cur) {
+        flush();
+        cur = op.group;
+      }
+      run.push_back(make_cop(op, n));
+    }
+    flush();
+  }
+  // ---- mutually commuting blocks ----------------------------------------------------------
+  std::vector<int> block_of(cops.size(), 0);
+  std::vector<std::vector<int>> blocks;
+  for (size_t i = 0; i < cops.size(); ++i) {
+    bool ok = !blocks.empty();
+    if (ok)
+      for (int j : blocks.back())
+        if (!commute(cops[i], cops[j])) { ok = false; break; }
+    if (!ok) blocks.push_back({});
+    blocks.back().push_back((int)i);
+    block_of[i] = (int)blocks.size() - 1;
+  }
+  // ---- parameters: block and generator type -------------------------------------------------
+  std::vector<int> param_block(P, -1);
+  bool grad_ok = prog->grad_supported;
+  for (size_t i = 0; i < cops.size() && grad_ok; ++i)
+    for (int p : {cops[i].param, cops[i].param2})
+      if (p >= 0) {
+        if (param_block[p] < 0) param_block[p] = block_of[i];
+        else if (param_block[p] != block_of[i]) grad_ok = false;   // spans blocks: keep v0
+      }
+  for (int p = 0; p < P && grad_ok; ++p)
+    if (param_block[p] < 0) grad_ok = false;
+  for (int p = 1; p < P && grad_ok; ++p)
+    if (param_block[p] < param_block[p - 1]) grad_ok = false;
+  std::vector<bool> param_diag(P, true);
+  if (grad_ok)
+    for (int p = 0; p < P; ++p)
+      for (int t = prog->gen_off[p]; t < prog->gen_off[p + 1]; ++t)
+        if (prog->gens[t].xmask) param_diag[p] = false;
+
+  std::vector<MOp> mops;
+  std::vector<SweepD> sweeps;
+  std::vector<TrigJob> tjobs;
+  std::vector<ZZTerm> zz;
+  const int cap = std::min(n, V1_LOCAL_BITS);
+  const int ipc = 1 << (V1_LOCAL_BITS - cap);
+
+  // one planning routine, with or without derivative markers
+  auto plan = [&](bool markers, std::vector<int>* run_out, std::vector<V1Stage>* stages) {
+    Builder B{prog, n, cap, ipc, mops, sweeps, tjobs, zz, prog->v1_passes};
+    std::vector<bool> spawned(P, false);
+    std::vector<int> pending_dots;
+    const bool onload = (ipc == 1);
+    auto emit_pass = [&]() {
+      const int idx = B.close();
+      if (run_out) run_out->push_back(idx);
+      if (stages) {
+        V1Stage st;
+        st.type = 0;
+        st.pass = idx;
+        if (onload) {
+          while (!pending_dots.empty() && (int)st.partners.size() < V1_MAX_PART) {
+            st.partners.push_back(pending_dots.front());
+            pending_dots.erase(pending_dots.begin());
+          }
+        }
+        if (!pending_dots.empty()) {            // overflow or packed items: standalone dots first
+          V1Stage d;
+          d.type = 2;
+          d.partners = pending_dots;
+          pending_dots.clear();
+          stages->push_back(d);
+        }
+        stages->push_back(st);
+        for (int p : prog->v1_passes[idx].spawn_param) pending_dots.push_back(p);
+      }
+    };
+    auto gather = [&](const std::vector<int>& ps) {
+      if (ps.empty() || !stages) return;
+      V1Stage st;
+      st.type = 1;
+      st.gather_params = ps;
+      stages->push_back(st);
+      for (int p : ps) pending_dots.push_back(p);
+    };
+    for (size_t bi = 0; bi < blocks.size(); ++bi) {
+      std::vector<int> todo = blocks[bi];
+      while (!todo.empty()) {
+        if (!B.open) B.begin();
+        int best = -1, bestp = 99;
+        for (size_t k = 0; k < todo.size(); ++k) {
+          const int pr = B.priority(cops[todo[k]]);
+          if (pr < bestp) { bestp = pr; best = (int)k; }
+          if (pr == 0) break;
+        }
+        if (best < 0) {
+          // natural boundary inside the block: every not-yet-spawned parameter of this block
+          // may be spawned here because its generator commutes with the rest of the block
+          emit_pass();
+          if (markers) {
+            std::vector<int> ps;
+            for (int p = 0; p < P; ++p)
+              if (param_block[p] == (int)bi && !spawned[p]) { ps.push_back(p); spawned[p] = true; }
+            gather(ps);
+          }
+          continue;
+        }
+        B.take(cops[todo[best]]);
+        todo.erase(todo.begin() + best);
+      }
+      if (markers) {
+        // block exhausted: diagonal generators are multiplied inside the pass ...
+        std::vector<int> nd;
+        for (int p = 0; p < P; ++p)
+          if (param_block[p] == (int)bi && !spawned[p]) {
+            if (param_diag[p] && onload) {
+              if (!B.open) B.begin();
+              if ((int)B.spawn_param.size() >= V1_MAX_SPAWN) { emit_pass(); B.begin(); }
+              B.take_gen(p);
+              spawned[p] = true;
+            } else {
+              nd.push_back(p);
+            }
+          }
+        // ... the others need the complete state: close the pass and gather
+        if (!nd.empty()) {
+          if (B.open) emit_pass();
+          for (int p : nd) spawned[p] = true;
+          gather(nd);
+        }
+      }
+    }
+    if (B.open || (run_out && run_out->empty())) {
+      if (!B.open) B.begin();
+      emit_pass();
+    }
+    if (stages && !pending_dots.empty()) {
+      V1Stage d;
+      d.type = 2;
+      d.partners = pending_dots;
+      stages->push_back(d);
+    }
+  };
+
+  plan(false, &prog->v1_run, nullptr);
+  prog->v1_ok = true;
+  if (grad_ok && P > 0) {
+    plan(true, nullptr, &prog->v1_grad);
+    prog->v1_grad_ok = true;
+  }
+
+  auto upload = [&](auto& vec, auto** dptr) -> int {
+    if (vec.empty()) return 0;
+    PQC_CUDA(cudaMalloc(dptr, vec.size() * sizeof(vec[0])));
+    PQC_CUDA(cudaMemcpy(*dptr, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
+    return 0;
+  };
+  if (upload(mops, &prog->d_mops) || upload(sweeps, &prog->d_sweeps) ||
+      upload(tjobs, &prog->d_tjobs) || upload(zz, &prog->d_zz))
+    return -2;
+  return 0;
+}
+
+// =====================================================================================
+// sweep kernel
+// =====================================================================================
+struct V1Args {
+  const c128* src;           // buffer read by normal items (ping) -- may equal dst (in place)
+  c128* dst;                 // buffer written (pong)
+  const double* angles;
+  long long ld;
+  const MOp* mops;
+  const SweepD* sweeps;
+  int nsweeps;
+  const TrigJob* tjobs;
+  int ntjobs, ntrig;
+  const ZZTerm* zz;
+  const GenTerm* gens;
+  int n, tb, items_log2, low_run;
+  int lbit[V1_LOCAL_BITS];
+  int obit[PQC_MAX_QUBITS];
+  long long n_items;         // samples * (active + nspawn)
+  int slots_total, active, nspawn;
+  int spawn_slot[V1_MAX_SPAWN], spawn_goff[V1_MAX_SPAWN], spawn_gcnt[V1_MAX_SPAWN];
+  int npartners;
+  int partner_slot[V1_MAX_PART];
+  c128* gpart;               // [S][P+1][P][ntiles]
+  int P, ntiles;
+  int sweeps_nmops, sweep0_io, last_io;
+};
+
+__device__ __forceinline__ uint32_t swz(uint32_t i) {
+  return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u);
+}
+
+// ---- pair-mixing micro-ops on the 16 register amplitudes ---------------------------------
+// rx-type update of every pair along register bit K: [[c, -i s], [-i s, c]]
+template <int K>
+__device__ __forceinline__ void op_rx(c128 (&a)[16], double c, double s) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j & (1 << K)) continue;
+    const c128 x = a[j], y = a[j | (1 << K)];
+    a[j] = make_double2(c * x.x + s * y.y, c * x.y - s * y.x);
+    a[j | (1 << K)] = make_double2(c * y.x + s * x.y, c * y.y - s * x.x);
+  }
+}
+// real 2x2 [[p, q], [r, t]] along register bit K (RY: c,-s,s,c; H: h,h,h,-h; identity: 1,0,0,1)
+template <int K>
+__device__ __forceinline__ void op_real(c128 (&a)[16], double p, double q, double r, double t) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j & (1 << K)) continue;
+    const c128 x = a[j], y = a[j | (1 << K)];
+    a[j] = make_double2(p * x.x + q * y.x, p * x.y + q * y.y);
+    a[j | (1 << K)] = make_double2(r * x.x + t * y.x, r * x.y + t * y.y);
+  }
+}
+
+// generic symmetric two-bit rotation: even-parity pair (00,11) by (ce, se), odd-parity pair
+// (01,10) by (co, so), each as [[c, -i s], [-i s, c]]; optional phase (pc - i ps) on |11>.
+template <int KA, int KB>
+__device__ __forceinline__ void op_pair(c128 (&a)[16], double ce, double se, double co, double so,
+                                        bool even, bool ph, double pc, double psn) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j & ((1 << KA) | (1 << KB))) continue;
+    const int j01 = j | (1 << KA), j10 = j | (1 << KB), j11 = j01 | j10;
+    {
+      const c128 x = a[j01], y = a[j10];
+      a[j01] = make_double2(co * x.x + so * y.y, co * x.y - so * y.x);
+      a[j10] = make_double2(co * y.x + so * x.y, co * y.y - so * x.x);
+    }
+    if (even) {
+      const c128 x = a[j], y = a[j11];
+      a[j] = make_double2(ce * x.x + se * y.y, ce * x.y - se * y.x);
+      a[j11] = make_double2(ce * y.x + se * x.y, ce * y.y - se * x.x);
+    }
+    if (ph) {
+      const c128 z = a[j11];
+      a[j11] = make_double2(z.x * pc + z.y * psn, z.y * pc - z.x * psn);
+    }
+  }
+}
+
+// initial state into slot 0 of every sample (mode 1 |0..0>, 2 broadcast, 3 per sample)
+__global__ void __launch_bounds__(256) k_init_slot0(c128* __restrict__ buf, int mode,
+                                                    const c128* __restrict__ init,
+                                                    long long init_stride, long long S,
+                                                    int slots_total, int n) {
+  const long long D = 1ll << n, total = S * D;
+  for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < total;
+       g += (long long)gridDim.x * 256) {
+    const long long s = g >> n, x = g & (D - 1);
+    c128 v;
+    if (mode == 1) v = make_double2(x == 0 ? 1.0 : 0.0, 0.0);
+    else if (mode == 2) v = init[x];
+    else v = init[s * init_stride + x];
+    buf[((s * slots_total) << n) + x] = v;
+  }
+}
+
+#define V1_MAX_MOPS 160
+#define V1_MAX_SWEEPS 32
+
+// DOTS: take Gram partials against `partner_slot[]` while loading; GEN: the pass carries
+// in-pass diagonal-generator spawn items.
+template <bool DOTS, bool GEN>
+__global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  c128* sm = reinterpret_cast<c128*>(smraw);
+  double2* trig = reinterpret_cast<double2*>(sm + (1u << V1_LOCAL_BITS));
+  __shared__ double red[32];
+  __shared__ MOp s_mops[V1_MAX_MOPS];
+  __shared__ SweepD s_sweeps[V1_MAX_SWEEPS];
+  const int tid = threadIdx.x;
+  const int tiles_log2 = A.n - A.tb;
+  const long long blk = blockIdx.x;
+  const long long group = blk >> tiles_log2;
+  const uint32_t tile = (uint32_t)(blk & ((1ll << tiles_log2) - 1));
+  uint32_t tbase = 0;
+  for (int j = 0; j < tiles_log2; ++j) tbase |= ((tile >> j) & 1u) << A.obit[j];
+  const int ipc = 1 << A.items_log2;
+  const long long item0 = group << A.items_log2;
+  const int ips = A.active + A.nspawn;              // items per sample
+  const uint32_t amask = (1u << A.tb) - 1u;
+
+  // ---- stage the micro-program and fill the per-item trig table ------------------------------
+  {
+    const int nm = A.sweeps_nmops;
+    int* d = reinterpret_cast<int*>(s_mops);
+    const int* g = reinterpret_cast<const int*>(A.mops);
+    for (int e = tid; e < nm * (int)(sizeof(MOp) / 4); e += 256) d[e] = g[e];
+    int* d2 = reinterpret_cast<int*>(s_sweeps);
+    const int* g2 = reinterpret_cast<const int*>(A.sweeps);
+    for (int e = tid; e < A.nsweeps * (int)(sizeof(SweepD) / 4); e += 256) d2[e] = g2[e];
+  }
+  for (int e = tid; e < ipc * A.ntjobs; e += 256) {
+    const int li = e / A.ntjobs;
+    const TrigJob jb = A.tjobs[e - li * A.ntjobs];
+    const long long item = item0 + li;
+    if (item >= A.n_items) continue;
+    const long long sample = item / ips;
+    double2* t = trig + (size_t)li * A.ntrig + jb.slot;
+    double th = jb.offset, s, c;
+    if (jb.kind == PQC_OP_FSIM || jb.kind == PQC_OP_FIXED_FSIM) {
+      if (jb.param >= 0) th += A.angles[sample * A.ld + jb.param];
+      sincos(th, &s, &c);
+      t[0] = make_double2(c, s);
+      const double ph = jb.param2 >= 0 ? A.angles[sample * A.ld + jb.param2] : jb.scale;
+      sincos(ph, &s, &c);
+      t[1] = make_double2(c, s);
+    } else {
+      if (jb.param >= 0) th += jb.scale * A.angles[sample * A.ld + jb.param];
+      if (jb.kind == PQC_K_ZZSUM) {
+        // entry[k] = exp(-i th/2 (npairs - 2k)), k = number of anti-aligned pairs
+        for (int k = 0; k <= jb.npairs; ++k) {
+          sincos(-0.5 * th * (double)(jb.npairs - 2 * k), &s, &c);
+          t[k] = make_double2(c, s);
+        }
+      } else if (jb.kind == PQC_K_RXY) {
+        sincos(th, &s, &c);                      // rx-like rotation by the FULL angle
+        t[0] = make_double2(c, s);
+      } else {
+        sincos(0.5 * th, &s, &c);
+        t[0] = make_double2(c, s);
+      }
+    }
+  }
+
+  auto item_info = [&](long long item, long long& sample, int& src_slot, int& dst_slot, int& gen) {
+    sample = item / ips;
+    const int r = (int)(item - sample * ips);
+    if (!GEN || r < A.active) {
+      src_slot = dst_slot = r;
+      gen = -1;
+    } else {
+      src_slot = 0;
+      dst_slot = A.spawn_slot[r - A.active];
+      gen = r - A.active;
+    }
+  };
+  auto local_to_amp = [&](uint32_t i) -> uint32_t {
+    uint32_t r = i & ((1u << A.low_run) - 1u);
+    for (int j = A.low_run; j < A.tb; ++j) r |= ((i >> j) & 1u) << A.lbit[j];
+    return r;
+  };
+
+  const bool direct_load = (A.sweep0_io & 1) != 0;
+  long long my_sample = 0;
+  int my_src = 0, my_dst = 0, my_gen = -1;
+  if (ipc == 1) item_info(item0, my_sample, my_src, my_dst, my_gen);
+
+  // ---- staged load (global -> swizzled shared) when the first sweep cannot load directly -------
+  if (!direct_load) {
+    for (uint32_t i = tid; i < (1u << V1_LOCAL_BITS); i += 256) {
+      const long long item = item0 + (i >> A.tb);
+      c128 v = make_double2(0.0, 0.0);
+      if (item < A.n_items) {
+        long long sample;
+        int ss, ds, gg;
+        item_info(item, sample, ss, ds, gg);
+        v = A.src[((sample * A.slots_total + ss) << A.n) + (tbase | local_to_amp(i & amask))];
+      }
+      sm[swz(i)] = v;
+    }
+    if (DOTS && my_gen < 0) {
+      const c128* own = A.src + ((my_sample * A.slots_total + my_src) << A.n);
+      for (int q = 0; q < A.npartners; ++q) {
+        const int ps = A.partner_slot[q];
+        if (my_src > ps) continue;
+        const c128* pv = A.src + ((my_sample * A.slots_total + ps) << A.n);
+        double re = 0.0, im = 0.0;
+        for (uint32_t i = tid; i < (1u << V1_LOCAL_BITS); i += 256) {
+          const uint32_t amp = tbase | local_to_amp(i);
+          const c128 x = own[amp], y = pv[amp];
+          re += x.x * y.x + x.y * y.y;
+          im += x.x * y.y - x.y * y.x;
+        }
+        re = block_sum<256>(re, red);
+        im = block_sum<256>(im, red);
+        if (tid == 0)
+          A.gpart[((my_sample * (A.P + 1) + my_src) * A.P + (ps - 1)) * A.ntiles + tile] =
+              make_double2(re, im);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- sweeps ------------------------------------------------------------------------------------
+  for (int si = 0; si < A.nsweeps; ++si) {
+    const SweepD sw = s_sweeps[si];
+    const uint32_t m0 = 1u << sw.rb[0], m1 = 1u << sw.rb[1], m2 = 1u << sw.rb[2], m3 = 1u << sw.rb[3];
+    const uint32_t rmask = m0 | m1 | m2 | m3;
+    uint32_t base = 0;
+    {
+      int tb_i = 0;
+#pragma unroll
+      for (int pos = 0; pos < V1_LOCAL_BITS; ++pos)
+        if (!((rmask >> pos) & 1u)) base |= ((tid >> tb_i++) & 1u) << pos;
+    }
+    // swz is linear over GF(2): swz(base | sel) = swz(base) ^ swz(sel)
+    const uint32_t sb = swz(base), s0 = swz(m0), s1 = swz(m1), s2 = swz(m2), s3 = swz(m3);
+    // global amplitude index of register j = amp0 | (selected g-masks)
+    const uint32_t g0 = 1u << A.lbit[sw.rb[0]], g1 = 1u << A.lbit[sw.rb[1]],
+                   g2 = 1u << A.lbit[sw.rb[2]], g3 = 1u << A.lbit[sw.rb[3]];
+    const uint32_t amp0 = tbase | local_to_amp(base & amask);
+    // X / CNOT are affine maps of the 4-bit register index: pi(j) = XOR_{k in j} col[k] ^ v.
+    // They cost nothing per amplitude: they only change the load / store address constants.
+    const int npre = sw.pad & 0xffff, npost = sw.pad >> 16;
+    auto affine = [&](int begin, int end, bool reverse, uint32_t (&col)[4], uint32_t& v) {
+      col[0] = 1u; col[1] = 2u; col[2] = 4u; col[3] = 8u;
+      v = 0u;
+      for (int q = 0; q < end - begin; ++q) {
+        const MOp& pm = s_mops[reverse ? end - 1 - q : begin + q];
+        if (pm.kind == PQC_OP_X) {
+          v ^= 1u << pm.k0;
+        } else if (pm.k0 >= 0) {               // CNOT, control in registers
+          const int kc = pm.k0, kt = pm.k1;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) col[c] ^= ((col[c] >> kc) & 1u) << kt;
+          v ^= ((v >> kc) & 1u) << kt;
+        } else {                               // CNOT, control fixed for this thread
+          const uint32_t cb = pm.l0 >= 0 ? ((base >> pm.l0) & 1u) : ((tbase >> pm.b0) & 1u);
+          v ^= cb << pm.k1;
+        }
+      }
+    };
+#define LIN4(x, a0, a1, a2, a3) \
+  ((((x)&1u) ? (a0) : 0u) ^ (((x)&2u) ? (a1) : 0u) ^ (((x)&4u) ? (a2) : 0u) ^ (((x)&8u) ? (a3) : 0u))
+    const int li = (int)(base >> A.tb);
+    long long sample = my_sample;
+    int src_slot = my_src, dst_slot = my_dst, gen = my_gen;
+    const bool live = item0 + li < A.n_items;
+    if (ipc > 1 && live) item_info(item0 + li, sample, src_slot, dst_slot, gen);
+    const double2* tg = trig + (size_t)li * A.ntrig;
+#define SEL4(j, a0, a1, a2, a3) \
+  ((((j)&1) ? (a0) : 0u) | (((j)&2) ? (a1) : 0u) | (((j)&4) ? (a2) : 0u) | (((j)&8) ? (a3) : 0u))
+#define XSEL4(j, a0, a1, a2, a3) \
+  ((((j)&1) ? (a0) : 0u) ^ (((j)&2) ? (a1) : 0u) ^ (((j)&4) ? (a2) : 0u) ^ (((j)&8) ? (a3) : 0u))
+
+    c128 a[16];
+    const bool dl = si == 0 && direct_load;
+    uint32_t lc[4] = {1u, 2u, 4u, 8u}, lv = 0u;
+    if (npre) affine(sw.mop_begin, sw.mop_begin + npre, true, lc, lv);
+    if (dl) {
+      const uint32_t lgb = amp0 ^ LIN4(lv, g0, g1, g2, g3);
+      const uint32_t lg0 = LIN4(lc[0], g0, g1, g2, g3), lg1 = LIN4(lc[1], g0, g1, g2, g3),
+                     lg2 = LIN4(lc[2], g0, g1, g2, g3), lg3 = LIN4(lc[3], g0, g1, g2, g3);
+      const c128* sp = A.src + ((sample * A.slots_total + src_slot) << A.n);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        a[j] = live ? sp[lgb ^ XSEL4(j, lg0, lg1, lg2, lg3)] : make_double2(0.0, 0.0);
+      if (DOTS && gen < 0) {
+        for (int q = 0; q < A.npartners; ++q) {
+          const int ps = A.partner_slot[q];
+          if (src_slot > ps) continue;               // uniform per CTA
+          const c128* pv = A.src + ((sample * A.slots_total + ps) << A.n);
+          double re = 0.0, im = 0.0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const c128 y = pv[lgb ^ XSEL4(j, lg0, lg1, lg2, lg3)];
+            re += a[j].x * y.x + a[j].y * y.y;
+            im += a[j].x * y.y - a[j].y * y.x;
+          }
+          re = block_sum<256>(re, red);
+          im = block_sum<256>(im, red);
+          if (tid == 0)
+            A.gpart[((sample * (A.P + 1) + src_slot) * A.P + (ps - 1)) * A.ntiles + tile] =
+                make_double2(re, im);
+        }
+      }
+    } else {
+      const uint32_t lsb = sb ^ LIN4(lv, s0, s1, s2, s3);
+      const uint32_t ls0 = LIN4(lc[0], s0, s1, s2, s3), ls1 = LIN4(lc[1], s0, s1, s2, s3),
+                     ls2 = LIN4(lc[2], s0, s1, s2, s3), ls3 = LIN4(lc[3], s0, s1, s2, s3);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a[j] = sm[lsb ^ XSEL4(j, ls0, ls1, ls2, ls3)];
+    }
+
+    for (int mi = sw.mop_begin + npre; mi < sw.mop_end - npost; ++mi) {
+      const MOp& m = s_mops[mi];
+      const int kind = m.kind;
+      if (kind == PQC_K_LAYER_RX4) {
+        // straight-line over the 4 register bits; absent gates are the identity (c 1, s 0)
+        const int sk = m.subk;
+        double2 c0 = make_double2(1.0, 0.0), c1 = c0, c2 = c0, c3 = c0;
+        if (sk & 0xff) c0 = tg[m.subt[0]];
+        if (sk & 0xff00) c1 = tg[m.subt[1]];
+        if (sk & 0xff0000) c2 = tg[m.subt[2]];
+        if (sk & 0xff000000) c3 = tg[m.subt[3]];
+        op_rx<0>(a, c0.x, c0.y);
+        op_rx<1>(a, c1.x, c1.y);
+        op_rx<2>(a, c2.x, c2.y);
+        op_rx<3>(a, c3.x, c3.y);
+      } else if (kind == PQC_K_LAYER_REAL4) {
+        const int sk = m.subk;
+        const double h = 0.70710678118654752440;
+#define REAL_SLOT(K)                                                            \
+  {                                                                             \
+    const int kd = ((sk >> (8 * K)) & 0xff) - 1;                                \
+    double p = 1.0, q = 0.0, r = 0.0, t = 1.0;                                  \
+    if (kd == PQC_OP_RY) { const double2 cs = tg[m.subt[K]]; p = cs.x; q = -cs.y; r = cs.y; t = cs.x; } \
+    else if (kd == PQC_OP_H) { p = h; q = h; r = h; t = -h; }                    \
+    op_real<K>(a, p, q, r, t);                                                   \
+  }
+        REAL_SLOT(0) REAL_SLOT(1) REAL_SLOT(2) REAL_SLOT(3)
+#undef REAL_SLOT
+      } else if (kind == PQC_K_ZZSUM) {
+        // count of anti-aligned pairs; <= 4 (mask, shift) terms, loaded once
+        uint32_t zm[4];
+        int zs[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const bool on = t < m.aux1;
+          const ZZTerm z = A.zz[m.aux0 + (on ? t : 0)];
+          zm[t] = on ? z.mask : 0u;
+          zs[t] = z.shift;
+        }
+        const double2* tz = tg + m.trig;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t x = amp0 | SEL4(j, g0, g1, g2, g3);
+          int cnt = __popc((x ^ (x >> zs[0])) & zm[0]) + __popc((x ^ (x >> zs[1])) & zm[1]);
+          if (m.aux1 > 2) cnt += __popc((x ^ (x >> zs[2])) & zm[2]) + __popc((x ^ (x >> zs[3])) & zm[3]);
+          const double2 ph = tz[cnt];
+          const c128 v = a[j];
+          a[j] = make_double2(v.x * ph.x - v.y * ph.y, v.y * ph.x + v.x * ph.y);
+        }
+      } else if (kind == PQC_OP_RZ || kind == PQC_OP_S || kind == PQC_OP_T) {
+        double c = 1.0, s = 0.0;
+        if (kind == PQC_OP_RZ) { const double2 cs = tg[m.trig]; c = cs.x; s = cs.y; }
+        const int cb = m.l0 >= 0 ? (int)((base >> m.l0) & 1u) : (int)((tbase >> m.b0) & 1u);
+        const int k0 = m.k0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int bit = k0 >= 0 ? ((j >> k0) & 1) : cb;
+          c128 v = a[j];
+          if (kind == PQC_OP_RZ) {
+            const double sg = bit ? s : -s;
+            v = make_double2(v.x * c - v.y * sg, v.y * c + v.x * sg);
+          } else if (bit) {
+            if (kind == PQC_OP_S) {
+              v = make_double2(-v.y, v.x);
+            } else {
+              const double r = 0.70710678118654752440;
+              v = make_double2(r * (v.x - v.y), r * (v.x + v.y));
+            }
+          }
+          a[j] = v;
+        }
+      } else if (kind == PQC_OP_CZ || kind == PQC_OP_RZZ) {
+        double c = 1.0, s = 0.0;
+        if (kind == PQC_OP_RZZ) { const double2 cs = tg[m.trig]; c = cs.x; s = cs.y; }
+        const int ca = m.l0 >= 0 ? (int)((base >> m.l0) & 1u) : (int)((tbase >> m.b0) & 1u);
+        const int cb = m.l1 >= 0 ? (int)((base >> m.l1) & 1u) : (int)((tbase >> m.b1) & 1u);
+        const int k0 = m.k0, k1 = m.k1;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int ba = k0 >= 0 ? ((j >> k0) & 1) : ca;
+          const int bb = k1 >= 0 ? ((j >> k1) & 1) : cb;
+          c128 v = a[j];
+          if (kind == PQC_OP_CZ) {
+            if (ba & bb) v = make_double2(-v.x, -v.y);
+          } else {
+            const double sg = (ba ^ bb) ? s : -s;
+            v = make_double2(v.x * c - v.y * sg, v.y * c + v.x * sg);
+          }
+          a[j] = v;
+        }
+      } else if (kind == PQC_K_GEN) {
+        if (GEN && gen == m.aux0) {
+          // uniform-coefficient diagonal generator: c0 * sum_t (-1)^{popc(x & z_t)}
+          const int goff = A.spawn_goff[gen], gcnt = A.spawn_gcnt[gen];
+          int sg[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sg[j] = 0;
+          for (int t = 0; t < gcnt; ++t) {
+            const uint32_t zmask = A.gens[goff + t].zmask;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              sg[j] += 1 - 2 * (__popc((amp0 | SEL4(j, g0, g1, g2, g3)) & zmask) & 1);
+          }
+          const double cr = A.gens[goff].re, ci = A.gens[goff].im;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const double f = (double)sg[j];
+            const c128 v = a[j];
+            a[j] = make_double2(f * (v.x * cr - v.y * ci), f * (v.y * cr + v.x * ci));
+          }
+        }
+      } else if (kind != PQC_OP_IDENT) {
+        // symmetric two-bit rotations, both bits in registers
+        double ce = 1.0, se = 0.0, co = 1.0, so = 0.0, pc = 1.0, psn = 0.0;
+        bool even = false, ph = false;
+        if (kind == PQC_OP_RXX) { const double2 cs = tg[m.trig]; ce = co = cs.x; se = so = cs.y; even = true; }
+        else if (kind == PQC_OP_RYY) { const double2 cs = tg[m.trig]; ce = co = cs.x; so = cs.y; se = -cs.y; even = true; }
+        else if (kind == PQC_K_RXY) { const double2 cs = tg[m.trig]; co = cs.x; so = cs.y; }
+        else if (kind == PQC_OP_SQRTISWAP) { co = 0.70710678118654752440; so = -co; }
+        else { const double2 cs = tg[m.trig]; co = cs.x; so = cs.y;
+               if (kind == PQC_OP_FSIM) { const double2 p2 = tg[m.trig + 1]; pc = p2.x; psn = p2.y; ph = true; } }
+        const int ka = m.k0 < m.k1 ? m.k0 : m.k1, kb = m.k0 < m.k1 ? m.k1 : m.k0;
+        switch (ka * 4 + kb) {
+          case 1: op_pair<0, 1>(a, ce, se, co, so, even, ph, pc, psn); break;
+          case 2: op_pair<0, 2>(a, ce, se, co, so, even, ph, pc, psn); break;
+          case 3: op_pair<0, 3>(a, ce, se, co, so, even, ph, pc, psn); break;
+          case 6: op_pair<1, 2>(a, ce, se, co, so, even, ph, pc, psn); break;
+          case 7: op_pair<1, 3>(a, ce, se, co, so, even, ph, pc, psn); break;
+          default: op_pair<2, 3>(a, ce, se, co, so, even, ph, pc, psn); break;
+        }
+      }
+    }
+
+    const bool ds = (si + 1 == A.nsweeps) && (sw.io & 2);
+    uint32_t sc[4] = {1u, 2u, 4u, 8u}, sv = 0u;
+    if (npost) affine(sw.mop_end - npost, sw.mop_end, false, sc, sv);
+    if (ds) {
+      const uint32_t sgb = amp0 ^ LIN4(sv, g0, g1, g2, g3);
+      const uint32_t sg0 = LIN4(sc[0], g0, g1, g2, g3), sg1 = LIN4(sc[1], g0, g1, g2, g3),
+                     sg2 = LIN4(sc[2], g0, g1, g2, g3), sg3 = LIN4(sc[3], g0, g1, g2, g3);
+      if (live) {
+        c128* dp = A.dst + ((sample * A.slots_total + dst_slot) << A.n);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dp[sgb ^ XSEL4(j, sg0, sg1, sg2, sg3)] = a[j];
+      }
+    } else {
+      const uint32_t ssb = sb ^ LIN4(sv, s0, s1, s2, s3);
+      const uint32_t ss0 = LIN4(sc[0], s0, s1, s2, s3), ss1 = LIN4(sc[1], s0, s1, s2, s3),
+                     ss2 = LIN4(sc[2], s0, s1, s2, s3), ss3 = LIN4(sc[3], s0, s1, s2, s3);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sm[ssb ^ XSEL4(j, ss0, ss1, ss2, ss3)] = a[j];
+      __syncthreads();
+    }
+  }
+
+  // ---- staged store -------------------------------------------------------------------------------
+  if (!(A.last_io & 2)) {
+    for (uint32_t i = tid; i < (1u << V1_LOCAL_BITS); i += 256) {
+      const long long item = item0 + (i >> A.tb);
+      if (item < A.n_items) {
+        long long sample;
+        int ss, ds, gg;
+        item_info(item, sample, ss, ds, gg);
+        A.dst[((sample * A.slots_total + ds) << A.n) + (tbase | local_to_amp(i & amask))] = sm[swz(i)];
+      }
+    }
+  }
+}
+
+// =====================================================================================
+// tile gather: dst slot <- (sum of Pauli terms) src slot 0, for one or more parameters.
+// One CTA per (sample, 4096-amplitude chunk); the chunk of psi sits in shared memory, terms
+// flipping only low bits read it from there, the others from global / L2.
+// =====================================================================================
+struct GatherArgs {
+  c128* buf;
+  int n, cb, slots_total;
+  int nparams;
+  int slot[V1_MAX_SPAWN], goff[V1_MAX_SPAWN], gcnt[V1_MAX_SPAWN];
+  const GenTerm* gens;
+};
+
+__global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs A) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  c128* sm = reinterpret_cast<c128*>(smraw);
+  const int chunks_log2 = A.n - A.cb;
+  const long long s = blockIdx.x >> chunks_log2;
+  const uint32_t c0 = (uint32_t)(blockIdx.x & ((1ll << chunks_log2) - 1)) << A.cb;
+  const uint32_t csize = 1u << A.cb;
+  const c128* psi = A.buf + ((s * A.slots_total) << A.n);
+  for (uint32_t i = threadIdx.x; i < csize; i += 256) sm[i] = psi[c0 + i];
+  __syncthreads();
+  for (int p = 0; p < A.nparams; ++p) {
+    c128* out = A.buf + ((s * A.slots_total + A.slot[p]) << A.n);
+    for (uint32_t i = threadIdx.x; i < csize; i += 256) {
+      const uint32_t y = c0 + i;
+      double re = 0.0, im = 0.0;
+      for (int t = 0; t < A.gcnt[p]; ++t) {
+        const GenTerm g = A.gens[A.goff[p] + t];
+        const uint32_t x = y ^ g.xmask;
+        const c128 v = (g.xmask >> A.cb) ? psi[x] : sm[x - c0];
+        int ph = (__popc(g.xmask & g.zmask) + 2 * __popc(x & g.zmask)) & 3;
+        c128 w;
+        if (ph == 0) w = v;
+        else if (ph == 1) w = make_double2(-v.y, v.x);
+        else if (ph == 2) w = make_double2(-v.x, -v.y);
+        else w = make_double2(v.y, -v.x);
+        re += g.re * w.x - g.im * w.y;
+        im += g.re * w.y + g.im * w.x;
+      }
+      out[y] = make_double2(re, im);
+    }
+  }
+}
+
+// standalone Gram columns: one CTA per (sample, row j, partner); writes the sum into tile 0 of
+// the partial array and zeroes the other tiles so the reducer stays uniform.
+__global__ void __launch_bounds__(256) k_multi_dots(const c128* __restrict__ buf, int n,
+                                                    int slots_total, int rows, int npart,
+                                                    const int* __restrict__ partner_slot_dev,
+                                                    V1Args A) {
+  __shared__ double red[32];
+  const long long D = 1ll << n;
+  long long b = blockIdx.x;
+  const int q = (int)(b % npart);
+  b /= npart;
+  const int j = (int)(b % rows);
+  const long long s = b / rows;
+  const int ps = A.partner_slot[q];
+  if (j > ps) return;
+  const c128* x = buf + ((s * slots_total + j) << n);
+  const c128* y = buf + ((s * slots_total + ps) << n);
+  double re = 0.0, im = 0.0;
+  for (long long i = threadIdx.x; i < D; i += 256) {
+    const c128 u = x[i], v = y[i];
+    re += u.x * v.x + u.y * v.y;
+    im += u.x * v.y - u.y * v.x;
+  }
+  re = block_sum<256>(re, red);
+  im = block_sum<256>(im, red);
+  if (threadIdx.x == 0) {
+    c128* g = A.gpart + ((s * (A.P + 1) + j) * A.P + (ps - 1)) * A.ntiles;
+    g[0] = make_double2(re, im);
+    for (int t = 1; t < A.ntiles; ++t) g[t] = make_double2(0.0, 0.0);
+  }
+}
+
+// F_pq = 4 Re(G_pq - conj(s_p) s_q), p <= q, mirrored (measure.py:55-70), G summed over tiles
+// in a fixed order (bitwise reproducible).
+__global__ void k_qfim_reduce(const c128* __restrict__ gpart, long long S, int P, int ntiles,
+                              double* __restrict__ F) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S * P * P) return;
+  const long long s = e / ((long long)P * P);
+  const int r = (int)((e / P) % P), c = (int)(e % P);
+  const int p = r < c ? r : c, q = r < c ? c : r;
+  auto G = [&](int row, int col) -> c128 {
+    const c128* g = gpart + ((s * (P + 1) + row) * P + col) * ntiles;
+    double re = 0.0, im = 0.0;
+    for (int t = 0; t < ntiles; ++t) { re += g[t].x; im += g[t].y; }
+    return make_double2(re, im);
+  };
+  const c128 sp = G(0, p), sq = G(0, q), d = G(1 + p, q);
+  F[e] = 4.0 * (d.x - (sp.x * sq.x + sp.y * sq.y));
+}
+
+// =====================================================================================
+// host drivers
+// =====================================================================================
+static int fill_pass_args(const pqc_program* prog, const V1Pass& ps, V1Args& a) {
+  a.mops = prog->d_mops + ps.mop_off;
+  a.sweeps = prog->d_sweeps + ps.sweep_off;
+  a.nsweeps = ps.nsweeps;
+  a.sweeps_nmops = ps.nmops;
+  a.sweep0_io = ps.io_first;
+  a.last_io = ps.io_last;
+  a.tjobs = prog->d_tjobs + ps.tj_off;
+  a.ntjobs = ps.ntjobs;
+  a.ntrig = ps.ntrig;
+  a.zz = prog->d_zz;
+  a.gens = prog->d_gens;
+  a.n = prog->n;
+  a.tb = ps.tb;
+  a.items_log2 = V1_LOCAL_BITS - ps.tb;
+  a.low_run = ps.low_run;
+  memcpy(a.lbit, ps.lbit, sizeof(a.lbit));
+  memcpy(a.obit, ps.obit, sizeof(a.obit));
+  return 0;
+}
+
+static int launch_init(c128* buf, int mode, const c128* init, long long init_stride, long long S,
+                       int slots_total, int n, cudaStream_t st) {
+  const long long total = S << n;
+  const long long grid = std::min<long long>((total + 255) / 256, 148 * 16);
+  k_init_slot0<<<(unsigned)grid, 256, 0, st>>>(buf, mode, init, init_stride, S, slots_total, n);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_v1(const V1Args& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PQC_CUDA(cudaFuncSetAttribute(k_sweep_pass<false, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    PQC_CUDA(cudaFuncSetAttribute(k_sweep_pass<true, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    PQC_CUDA(cudaFuncSetAttribute(k_sweep_pass<false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    PQC_CUDA(cudaFuncSetAttribute(k_sweep_pass<true, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set = true;
+  }
+  const int ipc = 1 << a.items_log2;
+  const long long groups = (a.n_items + ipc - 1) / ipc;
+  const long long grid = groups << (a.n - a.tb);
+  if (grid <= 0) return 0;
+  if (grid > 0x7fffffffLL) PQC_FAIL(-1, "pass grid too large; split the batch");
+  const size_t smem = ((size_t)1 << V1_LOCAL_BITS) * sizeof(c128) +
+                      (size_t)ipc * a.ntrig * sizeof(double2);
+  const int h = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st);
+  const bool dots = a.npartners > 0, gen = a.nspawn > 0;
+  if (dots && gen) k_sweep_pass<true, true><<<(unsigned)grid, 256, smem, st>>>(a);
+  else if (dots) k_sweep_pass<true, false><<<(unsigned)grid, 256, smem, st>>>(a);
+  else if (gen) k_sweep_pass<false, true><<<(unsigned)grid, 256, smem, st>>>(a);
+  else k_sweep_pass<false, false><<<(unsigned)grid, 256, smem, st>>>(a);
+  pqc_prof_launch_end(h, st);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
+int pqc_v1_run(const pqc_program* prog, const double* d_angles, long long ld, long long S,
+               const c128* d_init, long long init_stride, c128* d_out, cudaStream_t st) {
+  const int mode = !d_init ? 1 : (init_stride == 0 ? 2 : 3);
+  {
+    const int rc = launch_init(d_out, mode, d_init, init_stride, S, 1, prog->n, st);
+    if (rc) return rc;
+  }
+  for (int pi : prog->v1_run) {
+    V1Args a;
+    memset(&a, 0, sizeof(a));
+    fill_pass_args(prog, prog->v1_passes[pi], a);
+    a.src = d_out;
+    a.dst = d_out;
+    a.angles = d_angles;
+    a.ld = ld;
+    a.n_items = S;
+    a.slots_total = 1;
+    a.active = 1;
+    const int rc = launch_v1(a, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+long long pqc_v1_gpart_elems(const pqc_program* prog, long long S) {
+  const long long ntiles = 1ll << std::max(0, prog->n - V1_LOCAL_BITS);
+  return S * (prog->P + 1) * std::max(1, prog->P) * ntiles;
+}
+
+int pqc_v1_qfim_reduce(const pqc_program* prog, const c128* d_gpart, long long S, double* d_F,
+                       cudaStream_t st) {
+  const long long tot = S * prog->P * prog->P;
+  if (tot <= 0) return 0;
+  const int ntiles = 1 << std::max(0, prog->n - V1_LOCAL_BITS);
+  k_qfim_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_gpart, S, prog->P, ntiles, d_F);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
+// index one past the last stage that creates a derivative vector
+static size_t last_spawn_stage(const pqc_program* prog) {
+  size_t last = 0;
+  for (size_t i = 0; i < prog->v1_grad.size(); ++i) {
+    const V1Stage& sg = prog->v1_grad[i];
+    if (sg.type == 1 || (sg.type == 0 && !prog->v1_passes[sg.pass].spawn_param.empty())) last = i + 1;
+  }
+  return last;
+}
+
+int pqc_v1_n_passes(const pqc_program* prog, bool need_final) {
+  const size_t end = need_final ? prog->v1_grad.size() : last_spawn_stage(prog);
+  int k = 0;
+  for (size_t i = 0; i < end; ++i) k += prog->v1_grad[i].type == 0;
+  return k;
+}
+
+// Forward derivative pipeline on two ping-pong buffers [S][P+1][D].  need_final: also run the
+// passes after the last spawn so every vector is the FINAL derivative state (get_gradients);
+// without it (QFIM) those unitary passes are skipped because they cannot change an overlap.
+// *final_buf receives the buffer holding the vectors after the last executed pass.
+int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long long ld, long long S,
+                       const c128* d_init, c128* buf_a, c128* buf_b, c128* d_gpart,
+                       bool want_dots, bool need_final, c128** final_buf, cudaStream_t st) {
+  const int P = prog->P, n = prog->n;
+  const int slots_total = P + 1;
+  c128* pp[2] = {buf_a, buf_b};
+  int cur = 0;                       // buffer holding the current vectors
+  int nlive = 1;
+  const int mode = !d_init ? 1 : 2;
+  const int ntiles = 1 << std::max(0, n - V1_LOCAL_BITS);
+  bool first = true;
+  {
+    const int rc = launch_init(pp[0], mode, d_init, 0, S, slots_total, n, st);
+    if (rc) return rc;
+  }
+  const size_t end = need_final ? prog->v1_grad.size() : last_spawn_stage(prog);
+  std::vector<int> late_dots;        // Gram columns owed by skipped stages
+  for (size_t si = 0; si < prog->v1_grad.size(); ++si) {
+    const V1Stage& sg = prog->v1_grad[si];
+    if (si >= end) {
+      for (int p : sg.partners) late_dots.push_back(p);
+      continue;
+    }
+    if (sg.type == 0) {
+      const V1Pass& ps = prog->v1_passes[sg.pass];
+      V1Args a;
+      memset(&a, 0, sizeof(a));
+      fill_pass_args(prog, ps, a);
+      a.src = pp[cur];
+      a.dst = pp[cur ^ 1];
+      a.angles = d_angles;
+      a.ld = ld;
+      a.slots_total = slots_total;
+      a.active = nlive;
+      a.nspawn = (int)ps.spawn_param.size();
+      for (int k = 0; k < a.nspawn; ++k) {
+        const int p = ps.spawn_param[k];
+        a.spawn_slot[k] = 1 + p;
+        a.spawn_goff[k] = prog->gen_off[p];
+        a.spawn_gcnt[k] = prog->gen_off[p + 1] - prog->gen_off[p];
+      }
+      a.n_items = S * (a.active + a.nspawn);
+      if (want_dots) {
+        a.npartners = (int)sg.partners.size();
+        for (int q = 0; q < a.npartners; ++q) a.partner_slot[q] = 1 + sg.partners[q];
+        a.gpart = d_gpart;
+        a.P = P;
+        a.ntiles = ntiles;
+      }
+      const int rc = launch_v1(a, st);
+      if (rc) return rc;
+      cur ^= 1;
+      first = false;
+      for (int p : ps.spawn_param) nlive = std::max(nlive, p + 2);
+    } else if (sg.type == 1) {
+      if (first) PQC_FAIL(-5, "internal: gather before the first pass");
+      GatherArgs g;
+      memset(&g, 0, sizeof(g));
+      g.buf = pp[cur];
+      g.n = n;
+      g.cb = std::min(n, V1_LOCAL_BITS);
+      g.slots_total = slots_total;
+      g.gens = prog->d_gens;
+      for (size_t k0 = 0; k0 < sg.gather_params.size(); k0 += V1_MAX_SPAWN) {
+        g.nparams = (int)std::min<size_t>(V1_MAX_SPAWN, sg.gather_params.size() - k0);
+        for (int k = 0; k < g.nparams; ++k) {
+          const int p = sg.gather_params[k0 + k];
+          g.slot[k] = 1 + p;
+          g.goff[k] = prog->gen_off[p];
+          g.gcnt[k] = prog->gen_off[p + 1] - prog->gen_off[p];
+          nlive = std::max(nlive, p + 2);
+        }
+        const long long grid = S << (n - g.cb);
+        if (grid > 0x7fffffffLL) PQC_FAIL(-1, "gather grid too large");
+        static bool gather_attr = false;
+        if (!gather_attr) {
+          PQC_CUDA(cudaFuncSetAttribute(k_tile_gather, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        80 * 1024));
+          gather_attr = true;
+        }
+        k_tile_gather<<<(unsigned)grid, 256, ((size_t)1 << g.cb) * sizeof(c128), st>>>(g);
+        PQC_LAUNCH_CHECK();
+      }
+    } else {
+      for (int p : sg.partners) late_dots.push_back(p);
+    }
+    // standalone Gram columns (dots-only stages, and whatever skipped stages still owe)
+    const bool flush = want_dots && !late_dots.empty() &&
+                       (sg.type == 2 || si + 1 == prog->v1_grad.size());
+    if (flush) {
+      for (size_t q0 = 0; q0 < late_dots.size(); q0 += V1_MAX_PART) {
+        V1Args a;
+        memset(&a, 0, sizeof(a));
+        a.npartners = (int)std::min<size_t>(V1_MAX_PART, late_dots.size() - q0);
+        for (int q = 0; q < a.npartners; ++q) a.partner_slot[q] = 1 + late_dots[q0 + q];
+        a.gpart = d_gpart;
+        a.P = P;
+        a.ntiles = ntiles;
+        const long long grid = S * nlive * a.npartners;
+        if (grid > 0x7fffffffLL) PQC_FAIL(-1, "dot grid too large");
+        k_multi_dots<<<(unsigned)grid, 256, 0, st>>>(pp[cur], n, slots_total, nlive, a.npartners,
+                                                    nullptr, a);
+        PQC_LAUNCH_CHECK();
+      }
+      late_dots.clear();
+    }
+  }
+  if (want_dots && !late_dots.empty()) {
+    for (size_t q0 = 0; q0 < late_dots.size(); q0 += V1_MAX_PART) {
+      V1Args a;
+      memset(&a, 0, sizeof(a));
+      a.npartners = (int)std::min<size_t>(V1_MAX_PART, late_dots.size() - q0);
+      for (int q = 0; q < a.npartners; ++q) a.partner_slot[q] = 1 + late_dots[q0 + q];
+      a.gpart = d_gpart;
+      a.P = P;
+      a.ntiles = ntiles;
+      const long long grid = S * nlive * a.npartners;
+      if (grid > 0x7fffffffLL) PQC_FAIL(-1, "dot grid too large");
+      k_multi_dots<<<(unsigned)grid, 256, 0, st>>>(pp[cur], n, slots_total, nlive, a.npartners,
+                                                  nullptr, a);
+      PQC_LAUNCH_CHECK();
+    }
+  }
+  if (final_buf) *final_buf = pp[cur];
+  return 0;
+}
