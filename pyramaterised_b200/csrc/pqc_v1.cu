@@ -245,7 +245,12 @@ struct Builder {
     bool assigned = false;
     for (int b = 0; b < n; ++b)
       if (((c.mix >> b) & 1u) && grp_of[b] >= 0) assigned = true;
-    return assigned ? 2 : 3;
+    if (assigned) return 2;
+    // fresh bits: open the pass on high bits (direct global load), take the low nibble in the
+    // middle, finish on high bits again (direct global store)
+    const bool all_low = (c.mix & ~lowmask()) == 0;
+    const bool want_low = !sws.empty() && grp[0].empty();
+    return (all_low == want_low) ? 3 : 4;
   }
 
   MOp proto(const COp& c) {
@@ -268,7 +273,15 @@ struct Builder {
       j.npairs = (int)c.pairs.size();
       j.scale = c.scale;
       j.offset = c.offset;
-      tj.push_back(j);
+      if (c.kind == PQC_K_ZZSUM) {          // one job per table entry so they fill in parallel
+        for (int k = 0; k < te; ++k) {
+          j.slot = ntrig + k;
+          j.pad = k;
+          tj.push_back(j);
+        }
+      } else {
+        tj.push_back(j);
+      }
       ntrig += te;
     }
     if (c.kind == PQC_K_ZZSUM) {
@@ -727,6 +740,10 @@ __global__ void __launch_bounds__(256) k_init_slot0(c128* __restrict__ buf, int 
   }
 }
 
+#define SEL4R(j, a0, a1, a2, a3) \
+  ((((j)&1) ? (a0) : 0u) | (((j)&2) ? (a1) : 0u) | (((j)&4) ? (a2) : 0u) | (((j)&8) ? (a3) : 0u))
+#define XSEL4R(j, a0, a1, a2, a3) \
+  ((((j)&1) ? (a0) : 0u) ^ (((j)&2) ? (a1) : 0u) ^ (((j)&4) ? (a2) : 0u) ^ (((j)&8) ? (a3) : 0u))
 #define V1_MAX_MOPS 160
 #define V1_MAX_SWEEPS 32
 
@@ -780,11 +797,9 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     } else {
       if (jb.param >= 0) th += jb.scale * A.angles[sample * A.ld + jb.param];
       if (jb.kind == PQC_K_ZZSUM) {
-        // entry[k] = exp(-i th/2 (npairs - 2k)), k = number of anti-aligned pairs
-        for (int k = 0; k <= jb.npairs; ++k) {
-          sincos(-0.5 * th * (double)(jb.npairs - 2 * k), &s, &c);
-          t[k] = make_double2(c, s);
-        }
+        // entry[k] = exp(-i th/2 (npairs - 2k)), k = jb.pad = number of anti-aligned pairs
+        sincos(-0.5 * th * (double)(jb.npairs - 2 * jb.pad), &s, &c);
+        t[0] = make_double2(c, s);
       } else if (jb.kind == PQC_K_RXY) {
         sincos(th, &s, &c);                      // rx-like rotation by the FULL angle
         t[0] = make_double2(c, s);
@@ -795,9 +810,12 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     }
   }
 
-  auto item_info = [&](long long item, long long& sample, int& src_slot, int& dst_slot, int& gen) {
-    sample = item / ips;
-    const int r = (int)(item - sample * ips);
+  const long long sample0 = item0 / ips;
+  const int r0 = (int)(item0 - sample0 * ips);
+  // item li of this CTA (li < 16): 32-bit arithmetic only
+  auto item_info = [&](int li, long long& sample, int& src_slot, int& dst_slot, int& gen) {
+    const int rr = r0 + li, ds = rr / ips, r = rr - ds * ips;
+    sample = sample0 + ds;
     if (!GEN || r < A.active) {
       src_slot = dst_slot = r;
       gen = -1;
@@ -812,24 +830,34 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     for (int j = A.low_run; j < A.tb; ++j) r |= ((i >> j) & 1u) << A.lbit[j];
     return r;
   };
+  // staged (global <-> swizzled shared) element r of this thread: local index tid | r << 8
+  const uint32_t st_amp_tid = tbase | local_to_amp((uint32_t)tid & amask);
+  uint32_t st_h[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) st_h[k] = (8 + k < A.tb) ? (1u << A.lbit[8 + k]) : 0u;
+  const uint32_t st_s_tid = swz((uint32_t)tid);
+  const uint32_t st_s[4] = {swz(1u << 8), swz(1u << 9), swz(1u << 10), swz(1u << 11)};
+  const int st_item_shift = A.tb - 8;          // li = r >> (tb - 8)   (tb >= 8)
 
   const bool direct_load = (A.sweep0_io & 1) != 0;
   long long my_sample = 0;
   int my_src = 0, my_dst = 0, my_gen = -1;
-  if (ipc == 1) item_info(item0, my_sample, my_src, my_dst, my_gen);
+  if (ipc == 1) item_info(0, my_sample, my_src, my_dst, my_gen);
 
   // ---- staged load (global -> swizzled shared) when the first sweep cannot load directly -------
   if (!direct_load) {
-    for (uint32_t i = tid; i < (1u << V1_LOCAL_BITS); i += 256) {
-      const long long item = item0 + (i >> A.tb);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int li = r >> st_item_shift;
       c128 v = make_double2(0.0, 0.0);
-      if (item < A.n_items) {
-        long long sample;
-        int ss, ds, gg;
-        item_info(item, sample, ss, ds, gg);
-        v = A.src[((sample * A.slots_total + ss) << A.n) + (tbase | local_to_amp(i & amask))];
+      if (item0 + li < A.n_items) {
+        long long sample = my_sample;
+        int ss = my_src, ds = my_dst, gg = my_gen;
+        if (ipc > 1) item_info(li, sample, ss, ds, gg);
+        v = A.src[((sample * A.slots_total + ss) << A.n) +
+                  (st_amp_tid | SEL4R(r, st_h[0], st_h[1], st_h[2], st_h[3]))];
       }
-      sm[swz(i)] = v;
+      sm[st_s_tid ^ XSEL4R(r, st_s[0], st_s[1], st_s[2], st_s[3])] = v;
     }
     if (DOTS && my_gen < 0) {
       const c128* own = A.src + ((my_sample * A.slots_total + my_src) << A.n);
@@ -859,13 +887,11 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     const SweepD sw = s_sweeps[si];
     const uint32_t m0 = 1u << sw.rb[0], m1 = 1u << sw.rb[1], m2 = 1u << sw.rb[2], m3 = 1u << sw.rb[3];
     const uint32_t rmask = m0 | m1 | m2 | m3;
-    uint32_t base = 0;
-    {
-      int tb_i = 0;
+    uint32_t base = (uint32_t)tid;       // deposit the 8 thread bits around the register bits
 #pragma unroll
-      for (int pos = 0; pos < V1_LOCAL_BITS; ++pos)
-        if (!((rmask >> pos) & 1u)) base |= ((tid >> tb_i++) & 1u) << pos;
-    }
+    for (int k = 0; k < 4; ++k)
+      base = ((base >> sw.rb[k]) << (sw.rb[k] + 1)) | (base & ((1u << sw.rb[k]) - 1u));
+    (void)rmask;
     // swz is linear over GF(2): swz(base | sel) = swz(base) ^ swz(sel)
     const uint32_t sb = swz(base), s0 = swz(m0), s1 = swz(m1), s2 = swz(m2), s3 = swz(m3);
     // global amplitude index of register j = amp0 | (selected g-masks)
@@ -899,7 +925,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     long long sample = my_sample;
     int src_slot = my_src, dst_slot = my_dst, gen = my_gen;
     const bool live = item0 + li < A.n_items;
-    if (ipc > 1 && live) item_info(item0 + li, sample, src_slot, dst_slot, gen);
+    if (ipc > 1 && live) item_info(li, sample, src_slot, dst_slot, gen);
     const double2* tg = trig + (size_t)li * A.ntrig;
 #define SEL4(j, a0, a1, a2, a3) \
   ((((j)&1) ? (a0) : 0u) | (((j)&2) ? (a1) : 0u) | (((j)&4) ? (a2) : 0u) | (((j)&8) ? (a3) : 0u))
@@ -911,9 +937,12 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     uint32_t lc[4] = {1u, 2u, 4u, 8u}, lv = 0u;
     if (npre) affine(sw.mop_begin, sw.mop_begin + npre, true, lc, lv);
     if (dl) {
-      const uint32_t lgb = amp0 ^ LIN4(lv, g0, g1, g2, g3);
-      const uint32_t lg0 = LIN4(lc[0], g0, g1, g2, g3), lg1 = LIN4(lc[1], g0, g1, g2, g3),
-                     lg2 = LIN4(lc[2], g0, g1, g2, g3), lg3 = LIN4(lc[3], g0, g1, g2, g3);
+      uint32_t lgb = amp0, lg0 = g0, lg1 = g1, lg2 = g2, lg3 = g3;
+      if (npre) {
+        lgb = amp0 ^ LIN4(lv, g0, g1, g2, g3);
+        lg0 = LIN4(lc[0], g0, g1, g2, g3); lg1 = LIN4(lc[1], g0, g1, g2, g3);
+        lg2 = LIN4(lc[2], g0, g1, g2, g3); lg3 = LIN4(lc[3], g0, g1, g2, g3);
+      }
       const c128* sp = A.src + ((sample * A.slots_total + src_slot) << A.n);
 #pragma unroll
       for (int j = 0; j < 16; ++j)
@@ -938,9 +967,12 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
         }
       }
     } else {
-      const uint32_t lsb = sb ^ LIN4(lv, s0, s1, s2, s3);
-      const uint32_t ls0 = LIN4(lc[0], s0, s1, s2, s3), ls1 = LIN4(lc[1], s0, s1, s2, s3),
-                     ls2 = LIN4(lc[2], s0, s1, s2, s3), ls3 = LIN4(lc[3], s0, s1, s2, s3);
+      uint32_t lsb = sb, ls0 = s0, ls1 = s1, ls2 = s2, ls3 = s3;
+      if (npre) {
+        lsb = sb ^ LIN4(lv, s0, s1, s2, s3);
+        ls0 = LIN4(lc[0], s0, s1, s2, s3); ls1 = LIN4(lc[1], s0, s1, s2, s3);
+        ls2 = LIN4(lc[2], s0, s1, s2, s3); ls3 = LIN4(lc[3], s0, s1, s2, s3);
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) a[j] = sm[lsb ^ XSEL4(j, ls0, ls1, ls2, ls3)];
     }
@@ -985,14 +1017,25 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
           zs[t] = z.shift;
         }
         const double2* tz = tg + m.trig;
+        if (m.aux1 <= 2) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t x = amp0 | SEL4(j, g0, g1, g2, g3);
-          int cnt = __popc((x ^ (x >> zs[0])) & zm[0]) + __popc((x ^ (x >> zs[1])) & zm[1]);
-          if (m.aux1 > 2) cnt += __popc((x ^ (x >> zs[2])) & zm[2]) + __popc((x ^ (x >> zs[3])) & zm[3]);
-          const double2 ph = tz[cnt];
-          const c128 v = a[j];
-          a[j] = make_double2(v.x * ph.x - v.y * ph.y, v.y * ph.x + v.x * ph.y);
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t x = amp0 | SEL4(j, g0, g1, g2, g3);
+            const int cnt = __popc((x ^ (x >> zs[0])) & zm[0]) + __popc((x ^ (x >> zs[1])) & zm[1]);
+            const double2 ph = tz[cnt];
+            const c128 v = a[j];
+            a[j] = make_double2(v.x * ph.x - v.y * ph.y, v.y * ph.x + v.x * ph.y);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t x = amp0 | SEL4(j, g0, g1, g2, g3);
+            const int cnt = __popc((x ^ (x >> zs[0])) & zm[0]) + __popc((x ^ (x >> zs[1])) & zm[1]) +
+                            __popc((x ^ (x >> zs[2])) & zm[2]) + __popc((x ^ (x >> zs[3])) & zm[3]);
+            const double2 ph = tz[cnt];
+            const c128 v = a[j];
+            a[j] = make_double2(v.x * ph.x - v.y * ph.y, v.y * ph.x + v.x * ph.y);
+          }
         }
       } else if (kind == PQC_OP_RZ || kind == PQC_OP_S || kind == PQC_OP_T) {
         double c = 1.0, s = 0.0;
@@ -1082,18 +1125,24 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     uint32_t sc[4] = {1u, 2u, 4u, 8u}, sv = 0u;
     if (npost) affine(sw.mop_end - npost, sw.mop_end, false, sc, sv);
     if (ds) {
-      const uint32_t sgb = amp0 ^ LIN4(sv, g0, g1, g2, g3);
-      const uint32_t sg0 = LIN4(sc[0], g0, g1, g2, g3), sg1 = LIN4(sc[1], g0, g1, g2, g3),
-                     sg2 = LIN4(sc[2], g0, g1, g2, g3), sg3 = LIN4(sc[3], g0, g1, g2, g3);
+      uint32_t sgb = amp0, sg0 = g0, sg1 = g1, sg2 = g2, sg3 = g3;
+      if (npost) {
+        sgb = amp0 ^ LIN4(sv, g0, g1, g2, g3);
+        sg0 = LIN4(sc[0], g0, g1, g2, g3); sg1 = LIN4(sc[1], g0, g1, g2, g3);
+        sg2 = LIN4(sc[2], g0, g1, g2, g3); sg3 = LIN4(sc[3], g0, g1, g2, g3);
+      }
       if (live) {
         c128* dp = A.dst + ((sample * A.slots_total + dst_slot) << A.n);
 #pragma unroll
         for (int j = 0; j < 16; ++j) dp[sgb ^ XSEL4(j, sg0, sg1, sg2, sg3)] = a[j];
       }
     } else {
-      const uint32_t ssb = sb ^ LIN4(sv, s0, s1, s2, s3);
-      const uint32_t ss0 = LIN4(sc[0], s0, s1, s2, s3), ss1 = LIN4(sc[1], s0, s1, s2, s3),
-                     ss2 = LIN4(sc[2], s0, s1, s2, s3), ss3 = LIN4(sc[3], s0, s1, s2, s3);
+      uint32_t ssb = sb, ss0 = s0, ss1 = s1, ss2 = s2, ss3 = s3;
+      if (npost) {
+        ssb = sb ^ LIN4(sv, s0, s1, s2, s3);
+        ss0 = LIN4(sc[0], s0, s1, s2, s3); ss1 = LIN4(sc[1], s0, s1, s2, s3);
+        ss2 = LIN4(sc[2], s0, s1, s2, s3); ss3 = LIN4(sc[3], s0, s1, s2, s3);
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) sm[ssb ^ XSEL4(j, ss0, ss1, ss2, ss3)] = a[j];
       __syncthreads();
@@ -1102,13 +1151,16 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
 
   // ---- staged store -------------------------------------------------------------------------------
   if (!(A.last_io & 2)) {
-    for (uint32_t i = tid; i < (1u << V1_LOCAL_BITS); i += 256) {
-      const long long item = item0 + (i >> A.tb);
-      if (item < A.n_items) {
-        long long sample;
-        int ss, ds, gg;
-        item_info(item, sample, ss, ds, gg);
-        A.dst[((sample * A.slots_total + ds) << A.n) + (tbase | local_to_amp(i & amask))] = sm[swz(i)];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int li = r >> st_item_shift;
+      if (item0 + li < A.n_items) {
+        long long sample = my_sample;
+        int ss = my_src, ds = my_dst, gg = my_gen;
+        if (ipc > 1) item_info(li, sample, ss, ds, gg);
+        A.dst[((sample * A.slots_total + ds) << A.n) +
+              (st_amp_tid | SEL4R(r, st_h[0], st_h[1], st_h[2], st_h[3]))] =
+            sm[st_s_tid ^ XSEL4R(r, st_s[0], st_s[1], st_s[2], st_s[3])];
       }
     }
   }
