@@ -255,8 +255,8 @@ static int64_t qfim_chunk_target() {
   static int64_t v = -1;
   if (v < 0) {
     const char* e = getenv("PQC_QFIM_CHUNK");
-    v = e ? atoll(e) : 64;
-    if (v < 1) v = 64;
+    v = e ? atoll(e) : 256;
+    if (v < 1) v = 256;
   }
   return v;
 }

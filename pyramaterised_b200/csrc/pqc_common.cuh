@@ -111,7 +111,9 @@ struct SweepD {
   int rb[4];               // local positions held in registers, ascending
   int mop_begin, mop_end;
   int io;                  // bit0: load straight from global, bit1: store straight to global
-  int pad;
+  int pad;                 // npre | npost << 16
+  unsigned char tl[8];     // local position fed by thread bit t (the 8 non-register positions)
+  unsigned char tg[8];     // global amplitude bit of that position, 255 = item bit (n < 12)
 };
 struct TrigJob {           // per-item trig table entry (or run of entries) to fill
   int kind, param, param2, slot, npairs, pad;

@@ -396,6 +396,15 @@ struct Builder {
       }
       std::sort(rb.begin(), rb.end());
       for (int k = 0; k < 4; ++k) d.rb[k] = rb[k];
+      {
+        int t = 0;
+        for (int posn = 0; posn < V1_LOCAL_BITS; ++posn) {
+          if (std::find(rb.begin(), rb.end(), posn) != rb.end()) continue;
+          d.tl[t] = (unsigned char)posn;
+          d.tg[t] = posn < cap ? (unsigned char)ps.lbit[posn] : (unsigned char)255;
+          ++t;
+        }
+      }
       d.mop_begin = (int)mops.size() - ps.mop_off;
       auto emit = [&](std::vector<MOp>& list) {
         for (MOp m : list) {
@@ -887,17 +896,20 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     const SweepD sw = s_sweeps[si];
     const uint32_t m0 = 1u << sw.rb[0], m1 = 1u << sw.rb[1], m2 = 1u << sw.rb[2], m3 = 1u << sw.rb[3];
     const uint32_t rmask = m0 | m1 | m2 | m3;
-    uint32_t base = (uint32_t)tid;       // deposit the 8 thread bits around the register bits
+    // the 8 thread bits go to the non-register local positions (table from the planner)
+    uint32_t base = 0, amp0 = tbase;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      base = ((base >> sw.rb[k]) << (sw.rb[k] + 1)) | (base & ((1u << sw.rb[k]) - 1u));
+    for (int t = 0; t < 8; ++t) {
+      const uint32_t bit = ((uint32_t)tid >> t) & 1u;
+      base |= bit << sw.tl[t];
+      amp0 |= sw.tg[t] < 32 ? (bit << sw.tg[t]) : 0u;
+    }
     (void)rmask;
     // swz is linear over GF(2): swz(base | sel) = swz(base) ^ swz(sel)
     const uint32_t sb = swz(base), s0 = swz(m0), s1 = swz(m1), s2 = swz(m2), s3 = swz(m3);
     // global amplitude index of register j = amp0 | (selected g-masks)
     const uint32_t g0 = 1u << A.lbit[sw.rb[0]], g1 = 1u << A.lbit[sw.rb[1]],
                    g2 = 1u << A.lbit[sw.rb[2]], g3 = 1u << A.lbit[sw.rb[3]];
-    const uint32_t amp0 = tbase | local_to_amp(base & amask);
     // X / CNOT are affine maps of the 4-bit register index: pi(j) = XOR_{k in j} col[k] ^ v.
     // They cost nothing per amplitude: they only change the load / store address constants.
     const int npre = sw.pad & 0xffff, npost = sw.pad >> 16;
@@ -948,6 +960,9 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
       for (int j = 0; j < 16; ++j)
         a[j] = live ? sp[lgb ^ XSEL4(j, lg0, lg1, lg2, lg3)] : make_double2(0.0, 0.0);
       if (DOTS && gen < 0) {
+        // Gram partials against every pending partner: per-warp shuffles, then ONE barrier
+        __shared__ double dred[8][2 * V1_MAX_PART];
+        const int w = tid >> 5, l = tid & 31;
         for (int q = 0; q < A.npartners; ++q) {
           const int ps = A.partner_slot[q];
           if (src_slot > ps) continue;               // uniform per CTA
@@ -959,11 +974,21 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
             re += a[j].x * y.x + a[j].y * y.y;
             im += a[j].x * y.y - a[j].y * y.x;
           }
-          re = block_sum<256>(re, red);
-          im = block_sum<256>(im, red);
-          if (tid == 0)
-            A.gpart[((sample * (A.P + 1) + src_slot) * A.P + (ps - 1)) * A.ntiles + tile] =
-                make_double2(re, im);
+          re = warp_sum(re);
+          im = warp_sum(im);
+          if (l == 0) { dred[w][2 * q] = re; dred[w][2 * q + 1] = im; }
+        }
+        __syncthreads();
+        if (tid < 2 * A.npartners) {
+          const int q = tid >> 1, ps = A.partner_slot[q];
+          if (src_slot <= ps) {
+            double v = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) v += dred[ww][tid];
+            double* g = reinterpret_cast<double*>(
+                A.gpart + ((sample * (A.P + 1) + src_slot) * A.P + (ps - 1)) * A.ntiles + tile);
+            g[tid & 1] = v;
+          }
         }
       }
     } else {
