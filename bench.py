@@ -180,10 +180,14 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, algorithmic_bytes_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu
+    --set full capture, rescaled to this run's launch size through the measured
+    traffic / algorithmic-bytes ratio (profiles/roofline_traffic.json)."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(kernel)
+            r = json.load(f)[kernel]["ratio"]
+        return float(np.mean(r)) * algorithmic_bytes_per_launch
     except Exception:
         return None
 
@@ -270,7 +274,8 @@ def run_b200(a):
     e2e = total * a.steps / (ms_e2e / 1e3)
     peak, peak_src = measured_peak_gbs()
     achieved = prof["bytes"] / (prof["ms"] / 1e3) / 1e9 if prof["ms"] > 0 else 0.0
-    kern = "k_apply_pass"
+    kern = "k_sweep_pass"
+    alg_per_launch = prof["bytes"] / max(1, prof["launches"])
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps,
@@ -291,8 +296,8 @@ def run_b200(a):
                      "launches": prof["launches"],
                      "avg_launch_ms": prof["ms"] / max(1, prof["launches"]),
                      "kernel_share_of_step": prof["ms"] / ms,
-                     "algorithmic_bytes_per_launch": prof["bytes"] / max(1, prof["launches"]),
-                     "traffic": ncu_traffic(kern)},
+                     "algorithmic_bytes_per_launch": alg_per_launch,
+                     "traffic": ncu_traffic(kern, alg_per_launch)},
         "clocks": clocks,
     }
     if cpu is not None:
