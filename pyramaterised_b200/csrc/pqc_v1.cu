@@ -273,6 +273,7 @@ struct Builder {
       j.npairs = (int)c.pairs.size();
       j.scale = c.scale;
       j.offset = c.offset;
+      if (c.kind == PQC_OP_RX || c.kind == PQC_OP_RY) j.pad = 1;   // stored as (tan, cos)
       if (c.kind == PQC_K_ZZSUM) {          // one job per table entry so they fill in parallel
         for (int k = 0; k < te; ++k) {
           j.slot = ntrig + k;
@@ -683,27 +684,46 @@ __device__ __forceinline__ uint32_t swz(uint32_t i) {
 }
 
 // ---- pair-mixing micro-ops on the 16 register amplitudes ---------------------------------
-// rx-type update of every pair along register bit K: [[c, -i s], [-i s, c]]
+// Rotations are applied in tangent form: rx = c [[1, -i t], [-i t, 1]], ry = c [[1, -t], [t, 1]]
+// with t = tan(angle/2): two FMAs per amplitude instead of four.  The scalar c factors of a
+// layer op are multiplied in once afterwards (op_scale).  t is finite for every double angle
+// (cos never rounds to exactly 0 at pi/2: |c| >= 6e-17) and the result carries the usual
+// relative rounding error of c x + s y because x + t y is computed with one rounding and the
+// final multiplication by c is exact to one more.
 template <int K>
-__device__ __forceinline__ void op_rx(c128 (&a)[16], double c, double s) {
+__device__ __forceinline__ void op_rx_t(c128 (&a)[16], double t) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     if (j & (1 << K)) continue;
     const c128 x = a[j], y = a[j | (1 << K)];
-    a[j] = make_double2(c * x.x + s * y.y, c * x.y - s * y.x);
-    a[j | (1 << K)] = make_double2(c * y.x + s * x.y, c * y.y - s * x.x);
+    a[j] = make_double2(fma(t, y.y, x.x), fma(-t, y.x, x.y));
+    a[j | (1 << K)] = make_double2(fma(t, x.y, y.x), fma(-t, x.x, y.y));
   }
 }
-// real 2x2 [[p, q], [r, t]] along register bit K (RY: c,-s,s,c; H: h,h,h,-h; identity: 1,0,0,1)
 template <int K>
-__device__ __forceinline__ void op_real(c128 (&a)[16], double p, double q, double r, double t) {
+__device__ __forceinline__ void op_ry_t(c128 (&a)[16], double t) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     if (j & (1 << K)) continue;
     const c128 x = a[j], y = a[j | (1 << K)];
-    a[j] = make_double2(p * x.x + q * y.x, p * x.y + q * y.y);
-    a[j | (1 << K)] = make_double2(r * x.x + t * y.x, r * x.y + t * y.y);
+    a[j] = make_double2(fma(-t, y.x, x.x), fma(-t, y.y, x.y));
+    a[j | (1 << K)] = make_double2(fma(t, x.x, y.x), fma(t, x.y, y.y));
   }
+}
+// Hadamard without its 1/sqrt(2): (x + y, x - y)
+template <int K>
+__device__ __forceinline__ void op_h_u(c128 (&a)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j & (1 << K)) continue;
+    const c128 x = a[j], y = a[j | (1 << K)];
+    a[j] = make_double2(x.x + y.x, x.y + y.y);
+    a[j | (1 << K)] = make_double2(x.x - y.x, x.y - y.y);
+  }
+}
+__device__ __forceinline__ void op_scale(c128 (&a)[16], double f) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = make_double2(a[j].x * f, a[j].y * f);
 }
 
 // generic symmetric two-bit rotation: even-parity pair (00,11) by (ce, se), odd-parity pair
@@ -812,6 +832,9 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
       } else if (jb.kind == PQC_K_RXY) {
         sincos(th, &s, &c);                      // rx-like rotation by the FULL angle
         t[0] = make_double2(c, s);
+      } else if (jb.pad == 1) {                  // member of a 1-qubit layer op: (tan, cos)
+        sincos(0.5 * th, &s, &c);
+        t[0] = make_double2(s / c, c);
       } else {
         sincos(0.5 * th, &s, &c);
         t[0] = make_double2(c, s);
@@ -1006,30 +1029,31 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
       const MOp& m = s_mops[mi];
       const int kind = m.kind;
       if (kind == PQC_K_LAYER_RX4) {
-        // straight-line over the 4 register bits; absent gates are the identity (c 1, s 0)
+        // straight-line over the 4 register bits; absent gates are the identity (t 0, c 1).
+        // trig entries of layer ops hold (tan, cos) of the half angle.
         const int sk = m.subk;
-        double2 c0 = make_double2(1.0, 0.0), c1 = c0, c2 = c0, c3 = c0;
+        double2 c0 = make_double2(0.0, 1.0), c1 = c0, c2 = c0, c3 = c0;
         if (sk & 0xff) c0 = tg[m.subt[0]];
         if (sk & 0xff00) c1 = tg[m.subt[1]];
         if (sk & 0xff0000) c2 = tg[m.subt[2]];
         if (sk & 0xff000000) c3 = tg[m.subt[3]];
-        op_rx<0>(a, c0.x, c0.y);
-        op_rx<1>(a, c1.x, c1.y);
-        op_rx<2>(a, c2.x, c2.y);
-        op_rx<3>(a, c3.x, c3.y);
+        op_rx_t<0>(a, c0.x);
+        op_rx_t<1>(a, c1.x);
+        op_rx_t<2>(a, c2.x);
+        op_rx_t<3>(a, c3.x);
+        op_scale(a, (c0.y * c1.y) * (c2.y * c3.y));
       } else if (kind == PQC_K_LAYER_REAL4) {
         const int sk = m.subk;
-        const double h = 0.70710678118654752440;
-#define REAL_SLOT(K)                                                            \
-  {                                                                             \
-    const int kd = ((sk >> (8 * K)) & 0xff) - 1;                                \
-    double p = 1.0, q = 0.0, r = 0.0, t = 1.0;                                  \
-    if (kd == PQC_OP_RY) { const double2 cs = tg[m.subt[K]]; p = cs.x; q = -cs.y; r = cs.y; t = cs.x; } \
-    else if (kd == PQC_OP_H) { p = h; q = h; r = h; t = -h; }                    \
-    op_real<K>(a, p, q, r, t);                                                   \
+        double f = 1.0;
+#define REAL_SLOT(K)                                                       \
+  {                                                                        \
+    const int kd = ((sk >> (8 * K)) & 0xff) - 1;                           \
+    if (kd == PQC_OP_RY) { const double2 tc = tg[m.subt[K]]; op_ry_t<K>(a, tc.x); f *= tc.y; } \
+    else if (kd == PQC_OP_H) { op_h_u<K>(a); f *= 0.70710678118654752440; } \
   }
         REAL_SLOT(0) REAL_SLOT(1) REAL_SLOT(2) REAL_SLOT(3)
 #undef REAL_SLOT
+        op_scale(a, f);
       } else if (kind == PQC_K_ZZSUM) {
         // count of anti-aligned pairs; <= 4 (mask, shift) terms, loaded once
         uint32_t zm[4];
