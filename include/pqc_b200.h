@@ -105,12 +105,16 @@ PQC_API int pqc_device_check(int* cc_major, int* cc_minor, int* n_sms);
 /* ---- gate programs: replaces PQC.set_gates / the per-gate 2^n x 2^n operator rebuild
  * (circuit.py:53-72, gates.py:122-131,469-477) ---------------------------------------- */
 PQC_API int pqc_program_create(int n_qubits, int n_params, int n_ops, const pqc_op* h_ops,
-                       pqc_program** out);
+                       pqc_program** out);   /* planning only: works without a GPU */
 PQC_API int pqc_program_destroy(pqc_program* prog);
 /* out[0]=n_qubits out[1]=n_params out[2]=n_ops out[3]=n_passes (forward plan)
  * out[4]=tile_bits out[5]=1 if derivative states are supported out[6]=passes of the
  * derivative / QFIM plan out[7]=reserved */
 PQC_API int pqc_program_stats(const pqc_program* prog, int64_t* out8);
+
+/* Text description of the execution plan (one line per pass / gather / dots stage); needs no
+ * GPU.  Writes at most `cap` bytes including the terminator. */
+PQC_API int pqc_program_describe(const pqc_program* prog, char* out, int64_t cap);
 
 /* ---- PQC.run for a batch (circuit.py:118-125).  d_init: NULL = |0..0>; otherwise
  * init_stride = 0 broadcasts one [D] vector, init_stride = D gives one per sample

@@ -41,6 +41,7 @@ SIGNATURES = {
     "pqc_program_create": [_INT, _INT, _INT, C.POINTER(PqcOp), C.POINTER(_P)],
     "pqc_program_destroy": [_P],
     "pqc_program_stats": [_P, C.POINTER(_I64)],
+    "pqc_program_describe": [_P, C.c_char_p, _I64],
     "pqc_run_batch": [_P, _P, _I64, _I64, _P, _I64, _P, _P],
     "pqc_gradients_batch": [_P, _P, _I64, _I64, _P, _I64, _P, _P],
     "pqc_qfim_from_grads": [_P, _P, _INT, _INT, _I64, _P, _P],

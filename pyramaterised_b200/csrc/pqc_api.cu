@@ -116,6 +116,7 @@ extern "C" int pqc_run_batch(const pqc_program* prog, const double* d_angles, in
   if (S <= 0) return 0;
   if (prog->P > 0 && (!d_angles || ld < prog->P)) PQC_FAIL(-1, "No parameters supplied!");
   cudaStream_t st = (cudaStream_t)stream;
+  if (pqc_program_upload(prog)) return -2;
   if (prog->v1_ok && !pqc_use_v0())
     return pqc_v1_run(prog, d_angles, ld, S, (const c128*)d_init, init_stride, (c128*)d_out, st);
   int mode = init_mode_of(d_init, init_stride);
@@ -148,6 +149,7 @@ extern "C" int pqc_gradients_batch(const pqc_program* prog, const double* d_angl
   if (prog->P > 0 && (!d_angles || ld < prog->P)) PQC_FAIL(-1, "No parameters supplied!");
   if (init_stride != 0) PQC_FAIL(-1, "derivative states take one shared initial state");
   cudaStream_t st = (cudaStream_t)stream;
+  if (pqc_program_upload(prog)) return -2;
   if (prog->v1_grad_ok && !pqc_use_v0()) {
     // second ping-pong copy; ordered so that the last pass lands in the caller's buffer
     const size_t bytes = sizeof(c128) * (size_t)S * (prog->P + 1) * ((size_t)1 << prog->n);
@@ -275,6 +277,7 @@ extern "C" int pqc_qfim_batch(const pqc_program* prog, const double* d_angles, i
   if (!prog->grad_supported) PQC_FAIL(-4, "QFIM unsupported: " + prog->grad_reason);
   if (prog->P > 0 && (!d_angles || ld < prog->P)) PQC_FAIL(-1, "No parameters supplied!");
   cudaStream_t st = (cudaStream_t)stream;
+  if (pqc_program_upload(prog)) return -2;
   const int P = prog->P, n = prog->n;
   const int64_t D = 1ll << n;
   const int64_t per = qfim_bytes_per_sample(prog);

@@ -184,16 +184,26 @@ int pqc_plan_program(pqc_program* prog) {
   prog->gen_off[prog->P] = (int)prog->gens.size();
   if (prog->grad_supported) plan_range(prog, prev, nops, prog->seg_passes[prog->P], dops);
 
-  if (!dops.empty()) {
-    PQC_CUDA(cudaMalloc(&prog->d_ops, dops.size() * sizeof(DOp)));
-    PQC_CUDA(cudaMemcpy(prog->d_ops, dops.data(), dops.size() * sizeof(DOp),
-                        cudaMemcpyHostToDevice));
-  }
-  if (!prog->gens.empty()) {
-    PQC_CUDA(cudaMalloc(&prog->d_gens, prog->gens.size() * sizeof(GenTerm)));
-    PQC_CUDA(cudaMemcpy(prog->d_gens, prog->gens.data(), prog->gens.size() * sizeof(GenTerm),
-                        cudaMemcpyHostToDevice));
-  }
+  prog->h_dops = dops;
+  return 0;
+}
+
+// Copy the plan to the device once (planning itself needs no GPU, so the planner can be
+// exercised by the CPU test-suite).
+int pqc_program_upload(const pqc_program* cprog) {
+  pqc_program* prog = const_cast<pqc_program*>(cprog);
+  if (prog->uploaded) return 0;
+  auto up = [&](auto& vec, auto** dptr) -> int {
+    if (vec.empty()) return 0;
+    PQC_CUDA(cudaMalloc(dptr, vec.size() * sizeof(vec[0])));
+    PQC_CUDA(cudaMemcpy(*dptr, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
+    return 0;
+  };
+  if (up(prog->h_dops, &prog->d_ops) || up(prog->gens, &prog->d_gens) ||
+      up(prog->h_mops, &prog->d_mops) || up(prog->h_sweeps, &prog->d_sweeps) ||
+      up(prog->h_tjobs, &prog->d_tjobs) || up(prog->h_zz, &prog->d_zz))
+    return -2;
+  prog->uploaded = true;
   return 0;
 }
 

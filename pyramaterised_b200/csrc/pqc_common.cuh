@@ -151,6 +151,13 @@ struct pqc_program {
   std::vector<int> v1_run;                   // pass indices of the plain run plan
   std::vector<V1Stage> v1_grad;              // stages of the derivative / QFIM plan
   std::vector<int> v1_gen_diag_off;          // per parameter: offset/count of diagonal terms
+  // host copies of the device arrays (uploaded lazily by pqc_program_upload)
+  std::vector<MOp> h_mops;
+  std::vector<SweepD> h_sweeps;
+  std::vector<TrigJob> h_tjobs;
+  std::vector<ZZTerm> h_zz;
+  std::vector<DOp> h_dops;
+  bool uploaded = false;
   MOp* d_mops = nullptr;
   SweepD* d_sweeps = nullptr;
   TrigJob* d_tjobs = nullptr;
@@ -201,6 +208,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // ------------------------------------------------------------------ cross-file host API
 int pqc_plan_program(pqc_program* prog);
 int pqc_plan_v1(pqc_program* prog);
+int pqc_program_upload(const pqc_program* prog);   // idempotent; needs a CUDA device
 int pqc_v1_run(const pqc_program* prog, const double* d_angles, long long ld, long long S,
                const c128* d_init, long long init_stride, c128* d_out, cudaStream_t st);
 int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long long ld, long long S,

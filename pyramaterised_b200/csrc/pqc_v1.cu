@@ -379,7 +379,9 @@ struct Builder {
       if (lpos[b] < 0) ps.obit[o++] = b;
     ps.low_run = 0;
     while (ps.low_run < cap && ps.lbit[ps.low_run] == ps.low_run) ps.low_run++;
-    ps.direct_ok = (n >= V1_LOCAL_BITS) && gcount[0] == 4 && ps.low_run >= 4;
+    // a sweep may talk to global memory directly when the three lowest index bits are lane
+    // bits: every 8 lanes then cover one full 128-byte line
+    ps.direct_ok = (n >= V1_LOCAL_BITS) && ps.low_run >= 3;
     if (sws.empty()) sws.push_back(SW{-1, {}, {}, {}});
     ps.sweep_off = (int)sweeps.size();
     ps.mop_off = (int)mops.size();
@@ -450,7 +452,7 @@ struct Builder {
       emit(sw.post);
       d.mop_end = (int)mops.size() - ps.mop_off;
       d.pad = (int)sw.pre.size() | ((int)sw.post.size() << 16);
-      const bool touches_low = d.rb[0] < 4;
+      const bool touches_low = d.rb[0] < 3;
       if (ps.direct_ok && !touches_low) {
         if (si == 0) d.io |= 1;
         if (si + 1 == sws.size()) d.io |= 2;
@@ -639,15 +641,58 @@ int pqc_plan_v1(pqc_program* prog) {
     prog->v1_grad_ok = true;
   }
 
-  auto upload = [&](auto& vec, auto** dptr) -> int {
-    if (vec.empty()) return 0;
-    PQC_CUDA(cudaMalloc(dptr, vec.size() * sizeof(vec[0])));
-    PQC_CUDA(cudaMemcpy(*dptr, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
-    return 0;
+  prog->h_mops = mops;
+  prog->h_sweeps = sweeps;
+  prog->h_tjobs = tjobs;
+  prog->h_zz = zz;
+  return 0;
+}
+
+// Human-readable plan (planner tests): one line per stage of the derivative plan
+// (or of the run plan when there is none).
+extern "C" PQC_API int pqc_program_describe(const pqc_program* prog, char* out, int64_t cap) {
+  if (!prog || !out || cap <= 0) return -1;
+  std::string s;
+  char buf[256];
+  auto pass_line = [&](const V1Pass& ps) {
+    char buf[256];
+    int nm = 0;
+    std::string kinds;
+    for (int i = 0; i < ps.nsweeps; ++i) {
+      const SweepD& sw = prog->h_sweeps[ps.sweep_off + i];
+      snprintf(buf, sizeof(buf), " [rb %d,%d,%d,%d io%d:", sw.rb[0], sw.rb[1], sw.rb[2], sw.rb[3], sw.io);
+      kinds += buf;
+      for (int m = sw.mop_begin; m < sw.mop_end; ++m, ++nm) {
+        snprintf(buf, sizeof(buf), " %d", prog->h_mops[ps.mop_off + m].kind);
+        kinds += buf;
+      }
+      kinds += "]";
+    }
+    snprintf(buf, sizeof(buf), "sweeps=%d mops=%d spawns=%d direct=%d/%d", ps.nsweeps, nm,
+             (int)ps.spawn_param.size(), ps.io_first & 1, (ps.io_last >> 1) & 1);
+    return std::string(buf) + kinds;
   };
-  if (upload(mops, &prog->d_mops) || upload(sweeps, &prog->d_sweeps) ||
-      upload(tjobs, &prog->d_tjobs) || upload(zz, &prog->d_zz))
-    return -2;
+  if (prog->v1_grad_ok) {
+    for (const V1Stage& sg : prog->v1_grad) {
+      if (sg.type == 0) {
+        snprintf(buf, sizeof(buf), "PASS partners=%d ", (int)sg.partners.size());
+        s += std::string(buf) + pass_line(prog->v1_passes[sg.pass]) + "\n";
+      } else if (sg.type == 1) {
+        snprintf(buf, sizeof(buf), "GATHER params=%d\n", (int)sg.gather_params.size());
+        s += buf;
+      } else {
+        snprintf(buf, sizeof(buf), "DOTS partners=%d\n", (int)sg.partners.size());
+        s += buf;
+      }
+    }
+  } else if (prog->v1_ok) {
+    for (int pi : prog->v1_run) s += "PASS " + pass_line(prog->v1_passes[pi]) + "\n";
+  } else {
+    snprintf(buf, sizeof(buf), "v0 plan: %d run passes\n", (int)prog->run_passes.size());
+    s += buf;
+  }
+  if ((int64_t)s.size() + 1 > cap) s.resize((size_t)cap - 1);
+  memcpy(out, s.c_str(), s.size() + 1);
   return 0;
 }
 
@@ -1379,6 +1424,7 @@ static int launch_v1(const V1Args& a, cudaStream_t st) {
 int pqc_v1_run(const pqc_program* prog, const double* d_angles, long long ld, long long S,
                const c128* d_init, long long init_stride, c128* d_out, cudaStream_t st) {
   const int mode = !d_init ? 1 : (init_stride == 0 ? 2 : 3);
+  if (pqc_program_upload(prog)) return -2;
   {
     const int rc = launch_init(d_out, mode, d_init, init_stride, S, 1, prog->n, st);
     if (rc) return rc;
@@ -1447,6 +1493,7 @@ int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long lon
   const int mode = !d_init ? 1 : 2;
   const int ntiles = 1 << std::max(0, n - V1_LOCAL_BITS);
   bool first = true;
+  if (pqc_program_upload(prog)) return -2;
   {
     const int rc = launch_init(pp[0], mode, d_init, 0, S, slots_total, n, st);
     if (rc) return rc;

@@ -96,8 +96,7 @@ class Program:
     (kind, q0, q1, param, param2, group, scale, offset)."""
 
     def __init__(self, n_qubits, n_params, ops):
-        device()
-        lib = _lib.load()
+        lib = _lib.load()               # planning is host-only; the device is needed to run
         self.n = int(n_qubits)
         self.P = int(n_params)
         self.ops = list(ops)
@@ -117,6 +116,12 @@ class Program:
     @property
     def dim(self):
         return 1 << self.n
+
+    def describe(self):
+        """The execution plan, one line per stage (host-only)."""
+        buf = C.create_string_buffer(1 << 20)
+        _lib.check(_lib.load().pqc_program_describe(self._h, buf, len(buf)))
+        return buf.value.decode()
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -136,3 +136,25 @@ def test_no_cpu_fallback_and_no_oracle_import():
         qc = pyqc.templates.generate_circuit("generic_HE", 3, 1)
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             qc.run("random")
+
+
+def test_planner_runs_without_gpu_and_fuses_tfim_layers():
+    """Planning is host-only.  TFIM-16x16 must come out as ONE pass per layer (17 with the
+    Hadamard layer) + one gather per R_x parameter, every pass loading and storing directly."""
+    qc = pyqc.templates.generate_circuit("TFIM", 16, 16)
+    prog = qc.program
+    lines = prog.describe().splitlines()
+    passes = [l for l in lines if l.startswith("PASS")]
+    gathers = [l for l in lines if l.startswith("GATHER")]
+    assert prog.n_qfim_passes == 17 and len(gathers) == 16
+    assert all("direct=1/1" in l for l in passes)
+    assert sum("spawns=1" in l for l in passes) == 16          # R_zz rings: in-pass diagonal spawns
+    assert all(l.count("[rb") <= 3 for l in passes[:17])        # three sweeps per pass
+    # the 256 R_zz of the circuit became 16 fused phase ops (internal opcode 32)
+    assert sum(l.count(" 32") for l in passes) == 16
+    xxz = pyqc.templates.generate_circuit("XXZ", 16, 16, shuffle=False).program
+    assert xxz.n_qfim_passes <= 48 and " 33" in xxz.describe()   # XY fusion (opcode 33)
+    small = pyqc.templates.generate_circuit("generic_HE", 10, 10).program
+    assert small.n_passes <= 22 and small.grad_supported
+    tiny = pyqc.templates.generate_circuit("NPQC", 4, 4).program     # n < 8: v0 tile plan
+    assert "v0 plan" in tiny.describe()
