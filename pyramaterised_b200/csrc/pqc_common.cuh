@@ -114,6 +114,7 @@ struct SweepD {
   int pad;                 // npre | npost << 16
   unsigned char tl[8];     // local position fed by thread bit t (the 8 non-register positions)
   unsigned char tg[8];     // global amplitude bit of that position, 255 = item bit (n < 12)
+  unsigned short sz[4];    // swizzled shared-memory mask of register bit k
 };
 struct TrigJob {           // per-item trig table entry (or run of entries) to fill
   int kind, param, param2, slot, npairs, pad;

@@ -2,6 +2,8 @@
 // Each entry point cites the reference lines it replaces (/root/reference/pyramaterised/).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "pqc_common.cuh"
 
@@ -393,6 +395,130 @@ __global__ void __launch_bounds__(256) k_fidelity(const c128* __restrict__ A, lo
     }
 }
 
+// ---------------------------------------------------------------------------------
+// FP64 tensor-core version of the pair-fidelity block (the one genuinely dense contraction
+// of the path): C = conj(A) B^T as four real DMMA streams per 8x8x4 step,
+//   Re C = Ar Br^T + Ai Bi^T,   Im C = Ar Bi^T - Ai Br^T
+// (mma.sync.aligned.m8n8k4.f64 -- tcgen05 has no FP64 kind).  64x64 pair tile per CTA, 8
+// warps of 32x16 pairs, K streamed 16 amplitudes at a time through cp.async double-buffered
+// shared memory (row stride 320 B so the 16-byte fragment loads are bank-conflict free).
+// Epilogue identical to k_fidelity: np.abs(z)**2, numpy-exact binning, int64 atomics.
+// ---------------------------------------------------------------------------------
+#define DT 64
+#define DK 16
+#define DROW 20                      // complex per padded row (16 + 4)
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gmem));
+}
+
+__global__ void __launch_bounds__(256, 2) k_fidelity_dmma(
+    const c128* __restrict__ A, long long SA, const c128* __restrict__ Bm, long long SB, int n,
+    int triangular, long long bins, double step, unsigned long long* __restrict__ hist,
+    double* __restrict__ Fout) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  c128* sA = reinterpret_cast<c128*>(smraw);                 // [2][DT][DROW]
+  c128* sB = sA + 2 * DT * DROW;
+  long long bi, bj;
+  const long long nbj = (SB + DT - 1) / DT;
+  if (triangular) {
+    const long long t = blockIdx.x, nb = nbj;
+    const double disc = (2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t;
+    bi = (long long)(((2.0 * nb + 1.0) - sqrt(disc)) * 0.5);
+    if (bi < 0) bi = 0;
+    while (bi > 0 && bi * nb - bi * (bi - 1) / 2 > t) --bi;
+    while ((bi + 1) * nb - (bi + 1) * bi / 2 <= t) ++bi;
+    bj = bi + (t - (bi * nb - bi * (bi - 1) / 2));
+  } else {
+    bi = blockIdx.x / nbj;
+    bj = blockIdx.x % nbj;
+  }
+  const long long D = 1ll << n;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int wr = (warp >> 2) * 32, wc = (warp & 3) * 16;       // warp tile origin (rows x cols)
+
+  // each thread moves 4 + 4 16-byte pieces per stage: row = e / 16, k = e % 16
+  auto stage_load = [&](int buf, long long k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + q * 256, r = e >> 4, kk = e & 15;
+      long long ra = bi * DT + r, rb = bj * DT + r;
+      if (ra >= SA) ra = SA - 1;                                // clamp: masked in the epilogue
+      if (rb >= SB) rb = SB - 1;
+      cp_async16(sA + (buf * DT + r) * DROW + kk, A + ra * D + k0 + kk);
+      cp_async16(sB + (buf * DT + r) * DROW + kk, Bm + rb * D + k0 + kk);
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+
+  double re[4][2][2], im[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) re[i][j][0] = re[i][j][1] = im[i][j][0] = im[i][j][1] = 0.0;
+
+  const long long nk = D / DK;
+  stage_load(0, 0);
+  for (long long ks = 0; ks < nk; ++ks) {
+    const int buf = (int)(ks & 1);
+    if (ks + 1 < nk) {
+      stage_load(buf ^ 1, (ks + 1) * DK);
+      asm volatile("cp.async.wait_group 1;");
+    } else {
+      asm volatile("cp.async.wait_group 0;");
+    }
+    __syncthreads();
+    const c128* a_s = sA + buf * DT * DROW;
+    const c128* b_s = sB + buf * DT * DROW;
+#pragma unroll
+    for (int kk = 0; kk < DK / 4; ++kk) {
+      c128 fa[4], fb[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) fa[i] = a_s[(wr + 8 * i + g) * DROW + kk * 4 + t4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) fb[j] = b_s[(wc + 8 * j + g) * DROW + kk * 4 + t4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          dmma(re[i][j][0], re[i][j][1], fa[i].x, fb[j].x);
+          dmma(re[i][j][0], re[i][j][1], fa[i].y, fb[j].y);
+          dmma(im[i][j][0], im[i][j][1], fa[i].x, fb[j].y);
+          dmma(im[i][j][0], im[i][j][1], -fa[i].y, fb[j].x);
+        }
+    }
+    __syncthreads();
+  }
+  // accumulator element c of thread (g, t4): row g, column 2 * t4 + c of its 8x8 tile
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const long long row = bi * DT + wr + 8 * i + g, col = bj * DT + wc + 8 * j + 2 * t4 + c;
+        if (row >= SA || col >= SB) continue;
+        if (triangular && col <= row) continue;
+        const double mag = hypot(re[i][j][c], im[i][j][c]);
+        const double f = mag * mag;
+        if (hist) {
+          const long long b = np_hist_bin(f, bins, step);
+          if (b >= 0) atomicAdd(hist + b, 1ull);
+        }
+        if (Fout) {
+          const long long idx = triangular ? (row * (2 * SA - row - 1) / 2 + (col - row - 1))
+                                           : (row * SB + col);
+          Fout[idx] = f;
+        }
+      }
+}
+
 extern "C" int pqc_fidelity_hist(const pqc_c128* d_A, int64_t n_a, const pqc_c128* d_B,
                                  int64_t n_b, int n, int triangular, int64_t bins,
                                  long long* d_hist, double* d_F, void* stream) {
@@ -403,6 +529,22 @@ extern "C" int pqc_fidelity_hist(const pqc_c128* d_A, int64_t n_a, const pqc_c12
   const long long nbi = (n_a + FT - 1) / FT, nbj = (n_b + FT - 1) / FT;
   const long long grid = triangular ? nbi * (nbi + 1) / 2 : nbi * nbj;
   if (grid > 0x7fffffffLL) PQC_FAIL(-1, "fidelity grid too large; split the block");
+  const char* force = getenv("PQC_FIDELITY");
+  const bool use_dmma = n >= 4 && !(force && strcmp(force, "fma") == 0);
+  if (use_dmma) {
+    static bool attr_set = false;
+    const size_t smem = 4 * DT * DROW * sizeof(c128);
+    if (!attr_set) {
+      PQC_CUDA(cudaFuncSetAttribute(k_fidelity_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+      attr_set = true;
+    }
+    k_fidelity_dmma<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(
+        (const c128*)d_A, n_a, (const c128*)d_B, n_b, n, triangular, bins,
+        bins > 0 ? 1.0 / (double)bins : 0.0, (unsigned long long*)d_hist, d_F);
+    PQC_LAUNCH_CHECK();
+    return 0;
+  }
   k_fidelity<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
       (const c128*)d_A, n_a, (const c128*)d_B, n_b, n, triangular, bins,
       bins > 0 ? 1.0 / (double)bins : 0.0, (unsigned long long*)d_hist, d_F);

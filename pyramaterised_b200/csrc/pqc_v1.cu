@@ -399,6 +399,10 @@ struct Builder {
       }
       std::sort(rb.begin(), rb.end());
       for (int k = 0; k < 4; ++k) d.rb[k] = rb[k];
+      for (int k = 0; k < 4; ++k) {
+        const unsigned i = 1u << rb[k];
+        d.sz[k] = (unsigned short)(i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u));
+      }
       {
         int t = 0;
         for (int posn = 0; posn < V1_LOCAL_BITS; ++posn) {
@@ -974,7 +978,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     }
     (void)rmask;
     // swz is linear over GF(2): swz(base | sel) = swz(base) ^ swz(sel)
-    const uint32_t sb = swz(base), s0 = swz(m0), s1 = swz(m1), s2 = swz(m2), s3 = swz(m3);
+    const uint32_t sb = swz(base), s0 = sw.sz[0], s1 = sw.sz[1], s2 = sw.sz[2], s3 = sw.sz[3];
     // global amplitude index of register j = amp0 | (selected g-masks)
     const uint32_t g0 = 1u << A.lbit[sw.rb[0]], g1 = 1u << A.lbit[sw.rb[1]],
                    g2 = 1u << A.lbit[sw.rb[2]], g3 = 1u << A.lbit[sw.rb[3]];
@@ -1070,6 +1074,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
       for (int j = 0; j < 16; ++j) a[j] = sm[lsb ^ XSEL4(j, ls0, ls1, ls2, ls3)];
     }
 
+    double fscale = 1.0;      // product of the cos factors of this sweep's tangent-form layers
     for (int mi = sw.mop_begin + npre; mi < sw.mop_end - npost; ++mi) {
       const MOp& m = s_mops[mi];
       const int kind = m.kind;
@@ -1086,7 +1091,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
         op_rx_t<1>(a, c1.x);
         op_rx_t<2>(a, c2.x);
         op_rx_t<3>(a, c3.x);
-        op_scale(a, (c0.y * c1.y) * (c2.y * c3.y));
+        fscale *= (c0.y * c1.y) * (c2.y * c3.y);
       } else if (kind == PQC_K_LAYER_REAL4) {
         const int sk = m.subk;
         double f = 1.0;
@@ -1098,7 +1103,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
   }
         REAL_SLOT(0) REAL_SLOT(1) REAL_SLOT(2) REAL_SLOT(3)
 #undef REAL_SLOT
-        op_scale(a, f);
+        fscale *= f;
       } else if (kind == PQC_K_ZZSUM) {
         // count of anti-aligned pairs; <= 4 (mask, shift) terms, loaded once
         uint32_t zm[4];
@@ -1215,6 +1220,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
       }
     }
 
+    if (fscale != 1.0) op_scale(a, fscale);       // uniform per item
     const bool ds = (si + 1 == A.nsweeps) && (sw.io & 2);
     uint32_t sc[4] = {1u, 2u, 4u, 8u}, sv = 0u;
     if (npost) affine(sw.mop_end - npost, sw.mop_end, false, sc, sv);

@@ -309,3 +309,33 @@ def test_operator_algebra_and_state_surface(golden):
     assert out.dims == [[2] * N, [1] * N] and out.data.toarray().shape == (8, 1)
     d = g.derivative() * out
     assert np.abs(d.numpy() - orc.apply_1q(out.numpy()[None], N, 1, -0.5j * orc.SY)[0]).max() < ATOL
+
+
+def test_fidelity_dmma_matches_fma_and_numpy(monkeypatch):
+    """The FP64 tensor-core pair-fidelity kernel against the CUDA-core one and numpy, on
+    ragged sizes, rectangular and triangular blocks, with identical integer histograms."""
+    rng = np.random.default_rng(8)
+    for n, SA, SB in ((4, 5, 3), (6, 70, 70), (9, 131, 64), (10, 200, 77)):
+        D = 2 ** n
+        A = rng.normal(size=(SA, D)) + 1j * rng.normal(size=(SA, D))
+        A /= np.linalg.norm(A, axis=1, keepdims=True)
+        B = rng.normal(size=(SB, D)) + 1j * rng.normal(size=(SB, D))
+        B /= np.linalg.norm(B, axis=1, keepdims=True)
+        tA, tB = torch.as_tensor(A, device="cuda"), torch.as_tensor(B, device="cuda")
+        bins = 97
+        monkeypatch.setenv("PQC_FIDELITY", "fma")
+        h0, F0 = engine.fidelity_hist(tA, tB, bins=bins, want_F=True)
+        t0, T0 = engine.fidelity_hist(tA, bins=bins, want_F=True)
+        monkeypatch.delenv("PQC_FIDELITY")
+        h1, F1 = engine.fidelity_hist(tA, tB, bins=bins, want_F=True)
+        t1, T1 = engine.fidelity_hist(tA, bins=bins, want_F=True)
+        ref = np.abs(A.conj() @ B.T) ** 2
+        assert np.abs(F1.cpu().numpy() - ref).max() < 1e-13
+        assert np.abs(F0.cpu().numpy() - ref).max() < 1e-13
+        tri = np.abs(A.conj() @ A.T)[np.triu_indices(SA, 1)] ** 2
+        assert np.abs(T1.cpu().numpy() - tri).max() < 1e-13
+        assert np.abs(T0.cpu().numpy() - tri).max() < 1e-13
+        assert int(h1.sum()) == SA * SB and int(t1.sum()) == SA * (SA - 1) // 2
+        assert np.array_equal(h1.cpu().numpy(),
+                              np.histogram(F1.cpu().numpy().ravel(), bins=bins, range=(0, 1))[0])
+        assert np.abs(h1.cpu().numpy() - h0.cpu().numpy()).sum() <= 2
