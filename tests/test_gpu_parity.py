@@ -339,3 +339,63 @@ def test_fidelity_dmma_matches_fma_and_numpy(monkeypatch):
         assert np.array_equal(h1.cpu().numpy(),
                               np.histogram(F1.cpu().numpy().ravel(), bins=bins, range=(0, 1))[0])
         assert np.abs(h1.cpu().numpy() - h0.cpu().numpy()).sum() <= 2
+
+
+# ---- size-independent properties at BASELINE.json's full sizes ------------------------------
+def test_config2_full_size_properties():
+    """generic_HE 10q x 10 layers, S = 1e5: 4 999 950 000 pairs into 37 499 625 bins."""
+    S = 100000
+    qc = pyqc.templates.generate_circuit("generic_HE", 10, 10)
+    ang = torch.from_numpy(np.random.default_rng(1).random((S, qc.n_true_params)) * 2 * np.pi)
+    st = qc.run_batch(ang.cuda())
+    nrm = engine.overlap(st[:4096], st[:4096]).cpu().numpy()
+    assert np.abs(nrm - 1).max() < 1e-12
+    Q = engine.meyer_wallach(st).cpu().numpy()
+    assert Q.min() > 0.5 and Q.max() <= 1 + 1e-12
+    pairs = S * (S - 1) // 2
+    bins = engine.n_bins(pairs)
+    assert (pairs, bins) == (4999950000, 37499625)
+    hist, _ = engine.fidelity_hist(st, bins=bins)
+    assert int(hist.sum().item()) == pairs                       # every pair binned exactly once
+    kl = float(engine.kl_haar(hist, 2.0 ** 10).item())
+    assert 0 <= kl < 1e-2                                        # deep HE circuit ~ Haar
+    # integer histogram is invariant under a permutation of the sample set (subset for time)
+    sub = st[:3000]
+    perm = torch.randperm(3000, generator=torch.Generator().manual_seed(3)).cuda()
+    b = engine.n_bins(3000 * 2999 // 2)
+    h1, _ = engine.fidelity_hist(sub, bins=b)
+    h2, _ = engine.fidelity_hist(sub[perm].contiguous(), bins=b)
+    assert torch.equal(h1, h2)
+    # sharded form (dist.py partition, single rank) gives the same integer counts
+    from pyramaterised_b200 import dist as pdist
+    assert torch.equal(pdist.sharded_fidelity_hist(sub, b), h1)
+
+
+def test_config4_full_size_stabilizer_states_have_zero_magic():
+    """NPQC 12q, S = 1000: with Clifford angles every state is a stabilizer state, so the
+    Renyi-2 magic and the GKP magic vanish (cf. tests.py:284-295 for the Bell state), and for
+    random angles 0 <= M2 <= ln((2^n + 1) / 2)."""
+    qc = pyqc.templates.generate_circuit("NPQC", 12, 6)
+    P = qc.n_true_params
+    rng = np.random.default_rng(12)
+    cl = rng.integers(0, 4, size=(1000, P)) * (np.pi / 2)
+    mg = engine.magic(qc.run_batch(cl), (2.0, 0.5)).cpu().numpy()
+    assert np.abs(mg[0]).max() < 1e-9 and np.abs(mg[1]).max() < 1e-9
+    rnd = rng.random((1000, P)) * 2 * np.pi
+    m2 = engine.magic(qc.run_batch(rnd), (2.0,)).cpu().numpy()[0]
+    assert m2.min() > -1e-9 and m2.max() <= np.log((2 ** 12 + 1) / 2) + 1e-9
+
+
+def test_config3_size_npqc_identity_qfim_16q():
+    """The NPQC theorem QFIM(theta_ref) = I (tests.py:103-128) at 16 qubits: an exact
+    known answer for the multi-pass derivative pipeline at the headline state size."""
+    layers, th = pyqc.templates.NPQC_layers(4, 16)
+    qc = pyqc.PQC(16)
+    for l in layers:
+        qc.add_layer(l)
+    F = qc.qfim_batch(np.array([th, th], dtype=np.float64)).cpu().numpy()
+    assert np.abs(F - np.eye(F.shape[1])).max() < 1e-12
+    qc.update_state(th)
+    Q = pyqc.measure.Measurements(qc).get_QFI()
+    assert np.abs(Q - np.eye(len(Q))).max() < 1e-12
+    assert pyqc.measure.Measurements(qc).get_effective_quantum_dimension(1e-12) == len(th)
