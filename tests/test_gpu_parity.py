@@ -399,3 +399,67 @@ def test_config3_size_npqc_identity_qfim_16q():
     Q = pyqc.measure.Measurements(qc).get_QFI()
     assert np.abs(Q - np.eye(len(Q))).max() < 1e-12
     assert pyqc.measure.Measurements(qc).get_effective_quantum_dimension(1e-12) == len(th)
+
+
+# ---- host loops that drive the hot path ---------------------------------
+def test_tfim_training_reaches_ground_state():
+    """/root/reference/tests.py:130-156: BFGS on a 4-qubit, 4-layer TFIM circuit."""
+    import random
+    from math import isclose
+    N, p = 4, 4
+    tfim = pyqc.PQC(N)
+    ham = pyqc.templates.TFIM_hamiltonian(N, g=1, h=0)
+    e0, ground = ham.groundstate()
+    tfim.set_H(ham)
+    for l in pyqc.templates.TFIM_layers(p, N):
+        tfim.add_layer(l)
+    random.seed(11)
+    angles = [random.random() * np.pi for _ in range(2 * p)]
+    m = pyqc.measure.Measurements(tfim)
+    energy, traj, magics, ents, gkps = m.train(method="BFGS", angles=angles)
+    assert len(traj) == len(magics) == len(ents) == len(gkps) > 2
+    assert isclose(tfim.fidelity(ground), 1, abs_tol=1e-6)
+    assert abs(energy - e0) < 1e-6
+    # gradient descent branch: energy decreases monotonically for a small rate
+    e2, traj2, *_ = m.train(method="gradient", angles=angles, rate=0.01, epsilon=1e-3)
+    assert all(b <= a + 1e-12 for a, b in zip(traj2, traj2[1:]))
+
+
+def test_gradient_vector_matches_finite_differences():
+    qc = pyqc.templates.generate_circuit("generic_HE", 5, 2)
+    m = pyqc.measure.Measurements(qc)
+    th = list(np.random.default_rng(2).random(qc.n_true_params) * 2 * np.pi)
+    g = np.array(m.get_gradient_vector(th))
+    eps = 1e-6
+    for k in (0, 7, 19):
+        up, dn = list(th), list(th)
+        up[k] += eps
+        dn[k] -= eps
+        assert abs((qc.cost(up) - qc.cost(dn)) / (2 * eps) - g[k]) < 1e-7
+
+
+def test_effective_hilbert_space_generic_he():
+    """/root/reference/tests.py:297-309 for n = 2, 4 (statistical, rel 0.1 as there)."""
+    from math import isclose
+    reseed()
+    for n in (2, 4):
+        qc = pyqc.templates.generate_circuit("generic_HE", n, 2 * n)
+        m = pyqc.measure.Measurements(qc)
+        f = m._gen_f_samples(150)
+        assert isclose(m.find_eff_H(f, n), 2 ** n, rel_tol=0.1)
+
+
+def test_example_script_flow():
+    """/root/reference/example.py end to end (sizes reduced for time)."""
+    import random
+    ex = cases.build_example4(pyqc)
+    cap = pyqc.measure.Measurements(ex)
+    reseed()
+    assert cap.expressibility(150) > 0 and cap.entropy_of_magic(150) > 0
+    random.seed(5)
+    ang = [random.random() * np.pi for _ in range(12)]
+    out = cap.train(method="BFGS", angles=ang)
+    cap.set_minimise_function(cap.theta_to_magic)
+    out_magic = cap.train(method="BFGS", angles=ang)
+    assert out_magic[2][-1] >= out[2][-1] - 1e-6           # optimising for magic finds more magic
+    assert "4 qubit, 3 layer deep PQC" in repr(ex)
