@@ -211,8 +211,19 @@ class PQC():
     # ---- derivative states (circuit.py:149-192) ----------------------------------------------------
     def _gradient_buffer(self):
         if not self.program.grad_supported or not self._derivatives_exact():
-            raise NotImplementedError("derivative states for this gate set (fSim family / "
-                                      "non-commuting shared_parameter) are not lowered yet")
+            raise NotImplementedError("derivative states for this gate set (non-commuting "
+                                      "shared_parameter) are not lowered yet")
+        # quirk Q2 (circuit.py:186-189): for a two-parameter gate the reference re-finds the
+        # gate with an index into the PARAMETERISED list; that is the intended gate only when
+        # every earlier gate is parameterised.  Anything else is fenced off, not imitated.
+        count = 0
+        for loc, g in enumerate(self.gates):
+            if g.param_count == 0:
+                continue
+            if g.param_count == 2 and count != loc:
+                raise NotImplementedError("two-parameter gate after a non-parameterised gate: the "
+                                          "reference differentiates the wrong gate here (quirk Q2)")
+            count += 1
         raw = np.array([a for g in self.gates if g.param_count > 0
                         for a in self._raw_of(g)], dtype=np.float64)
         return self.program.gradients(raw.reshape(1, -1), init=self.initial_state.tensor)[0]

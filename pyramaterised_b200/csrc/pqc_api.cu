@@ -216,8 +216,10 @@ static int forward_derivatives(const pqc_program* prog, const double* d_angles, 
       mode = 0;
     }
     const int g0 = prog->gen_off[p], g1 = prog->gen_off[p + 1];
-    int rc = pqc_pauli_apply_slots(buf, buf, n, S, slots_total, 0, p + 1, prog->d_gens + g0,
-                                   g1 - g0, st);
+    int rc = prog->pspawn[p].type == 1
+                 ? pqc_pair_spawn(buf, n, S, slots_total, p + 1, prog->pspawn[p], d_angles, ld, st)
+                 : pqc_pauli_apply_slots(buf, buf, n, S, slots_total, 0, p + 1,
+                                         prog->d_gens + g0, g1 - g0, st);
     if (rc) return rc;
     if (d_G) {
       const long long grid = S * (p + 2);

@@ -162,6 +162,7 @@ int pqc_plan_program(pqc_program* prog) {
     }
   }
   int prev = 0;
+  prog->pspawn.assign(prog->P, ParamSpawn());
   for (int p = 0; p < prog->P; ++p) {
     prog->gen_off[p] = (int)prog->gens.size();
     if (last[p] < 0 || last[p] + 1 < prev) {
@@ -169,17 +170,29 @@ int pqc_plan_program(pqc_program* prog) {
       prog->grad_reason = "parameter slots are not used in gate order";
       break;
     }
-    for (int i = prev; i <= last[p]; ++i) {
+    // every op carrying slot p (both slots of an fSim sit on the same op, so the segment of
+    // its second slot is empty and the op is found behind `prev`)
+    for (int i = std::min(prev, last[p]); i <= last[p]; ++i) {
       const pqc_op& op = prog->ops[i];
-      if (op.param == p || op.param2 == p) {
-        if (!generator_terms(op, n, prog->gens)) {
-          prog->grad_supported = false;
-          prog->grad_reason = "derivative of this gate kind (fSim family) is not lowered yet";
-        }
+      if (op.param != p && op.param2 != p) continue;
+      if (op.kind == PQC_OP_FSIM || op.kind == PQC_OP_FIXED_FSIM) {
+        // the reference's "derivative" matrices of gates.py:609-648,719-737 (quirk Q3)
+        ParamSpawn& ps = prog->pspawn[p];
+        ps.type = 1;
+        ps.b0 = n - 1 - op.q0;
+        ps.b1 = n - 1 - op.q1;
+        ps.p_theta = op.param;
+        ps.p_phi = op.param2;
+        ps.offset = op.offset;
+        ps.phi_fixed = op.scale;
+        ps.which = op.kind == PQC_OP_FIXED_FSIM ? 3 : (op.param == p ? 1 : 2);
+      } else if (!generator_terms(op, n, prog->gens)) {
+        prog->grad_supported = false;
+        prog->grad_reason = "no derivative rule for this gate kind";
       }
     }
     plan_range(prog, prev, last[p] + 1, prog->seg_passes[p], dops);
-    prev = last[p] + 1;
+    prev = std::max(prev, last[p] + 1);
   }
   prog->gen_off[prog->P] = (int)prog->gens.size();
   if (prog->grad_supported) plan_range(prog, prev, nops, prog->seg_passes[prog->P], dops);

@@ -141,8 +141,18 @@ struct V1Stage {
   std::vector<int> partners;     // parameters whose Gram column is taken on this pass' load
 };
 
+// how the derivative vector of a parameter is created from psi
+struct ParamSpawn {
+  int type = 0;            // 0: sum of Pauli generators (gens); 1: fSim-family pair matrix
+  int b0 = -1, b1 = -1;    // pair bits (type 1)
+  int p_theta = -1, p_phi = -1;
+  int which = 0;           // 1 d/dtheta of fSim, 2 d/dphi of fSim, 3 d/dtheta of fixed_fSim
+  double offset = 0.0, phi_fixed = 0.0;
+};
+
 struct pqc_program {
   int n = 0, P = 0;
+  std::vector<ParamSpawn> pspawn;
   std::vector<pqc_op> ops;
   int tile_bits = 12;
   // ---- v1 plans
@@ -226,6 +236,8 @@ int pqc_pauli_apply_slots(const c128* src, c128* dst, int n, long long S, int sl
                           int src_slot, int dst_slot, const GenTerm* d_terms, int nterms,
                           cudaStream_t st);
 int pqc_qfim_finalize(const c128* d_G, long long S, int P, double* d_F, cudaStream_t st);
+int pqc_pair_spawn(c128* buf, int n, long long S, int slots_total, int dst_slot,
+                   const ParamSpawn& ps, const double* d_angles, long long ld, cudaStream_t st);
 int pqc_launch_pass(const pqc_program* prog, const Pass& ps, c128* buf, const c128* init,
                     long long init_stride, int init_mode, const double* d_angles, long long ld,
                     long long n_items, int slots_active, int slots_total, int slot_base,

@@ -198,6 +198,55 @@ int pqc_pauli_apply_slots(const c128* src, c128* dst, int n, long long S, int sl
   return 0;
 }
 
+// ---------------------------------------------------------------------------------
+// fSim-family derivative spawn: dst <- M psi with M = diag(1, [[d, o],[o, d]], corner) on the
+// pair (b0, b1): the element-wise "d/dtheta" / "d/dphi" matrices of gates.py:609-648,719-737
+// (quirk Q3: [0,0] stays 1 and [3,3] is not differentiated).  M commutes with the fSim gate
+// (both are polynomials of the same 2x2 block), so it may be applied right after the gate.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pair_spawn(c128* __restrict__ buf, int n, long long S,
+                                                    int slots_total, int dst_slot, ParamSpawn ps,
+                                                    const double* __restrict__ angles, long long ld) {
+  const long long D = 1ll << n, total = S * D;
+  const long long ma = 1ll << ps.b0, mb = 1ll << ps.b1;
+  for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < total;
+       g += (long long)gridDim.x * 256) {
+    const long long s = g >> n, x = g & (D - 1);
+    const c128* psi = buf + ((s * slots_total) << n);
+    double th = ps.offset + (ps.p_theta >= 0 ? angles[s * ld + ps.p_theta] : 0.0);
+    const double ph = ps.which == 3 ? 0.0 : (ps.p_phi >= 0 ? angles[s * ld + ps.p_phi] : ps.phi_fixed);
+    double sn, cs, sp, cp;
+    sincos(th, &sn, &cs);
+    sincos(ph, &sp, &cp);
+    const bool ba = (x & ma) != 0, bb = (x & mb) != 0;
+    const c128 v = psi[x];
+    c128 out;
+    if (!ba && !bb) {
+      out = v;
+    } else if (ba && bb) {
+      // corner: e^{-i phi} (which 1), -i e^{-i phi} (which 2), 1 (which 3)
+      const double cr = ps.which == 3 ? 1.0 : (ps.which == 1 ? cp : -sp);
+      const double ci = ps.which == 3 ? 0.0 : (ps.which == 1 ? -sp : -cp);
+      out = make_double2(v.x * cr - v.y * ci, v.y * cr + v.x * ci);
+    } else {
+      const c128 w = psi[x ^ ma ^ mb];
+      // which 2: diag cos, off -i sin;  which 1 / 3: diag -sin, off -i cos
+      const double d = ps.which == 2 ? cs : -sn, o = ps.which == 2 ? sn : cs;
+      out = make_double2(d * v.x + o * w.y, d * v.y - o * w.x);
+    }
+    buf[((s * slots_total + dst_slot) << n) + x] = out;
+  }
+}
+
+int pqc_pair_spawn(c128* buf, int n, long long S, int slots_total, int dst_slot,
+                   const ParamSpawn& ps, const double* d_angles, long long ld, cudaStream_t st) {
+  const long long total = S << n;
+  const long long grid = std::min<long long>((total + 255) / 256, 148 * 32);
+  k_pair_spawn<<<(unsigned)grid, 256, 0, st>>>(buf, n, S, slots_total, dst_slot, ps, d_angles, ld);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void __launch_bounds__(256) k_pauli_expect(const c128* __restrict__ states, int n,
                                                       const GenTerm* __restrict__ terms, int nterms,
                                                       c128* __restrict__ out) {

@@ -530,9 +530,19 @@ int pqc_plan_v1(pqc_program* prog) {
     if (param_block[p] < param_block[p - 1]) grad_ok = false;
   std::vector<bool> param_diag(P, true);
   if (grad_ok)
-    for (int p = 0; p < P; ++p)
-      for (int t = prog->gen_off[p]; t < prog->gen_off[p + 1]; ++t)
+    for (int p = 0; p < P; ++p) {
+      if (prog->pspawn[p].type == 1) param_diag[p] = false;      // fSim family: pair-matrix spawn
+      double cr = 0.0, ci = 0.0;
+      for (int t = prog->gen_off[p]; t < prog->gen_off[p + 1]; ++t) {
         if (prog->gens[t].xmask) param_diag[p] = false;
+        // the in-pass generator multiply assumes one common coefficient
+        if (t > prog->gen_off[p] && (prog->gens[t].re != cr || prog->gens[t].im != ci))
+          param_diag[p] = false;
+        cr = prog->gens[t].re;
+        ci = prog->gens[t].im;
+      }
+      if (prog->gen_off[p + 1] == prog->gen_off[p]) param_diag[p] = false;
+    }
 
   std::vector<MOp> mops;
   std::vector<SweepD> sweeps;
@@ -1552,14 +1562,24 @@ int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long lon
       g.cb = std::min(n, V1_LOCAL_BITS);
       g.slots_total = slots_total;
       g.gens = prog->d_gens;
-      for (size_t k0 = 0; k0 < sg.gather_params.size(); k0 += V1_MAX_SPAWN) {
-        g.nparams = (int)std::min<size_t>(V1_MAX_SPAWN, sg.gather_params.size() - k0);
+      std::vector<int> pauli_params;
+      for (int p : sg.gather_params) {
+        nlive = std::max(nlive, p + 2);
+        if (prog->pspawn[p].type == 1) {
+          const int rc = pqc_pair_spawn(pp[cur], n, S, slots_total, 1 + p, prog->pspawn[p],
+                                        d_angles, ld, st);
+          if (rc) return rc;
+        } else {
+          pauli_params.push_back(p);
+        }
+      }
+      for (size_t k0 = 0; k0 < pauli_params.size(); k0 += V1_MAX_SPAWN) {
+        g.nparams = (int)std::min<size_t>(V1_MAX_SPAWN, pauli_params.size() - k0);
         for (int k = 0; k < g.nparams; ++k) {
-          const int p = sg.gather_params[k0 + k];
+          const int p = pauli_params[k0 + k];
           g.slot[k] = 1 + p;
           g.goff[k] = prog->gen_off[p];
           g.gcnt[k] = prog->gen_off[p + 1] - prog->gen_off[p];
-          nlive = std::max(nlive, p + 2);
         }
         const long long grid = S << (n - g.cb);
         if (grid > 0x7fffffffLL) PQC_FAIL(-1, "gather grid too large");

@@ -516,7 +516,8 @@ class fSim(PRot):
         return [_op(_lib.OP_FSIM, self.q1, self.q2, scale=self.phi, offset=self.theta)]
 
     def derivative(self):
-        raise NotImplementedError("fSim derivative matrices (quirk Q3) are not lowered yet")
+        raise NotImplementedError("fSim has no symbolic derivative operator; derivative STATES "
+                                  "(quirk-Q3 matrices) come from PQC.get_gradients / take_derivative")
 
     parameterised_derivative = lambda self, param: self.derivative()
 
@@ -545,7 +546,8 @@ class fixed_fSim(PRot):
         return [_op(_lib.OP_FIXED_FSIM, self.q1, self.q2, offset=self.theta)]
 
     def derivative(self):
-        raise NotImplementedError("fixed_fSim derivative matrix (quirk Q3) is not lowered yet")
+        raise NotImplementedError("fixed_fSim has no symbolic derivative operator; derivative "
+                                  "STATES come from PQC.get_gradients / take_derivative")
 
     def flip_pauli(self):
         pass

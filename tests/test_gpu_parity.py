@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 ALL = sorted(cases.CASES)
 ATOL = 1e-10
 RTOL = 1e-8
-GRAD_OK = [c for c in ALL if cases.CASES[c][2] > 0 and "fsim" not in c]
+GRAD_OK = [c for c in ALL if cases.CASES[c][2] > 0]
 
 
 def reseed():
@@ -74,11 +74,18 @@ def test_gradients_qfi_eqd_vs_golden(golden, name):
     assert list(eq.cpu().numpy()) == list(golden[f"{name}/eqd"])
 
 
-@pytest.mark.parametrize("name", [c for c in ALL if "fsim" in c])
-def test_fsim_family_fails_loudly_on_derivatives(name):
-    qc = cases.CASES[name][0](pyqc)
+def test_quirk_q2_is_fenced_not_imitated():
+    """fSim behind a non-parameterised gate: the reference would differentiate the wrong gate
+    (circuit.py:186-189); the replacement refuses instead of silently diverging."""
+    qc = pyqc.PQC(3)
+    qc.add_layer([pyqc.H(0, 3), pyqc.fSim([0, 1], 3), pyqc.R_x(2, 3)])
+    qc.update_state([0.3, 0.4, 0.5])
     with pytest.raises(NotImplementedError):
         qc.get_gradients()
+    bad = pyqc.PQC(3)
+    bad.add_layer([pyqc.shared_parameter([pyqc.R_x(0, 3), pyqc.R_z(0, 3)], 3, commute=False)])
+    with pytest.raises(NotImplementedError):
+        bad.get_gradients()
 
 
 def test_reference_known_answers(golden):
@@ -236,7 +243,10 @@ def test_multi_pass_states_vs_oracle(kind, n, p):
     assert np.abs(Q - [orc.single_Q(r, n) for r in ref]).max() < ATOL
 
 
-@pytest.mark.parametrize("kind,n,p", [("TFIM", 13, 2), ("XXZ", 14, 1), ("TFIM", 16, 1)])
+@pytest.mark.parametrize("kind,n,p", [("TFIM", 13, 2), ("XXZ", 14, 1), ("TFIM", 16, 1),
+                                      ("generic_HE", 9, 2), ("NPQC", 10, 4), ("zfsim", 9, 2),
+                                      ("fsim", 12, 1), ("fermionic", 8, 1), ("Circuit_9", 8, 2),
+                                      ("TFIM_modified", 12, 2), ("qg_circuit", 11, 1)])
 def test_multi_pass_qfim_vs_oracle(kind, n, p):
     qc = pyqc.templates.generate_circuit(kind, n, p, shuffle=False)
     specs, init = orc.generate_circuit(kind, n, p)
