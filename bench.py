@@ -262,6 +262,21 @@ def run_b200(a):
     launches = engine.launch_count() - l0
     clocks = sampler.stop() if sampler else None
 
+    # secondary: pure state generation (PQC.run over a batch) of the same circuit -- the
+    # "gate apply" figure of SURVEY 8d: L x 2 x 16 x 2^n bytes per state
+    S_apply = min(a.samples, 4096)
+    st_buf = torch.empty((S_apply, 1 << a.qubits), dtype=torch.complex128, device=dev)
+    init_t = qc.initial_state.tensor
+
+    def step_apply():
+        return qc.program.run(ang_dev[:S_apply], init=init_t, out=st_buf)
+    for _ in range(3):
+        step_apply()
+    engine.profile_begin()
+    ms_apply, _ = timed(step_apply, 3)
+    prof_apply = engine.profile_end()
+    del st_buf
+
     step_e2e()
     ms_e2e, eq_h = timed(step_e2e, a.steps)
     assert np.array_equal(eq_h.numpy(), eq.cpu().numpy())
@@ -298,8 +313,19 @@ def run_b200(a):
                      "kernel_share_of_step": prof["ms"] / ms,
                      "algorithmic_bytes_per_launch": alg_per_launch,
                      "traffic": ncu_traffic(kern, alg_per_launch)},
+        "roofline_apply_only": {
+            "what": f"PQC.run_batch, {S_apply} states per GPU, no measures",
+            "states_per_s": S_apply * world * 3 / (ms_apply / 1e3),
+            "by_template_layers_GBps": (a.layers + (1 if a.circuit == "TFIM" else 0)) * 2 * 16 *
+            (1 << a.qubits) * S_apply * 3 / (ms_apply / 1e3) / 1e9,
+            "pass_kernel_GBps": prof_apply["bytes"] / (prof_apply["ms"] / 1e3) / 1e9
+            if prof_apply["ms"] > 0 else 0.0,
+            "passes": qc.program.n_passes, "peak": peak, "unit": "GB/s"},
         "clocks": clocks,
     }
+    ra = line["roofline_apply_only"]
+    ra["frac_by_layers"] = ra["by_template_layers_GBps"] / peak
+    ra["frac_pass_kernel"] = ra["pass_kernel_GBps"] / peak
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if rank == 0:

@@ -297,10 +297,14 @@ extern "C" int pqc_qfim_batch(const pqc_program* prog, const double* d_angles, i
       c128* buf_b = buf_a + c * (int64_t)(P + 1) * D;
       c128* G = buf_b + c * (int64_t)(P + 1) * D;
       c128* fin = nullptr;
+      // Gram mode: run the pipeline without in-pass Gram partials, then ONE batched V^H V
+      // on the FP64 tensor cores at the common time all vectors have reached
+      const bool gram = pqc_v1_gram_ok(prog);
       int rc = pqc_v1_derivatives(prog, d_angles + c0 * ld, ld, c, (const c128*)d_init, buf_a,
-                                  buf_b, G, true, d_states_out != nullptr, &fin, st);
+                                  buf_b, G, !gram, d_states_out != nullptr, &fin, st);
       if (rc) return rc;
-      rc = pqc_v1_qfim_reduce(prog, G, c, d_qfim + c0 * (int64_t)P * P, st);
+      rc = gram ? pqc_v1_gram_qfim(prog, fin, c, G, d_qfim + c0 * (int64_t)P * P, st)
+                : pqc_v1_qfim_reduce(prog, G, c, d_qfim + c0 * (int64_t)P * P, st);
       if (rc) return rc;
       if (d_states_out) {
         PQC_CUDA(cudaMemcpy2DAsync((c128*)d_states_out + c0 * D, D * sizeof(c128), fin,

@@ -230,6 +230,9 @@ long long pqc_v1_gpart_elems(const pqc_program* prog, long long S);
 int pqc_v1_qfim_reduce(const pqc_program* prog, const c128* d_gpart, long long S, double* d_F,
                        cudaStream_t st);
 bool pqc_use_v0();
+bool pqc_v1_gram_ok(const pqc_program* prog);
+int pqc_v1_gram_qfim(const pqc_program* prog, const c128* buf, long long S, c128* d_gpart,
+                     double* d_F, cudaStream_t st);
 int pqc_prof_launch_begin(double bytes, cudaStream_t st);
 void pqc_prof_launch_end(int h, cudaStream_t st);
 int pqc_pauli_apply_slots(const c128* src, c128* dst, int n, long long S, int slots_total,

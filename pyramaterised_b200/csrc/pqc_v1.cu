@@ -193,11 +193,6 @@ struct Builder {
     open = true;
     nmops_cur = 0;
   }
-  int unassigned_low() const {
-    int c = 0;
-    for (int b = 0; b < 4 && b < n; ++b) c += grp_of[b] < 0;
-    return c;
-  }
   int room(int g, uint32_t need) const {   // free slots of group g for bits of `need`
     int r = 4 - (int)grp[g].size();
     if (g == 0) {                          // keep space for low bits that are still unplaced
@@ -1301,23 +1296,36 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs A) {
   __syncthreads();
   for (int p = 0; p < A.nparams; ++p) {
     c128* out = A.buf + ((s * A.slots_total + A.slot[p]) << A.n);
-    for (uint32_t i = threadIdx.x; i < csize; i += 256) {
-      const uint32_t y = c0 + i;
-      double re = 0.0, im = 0.0;
+    // 16 outputs per thread (element e = tid + 256 r); terms visited once each
+    for (uint32_t i0 = threadIdx.x; i0 < csize; i0 += 256 * 16) {
+      double are[16], aim[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) are[r] = aim[r] = 0.0;
       for (int t = 0; t < A.gcnt[p]; ++t) {
         const GenTerm g = A.gens[A.goff[p] + t];
-        const uint32_t x = y ^ g.xmask;
-        const c128 v = (g.xmask >> A.cb) ? psi[x] : sm[x - c0];
-        int ph = (__popc(g.xmask & g.zmask) + 2 * __popc(x & g.zmask)) & 3;
-        c128 w;
-        if (ph == 0) w = v;
-        else if (ph == 1) w = make_double2(-v.y, v.x);
-        else if (ph == 2) w = make_double2(-v.x, -v.y);
-        else w = make_double2(v.y, -v.x);
-        re += g.re * w.x - g.im * w.y;
-        im += g.re * w.y + g.im * w.x;
+        const bool far = (g.xmask >> A.cb) != 0;
+        const int ny = __popc(g.xmask & g.zmask);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const uint32_t i = i0 + 256u * r;
+          if (i >= csize) continue;
+          const uint32_t x = (c0 + i) ^ g.xmask;
+          const c128 v = far ? psi[x] : sm[x - c0];
+          const int ph = (ny + 2 * __popc(x & g.zmask)) & 3;
+          c128 w;
+          if (ph == 0) w = v;
+          else if (ph == 1) w = make_double2(-v.y, v.x);
+          else if (ph == 2) w = make_double2(-v.x, -v.y);
+          else w = make_double2(v.y, -v.x);
+          are[r] += g.re * w.x - g.im * w.y;
+          aim[r] += g.re * w.y + g.im * w.x;
+        }
       }
-      out[y] = make_double2(re, im);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const uint32_t i = i0 + 256u * r;
+        if (i < csize) out[c0 + i] = make_double2(are[r], aim[r]);
+      }
     }
   }
 }
@@ -1326,7 +1334,6 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs A) {
 // the partial array and zeroes the other tiles so the reducer stays uniform.
 __global__ void __launch_bounds__(256) k_multi_dots(const c128* __restrict__ buf, int n,
                                                     int slots_total, int rows, int npart,
-                                                    const int* __restrict__ partner_slot_dev,
                                                     V1Args A) {
   __shared__ double red[32];
   const long long D = 1ll << n;
@@ -1371,6 +1378,199 @@ __global__ void k_qfim_reduce(const c128* __restrict__ gpart, long long S, int P
   };
   const c128 sp = G(0, p), sq = G(0, q), d = G(1 + p, q);
   F[e] = 4.0 * (d.x - (sp.x * sq.x + sp.y * sq.y));
+}
+
+// =====================================================================================
+// Batched Gram matrix on the FP64 tensor cores: G_s = V_s^H V_s for the M = P + 1 live
+// vectors (psi, d_0 psi .. d_{P-1} psi) of every parameter set, all taken at ONE common
+// time (overlaps are invariant under the later unitary gates, measure.py:50-63 needs exactly
+// <psi|d_p> and <d_p|d_q>).  One CTA per (sample, K slice); 8 warps share the upper-triangular
+// 8x8 output tiles; K streamed 16 amplitudes at a time through cp.async double buffers.
+// =====================================================================================
+#define GR_K 64                   // amplitudes per stage: 1 KB contiguous per vector row
+#define GR_ROW (GR_K + 4)         // padded complex per smem row (bank-conflict-free fragments)
+#define GR_TPW 16                 // 8x8 output tiles per warp (one "tile group")
+#define GR_SLICE 1024             // amplitudes per CTA: DMMA chains stay <= 64 long
+#define GR_MAXSPLIT 64
+
+__device__ __forceinline__ void gr_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+static int gram_ksplit(int n) {
+  const long long D = 1ll << n;
+  return (int)std::max<long long>(1, std::min<long long>(GR_MAXSPLIT, D / GR_SLICE));
+}
+
+// Block = 4 K-shares x NG tile groups warps.  Warp (kw, grp) owns the upper-triangular tiles
+// [grp*GR_TPW, (grp+1)*GR_TPW) and the k4-steps kw, kw+4, .. of every 64-amplitude stage: it
+// loads each row-block fragment ONCE per step and feeds up to 16 tiles x 4 DMMAs from it.
+// Each CTA covers a short K slice (<= 1024 amplitudes), so every DMMA accumulation chain is
+// at most 64 long and the slices are added afterwards in a fixed order (blocked summation).
+__global__ void __launch_bounds__(384) k_gram_dmma(const c128* __restrict__ buf, int n,
+                                                   int slots_total, int M, int M8, int ksplit,
+                                                   c128* __restrict__ gpart) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int NT = blockDim.x;
+  c128* sm = reinterpret_cast<c128*>(smraw);                       // [2][M8][GR_ROW]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const int kw = warp & 3, grp = warp >> 2;
+  const long long s = blockIdx.x / ksplit;
+  const int ks = blockIdx.x % ksplit;
+  const long long D = 1ll << n, kbeg = (D / ksplit) * ks, nk = (D / ksplit) / GR_K;
+  const c128* V = buf + ((s * slots_total) << n);
+  const int T = M8 / 8, ntile = T * (T + 1) / 2;
+  const int t_begin = grp * GR_TPW, t_end = min(ntile, t_begin + GR_TPW);
+  // tile index -> (row block, col block), 4 bits each, upper triangle row-major
+  unsigned long long tij_lo = 0, tij_hi = 0;   // 16 tiles x 8 bits
+  {
+    int idx = 0;
+    for (int i = 0; i < T; ++i)
+      for (int j = i; j < T; ++j, ++idx)
+        if (idx >= t_begin && idx < t_end) {
+          const int q = idx - t_begin;
+          const unsigned long long v = (unsigned long long)(i | (j << 4)) << (8 * (q & 7));
+          if (q < 8) tij_lo |= v; else tij_hi |= v;
+        }
+  }
+  for (int e = tid; e < 2 * M8 * GR_ROW; e += NT) sm[e] = make_double2(0.0, 0.0);   // pad rows
+  __syncthreads();
+  auto stage_load = [&](int b, long long k0) {
+    for (int e = tid; e < M * GR_K; e += NT) {
+      const int r = e / GR_K, kk = e % GR_K;
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(sm + (b * M8 + r) * GR_ROW + kk);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa),
+                   "l"(V + ((long long)r << n) + k0 + kk));
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+  double re[GR_TPW][2], im[GR_TPW][2];
+#pragma unroll
+  for (int q = 0; q < GR_TPW; ++q) re[q][0] = re[q][1] = im[q][0] = im[q][1] = 0.0;
+  stage_load(0, kbeg);
+  for (long long it = 0; it < nk; ++it) {
+    const int b = (int)(it & 1);
+    if (it + 1 < nk) {
+      stage_load(b ^ 1, kbeg + (it + 1) * GR_K);
+      asm volatile("cp.async.wait_group 1;");
+    } else {
+      asm volatile("cp.async.wait_group 0;");
+    }
+    __syncthreads();
+    for (int kk = kw; kk < GR_K / 4; kk += 4) {
+      const c128* a_s = sm + (b * M8 + g) * GR_ROW + kk * 4 + t4;
+#pragma unroll
+      for (int q = 0; q < GR_TPW; ++q) {
+        if (t_begin + q < t_end) {          // warp-uniform
+          const unsigned ij = (unsigned)(((q < 8 ? tij_lo : tij_hi) >> (8 * (q & 7))) & 0xff);
+          // fragments straight from shared memory: 2 LDS.128 per 4 DMMAs
+          const c128 fa = a_s[(ij & 15u) * (8 * GR_ROW)];
+          const c128 fb = a_s[(ij >> 4) * (8 * GR_ROW)];
+          gr_dmma(re[q][0], re[q][1], fa.x, fb.x);
+          gr_dmma(re[q][0], re[q][1], fa.y, fb.y);
+          gr_dmma(im[q][0], im[q][1], fa.x, fb.y);
+          gr_dmma(im[q][0], im[q][1], -fa.y, fb.x);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // add the 4 K-shares of every tile group in a fixed order through the (now idle) stage
+  // buffers: scratch [grp][q][4][32] doubles
+  double* scr = reinterpret_cast<double*>(sm);
+  for (int r = 1; r < 4; ++r) {
+    if (kw == r) {
+      double* o = scr + (size_t)grp * GR_TPW * 4 * 32 + lane;
+#pragma unroll
+      for (int q = 0; q < GR_TPW; ++q) {
+        o[(q * 4 + 0) * 32] = re[q][0]; o[(q * 4 + 1) * 32] = re[q][1];
+        o[(q * 4 + 2) * 32] = im[q][0]; o[(q * 4 + 3) * 32] = im[q][1];
+      }
+    }
+    __syncthreads();
+    if (kw == 0) {
+      const double* o = scr + (size_t)grp * GR_TPW * 4 * 32 + lane;
+#pragma unroll
+      for (int q = 0; q < GR_TPW; ++q) {
+        re[q][0] += o[(q * 4 + 0) * 32]; re[q][1] += o[(q * 4 + 1) * 32];
+        im[q][0] += o[(q * 4 + 2) * 32]; im[q][1] += o[(q * 4 + 3) * 32];
+      }
+    }
+    __syncthreads();
+  }
+  c128* out = gpart + (s * ksplit + ks) * (long long)M * M;
+  if (kw == 0) {
+#pragma unroll
+    for (int q = 0; q < GR_TPW; ++q)
+      if (t_begin + q < t_end) {
+        const unsigned ij = (unsigned)(((q < 8 ? tij_lo : tij_hi) >> (8 * (q & 7))) & 0xff);
+        const int ti = ij & 15, tj = ij >> 4;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int row = 8 * ti + g, col = 8 * tj + 2 * t4 + c;
+          if (row < M && col < M) out[(long long)row * M + col] = make_double2(re[q][c], im[q][c]);
+        }
+      }
+  }
+}
+
+// F_pq = 4 Re(G[1+p][1+q] - conj(G[0][1+p]) G[0][1+q]), p <= q, mirrored; K slices summed in
+// a fixed order.
+__global__ void k_qfim_from_gram(const c128* __restrict__ gpart, long long S, int P, int ksplit,
+                                 double* __restrict__ F) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S * P * P) return;
+  const int M = P + 1;
+  const long long s = e / ((long long)P * P);
+  const int r = (int)((e / P) % P), c = (int)(e % P);
+  const int p = r < c ? r : c, q = r < c ? c : r;
+  auto G = [&](int row, int col) -> c128 {
+    double re = 0.0, im = 0.0;
+    for (int ks = 0; ks < ksplit; ++ks) {
+      const c128 v = gpart[((s * ksplit + ks) * M + row) * M + col];
+      re += v.x;
+      im += v.y;
+    }
+    return make_double2(re, im);
+  };
+  const c128 sp = G(0, 1 + p), sq = G(0, 1 + q), d = G(1 + p, 1 + q);
+  F[e] = 4.0 * (d.x - (sp.x * sq.x + sp.y * sq.y));
+}
+
+bool pqc_v1_gram_ok(const pqc_program* prog) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("PQC_QFIM_GRAM");
+    off = (e && strcmp(e, "0") == 0) ? 1 : 0;
+  }
+  const int M8 = (prog->P + 1 + 7) & ~7;
+  const int T = M8 / 8;
+  // T <= 9 row blocks (P <= 71): 45 tiles = 3 tile groups x 4 K-shares = 12 warps
+  return !off && prog->n >= 7 && T <= 9;
+}
+
+int pqc_v1_gram_qfim(const pqc_program* prog, const c128* buf, long long S, c128* d_gpart,
+                     double* d_F, cudaStream_t st) {
+  const int P = prog->P, M = P + 1, M8 = (M + 7) & ~7;
+  const int T = M8 / 8, ntile = T * (T + 1) / 2, ngrp = (ntile + GR_TPW - 1) / GR_TPW;
+  const int nthreads = 128 * ngrp;
+  const int ksplit = gram_ksplit(prog->n);
+  const size_t smem = std::max((size_t)2 * M8 * GR_ROW * sizeof(c128),
+                               (size_t)ngrp * GR_TPW * 4 * 32 * sizeof(double));
+  static bool attr_set = false;
+  if (!attr_set) {
+    PQC_CUDA(cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  if (S * ksplit > 0x7fffffffLL) PQC_FAIL(-1, "gram grid too large");
+  k_gram_dmma<<<(unsigned)(S * ksplit), nthreads, smem, st>>>(buf, prog->n, P + 1, M, M8, ksplit,
+                                                              d_gpart);
+  PQC_LAUNCH_CHECK();
+  const long long tot = S * P * P;
+  k_qfim_from_gram<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_gpart, S, P, ksplit, d_F);
+  PQC_LAUNCH_CHECK();
+  return 0;
 }
 
 // =====================================================================================
@@ -1464,7 +1664,9 @@ int pqc_v1_run(const pqc_program* prog, const double* d_angles, long long ld, lo
 
 long long pqc_v1_gpart_elems(const pqc_program* prog, long long S) {
   const long long ntiles = 1ll << std::max(0, prog->n - V1_LOCAL_BITS);
-  return S * (prog->P + 1) * std::max(1, prog->P) * ntiles;
+  const long long dots = (long long)(prog->P + 1) * std::max(1, prog->P) * ntiles;
+  const long long gram = (long long)gram_ksplit(prog->n) * (prog->P + 1) * (prog->P + 1);
+  return S * std::max(dots, gram);
 }
 
 int pqc_v1_qfim_reduce(const pqc_program* prog, const c128* d_gpart, long long S, double* d_F,
@@ -1609,8 +1811,7 @@ int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long lon
         a.ntiles = ntiles;
         const long long grid = S * nlive * a.npartners;
         if (grid > 0x7fffffffLL) PQC_FAIL(-1, "dot grid too large");
-        k_multi_dots<<<(unsigned)grid, 256, 0, st>>>(pp[cur], n, slots_total, nlive, a.npartners,
-                                                    nullptr, a);
+        k_multi_dots<<<(unsigned)grid, 256, 0, st>>>(pp[cur], n, slots_total, nlive, a.npartners, a);
         PQC_LAUNCH_CHECK();
       }
       late_dots.clear();
@@ -1627,8 +1828,7 @@ int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long lon
       a.ntiles = ntiles;
       const long long grid = S * nlive * a.npartners;
       if (grid > 0x7fffffffLL) PQC_FAIL(-1, "dot grid too large");
-      k_multi_dots<<<(unsigned)grid, 256, 0, st>>>(pp[cur], n, slots_total, nlive, a.npartners,
-                                                  nullptr, a);
+      k_multi_dots<<<(unsigned)grid, 256, 0, st>>>(pp[cur], n, slots_total, nlive, a.npartners, a);
       PQC_LAUNCH_CHECK();
     }
   }
