@@ -257,6 +257,23 @@ struct Builder {
     m.k0 = m.k1 = m.l0 = m.l1 = -1;
     m.trig = -1;
     const int te = trig_entries(c);
+    if (te && c.kind != PQC_K_ZZSUM) {
+      // ops driven by the same angle (shared_parameter layers) share one trig slot
+      const int want_pad = (c.kind == PQC_OP_RX || c.kind == PQC_OP_RY) ? 1 : 0;
+      for (const TrigJob& e : tj) {
+        const bool same_class = (e.kind == c.kind) ||
+                                (e.pad == 1 && want_pad == 1) ||
+                                (e.pad == 0 && want_pad == 0 && e.kind != PQC_K_ZZSUM &&
+                                 e.kind != PQC_OP_FSIM && e.kind != PQC_OP_FIXED_FSIM &&
+                                 e.kind != PQC_K_RXY && c.kind != PQC_OP_FSIM &&
+                                 c.kind != PQC_OP_FIXED_FSIM && c.kind != PQC_K_RXY);
+        if (same_class && e.param == c.param && e.param2 == c.param2 && e.scale == c.scale &&
+            e.offset == c.offset && e.npairs == 0) {
+          m.trig = e.slot;
+          return m;
+        }
+      }
+    }
     if (te) {
       m.trig = ntrig;
       TrigJob j;
@@ -852,6 +869,60 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
   const int ips = A.active + A.nspawn;              // items per sample
   const uint32_t amask = (1u << A.tb) - 1u;
 
+  const long long sample0 = item0 / ips;
+  const int r0 = (int)(item0 - sample0 * ips);
+  // item li of this CTA (li < 16): 32-bit arithmetic only
+  auto item_info = [&](int li, long long& sample, int& src_slot, int& dst_slot, int& gen) {
+    const int rr = r0 + li, ds = rr / ips, r = rr - ds * ips;
+    sample = sample0 + ds;
+    if (!GEN || r < A.active) {
+      src_slot = dst_slot = r;
+      gen = -1;
+    } else {
+      src_slot = 0;
+      dst_slot = A.spawn_slot[r - A.active];
+      gen = r - A.active;
+    }
+  };
+  auto local_to_amp = [&](uint32_t i) -> uint32_t {
+    uint32_t r = i & ((1u << A.low_run) - 1u);
+    for (int j = A.low_run; j < A.tb; ++j) r |= ((i >> j) & 1u) << A.lbit[j];
+    return r;
+  };
+  // staged (global <-> swizzled shared) element r of this thread: local index tid | r << 8
+  const uint32_t st_amp_tid = tbase | local_to_amp((uint32_t)tid & amask);
+  uint32_t st_h[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) st_h[k] = (8 + k < A.tb) ? (1u << A.lbit[8 + k]) : 0u;
+  const uint32_t st_s_tid = swz((uint32_t)tid);
+  const uint32_t st_s[4] = {swz(1u << 8), swz(1u << 9), swz(1u << 10), swz(1u << 11)};
+  const int st_item_shift = A.tb - 8;          // li = r >> (tb - 8)   (tb >= 8)
+
+  const bool direct_load = (A.sweep0_io & 1) != 0;
+  long long my_sample = 0;
+  int my_src = 0, my_dst = 0, my_gen = -1;
+  if (ipc == 1) item_info(0, my_sample, my_src, my_dst, my_gen);
+
+  // ---- early tile load: when sweep 0 reads global memory directly (and has no index
+  // permutation in front), issue its 16 loads NOW so their latency overlaps the prologue
+  c128 a[16];
+  bool preloaded = false;
+  if (!DOTS && direct_load && ipc == 1) {     // (the in-pass Gram path loads + dots together)
+    const SweepD sw = A.sweeps[0];
+    if ((sw.pad & 0xffff) == 0) {
+      uint32_t amp0 = tbase;
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        amp0 |= sw.tg[t] < 32 ? ((((uint32_t)tid >> t) & 1u) << sw.tg[t]) : 0u;
+      const uint32_t g0 = 1u << A.lbit[sw.rb[0]], g1 = 1u << A.lbit[sw.rb[1]],
+                     g2 = 1u << A.lbit[sw.rb[2]], g3 = 1u << A.lbit[sw.rb[3]];
+      const c128* sp = A.src + ((my_sample * A.slots_total + my_src) << A.n);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a[j] = sp[amp0 ^ XSEL4R(j, g0, g1, g2, g3)];
+      preloaded = true;
+    }
+  }
+
   // ---- stage the micro-program and fill the per-item trig table ------------------------------
   {
     const int nm = A.sweeps_nmops;
@@ -895,40 +966,6 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
       }
     }
   }
-
-  const long long sample0 = item0 / ips;
-  const int r0 = (int)(item0 - sample0 * ips);
-  // item li of this CTA (li < 16): 32-bit arithmetic only
-  auto item_info = [&](int li, long long& sample, int& src_slot, int& dst_slot, int& gen) {
-    const int rr = r0 + li, ds = rr / ips, r = rr - ds * ips;
-    sample = sample0 + ds;
-    if (!GEN || r < A.active) {
-      src_slot = dst_slot = r;
-      gen = -1;
-    } else {
-      src_slot = 0;
-      dst_slot = A.spawn_slot[r - A.active];
-      gen = r - A.active;
-    }
-  };
-  auto local_to_amp = [&](uint32_t i) -> uint32_t {
-    uint32_t r = i & ((1u << A.low_run) - 1u);
-    for (int j = A.low_run; j < A.tb; ++j) r |= ((i >> j) & 1u) << A.lbit[j];
-    return r;
-  };
-  // staged (global <-> swizzled shared) element r of this thread: local index tid | r << 8
-  const uint32_t st_amp_tid = tbase | local_to_amp((uint32_t)tid & amask);
-  uint32_t st_h[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) st_h[k] = (8 + k < A.tb) ? (1u << A.lbit[8 + k]) : 0u;
-  const uint32_t st_s_tid = swz((uint32_t)tid);
-  const uint32_t st_s[4] = {swz(1u << 8), swz(1u << 9), swz(1u << 10), swz(1u << 11)};
-  const int st_item_shift = A.tb - 8;          // li = r >> (tb - 8)   (tb >= 8)
-
-  const bool direct_load = (A.sweep0_io & 1) != 0;
-  long long my_sample = 0;
-  int my_src = 0, my_dst = 0, my_gen = -1;
-  if (ipc == 1) item_info(0, my_sample, my_src, my_dst, my_gen);
 
   // ---- staged load (global -> swizzled shared) when the first sweep cannot load directly -------
   if (!direct_load) {
@@ -1021,11 +1058,12 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
 #define XSEL4(j, a0, a1, a2, a3) \
   ((((j)&1) ? (a0) : 0u) ^ (((j)&2) ? (a1) : 0u) ^ (((j)&4) ? (a2) : 0u) ^ (((j)&8) ? (a3) : 0u))
 
-    c128 a[16];
     const bool dl = si == 0 && direct_load;
     uint32_t lc[4] = {1u, 2u, 4u, 8u}, lv = 0u;
     if (npre) affine(sw.mop_begin, sw.mop_begin + npre, true, lc, lv);
-    if (dl) {
+    if (dl && preloaded) {
+      // loaded before the prologue
+    } else if (dl) {
       uint32_t lgb = amp0, lg0 = g0, lg1 = g1, lg2 = g2, lg3 = g3;
       if (npre) {
         lgb = amp0 ^ LIN4(lv, g0, g1, g2, g3);
