@@ -32,8 +32,10 @@ extern "C" int pqc_device_check(int* cc_major, int* cc_minor, int* n_sms) {
 // ---------------------------------------------------------------------------------
 // programs
 // ---------------------------------------------------------------------------------
-extern "C" int pqc_program_create(int n_qubits, int n_params, int n_ops, const pqc_op* h_ops,
-                                  pqc_program** out) {
+static int plan_bidir(pqc_program* p);
+
+static int program_create(int n_qubits, int n_params, int n_ops, const pqc_op* h_ops,
+                          bool with_bidir, pqc_program** out) {
   if (!out) PQC_FAIL(-1, "null output handle");
   *out = nullptr;
   if (n_qubits < 1 || n_qubits > PQC_MAX_QUBITS) PQC_FAIL(-1, "n_qubits must be in [1, 30]");
@@ -63,6 +65,7 @@ extern "C" int pqc_program_create(int n_qubits, int n_params, int n_ops, const p
   }
   int rc = pqc_plan_program(p);
   if (rc == 0) rc = pqc_plan_v1(p);
+  if (rc == 0 && with_bidir) rc = plan_bidir(p);
   if (rc) {
     pqc_program_destroy(p);
     return rc;
@@ -71,8 +74,145 @@ extern "C" int pqc_program_create(int n_qubits, int n_params, int n_ops, const p
   return 0;
 }
 
+extern "C" int pqc_program_create(int n_qubits, int n_params, int n_ops, const pqc_op* h_ops,
+                                  pqc_program** out) {
+  return program_create(n_qubits, n_params, n_ops, h_ops, true, out);
+}
+
+// ---------------------------------------------------------------------------------
+// Meet-in-the-middle QFIM plan.  Gram entries <d_j|d_p> are invariant under a unitary applied
+// to both vectors, so they can be taken at ANY common time.  Cutting the circuit at op `c`:
+//   F: ops[0,c) forward from |init>, spawning the derivative vectors of its parameters;
+//   M: ops[c,T) forward on psi alone -> psi(T);
+//   B: ops[c,T) inverted and reversed, from psi(T) back to time c, spawning -d_p on the way
+//      (the inverse of exp(-i a G/2) is the same gate at -a, so its generator flips sign).
+// A vector then lives for |t_p - c| passes instead of T - t_p: about half the vector-passes of
+// the forward-only pipeline.  Only for circuits whose every op is inverted by negating its
+// angle, and whose parameters / reference gates do not straddle the cut.
+// ---------------------------------------------------------------------------------
+static bool bidir_enabled() {
+  const char* e = getenv("PQC_BIDIR");
+  return !(e && strcmp(e, "0") == 0);
+}
+
+static bool op_negatable(int kind) {
+  switch (kind) {
+    case PQC_OP_RX: case PQC_OP_RY: case PQC_OP_RZ: case PQC_OP_RXX: case PQC_OP_RYY:
+    case PQC_OP_RZZ: case PQC_OP_H: case PQC_OP_X: case PQC_OP_CNOT: case PQC_OP_CZ:
+    case PQC_OP_IDENT:
+      return true;
+    default:
+      return false;
+  }
+}
+
+static void bidir_free(pqc_program* p) {
+  if (p->bi_F) pqc_program_destroy(p->bi_F);
+  if (p->bi_M) pqc_program_destroy(p->bi_M);
+  if (p->bi_B) pqc_program_destroy(p->bi_B);
+  p->bi_F = p->bi_M = p->bi_B = nullptr;
+  p->bi_cut = -1;
+}
+
+// build the three sub-programs for a cut; returns false if one of them is unusable
+static bool bidir_build(pqc_program* p, int cut, const std::vector<int>& first,
+                        const std::vector<int>& last) {
+  const int nops = (int)p->ops.size(), P = p->P;
+  std::vector<int> loc(P, -1);
+  std::vector<int> cols;
+  std::vector<pqc_op> f_ops(p->ops.begin(), p->ops.begin() + cut), b_ops;
+  int PF = 0, PB = 0;
+  // parameters that never appear in an op go to the forward side (their vectors are zero)
+  for (int q = 0; q < P; ++q)
+    if (first[q] < 0) { loc[q] = -2; }
+  for (auto& op : f_ops)
+    if (op.param >= 0) {
+      if (loc[op.param] < 0) { loc[op.param] = PF++; cols.push_back(op.param); }
+      op.param = loc[op.param];
+    }
+  for (int q = 0; q < P; ++q)
+    if (loc[q] == -2) { loc[q] = PF++; cols.push_back(q); }
+  for (int i = nops - 1; i >= cut; --i) {
+    pqc_op op = p->ops[i];
+    op.scale = -op.scale;
+    op.offset = -op.offset;
+    if (op.param >= 0) {
+      if (loc[op.param] < 0) { loc[op.param] = PB++; cols.push_back(op.param); }
+      op.param = loc[op.param];
+    }
+    b_ops.push_back(op);
+  }
+  if (PF + PB != P || PB == 0 || PF == 0) return false;
+  bidir_free(p);
+  if (program_create(p->n, PF, (int)f_ops.size(), f_ops.data(), false, &p->bi_F)) return false;
+  if (program_create(p->n, P, nops - cut, p->ops.data() + cut, false, &p->bi_M)) return false;
+  if (program_create(p->n, PB, (int)b_ops.size(), b_ops.data(), false, &p->bi_B)) return false;
+  for (pqc_program* q : {p->bi_F, p->bi_B})
+    if (!q->v1_grad_ok || !q->grad_supported || q->v1_grad.empty() || q->v1_grad[0].type != 0)
+      return false;
+  if (!p->bi_M->v1_ok) return false;
+  p->bi_cut = cut;
+  p->bi_PF = PF;
+  p->bi_PB = PB;
+  p->bi_cols = cols;
+  p->bi_inv.assign(P, 0);
+  for (int v = 0; v < P; ++v) p->bi_inv[cols[v]] = v | (v >= PF ? (int)0x80000000 : 0);
+  p->bi_cost = pqc_v1_plan_cost(p->bi_F) + pqc_v1_plan_cost(p->bi_B) +
+               (long long)p->bi_M->v1_run.size() + 2;
+  (void)last;
+  return true;
+}
+
+static int plan_bidir(pqc_program* p) {
+  const int nops = (int)p->ops.size(), P = p->P;
+  if (!bidir_enabled() || !p->v1_grad_ok || !p->grad_supported || P < 4 || p->n < 10) return 0;
+  for (const pqc_op& op : p->ops)
+    if (!op_negatable(op.kind)) return 0;
+  p->fwd_cost = pqc_v1_plan_cost(p);
+  std::vector<int> first(P, -1), last(P, -1);
+  for (int i = 0; i < nops; ++i) {
+    const int q = p->ops[i].param;
+    if (q < 0) continue;
+    if (first[q] < 0) first[q] = i;
+    last[q] = i;
+  }
+  // valid cuts: between two reference gates, no parameter on both sides
+  std::vector<std::pair<long long, int>> cand;
+  for (int c = 1; c < nops; ++c) {
+    if (p->ops[c].group == p->ops[c - 1].group) continue;
+    bool ok = true;
+    long long cost = nops - c;
+    for (int q = 0; q < P && ok; ++q) {
+      if (first[q] < 0) continue;
+      if (first[q] < c && last[q] >= c) ok = false;
+      else if (last[q] < c) cost += c - first[q];
+      else cost += last[q] + 1 - c;
+    }
+    if (ok) cand.push_back({cost, c});
+  }
+  for (int q = 0; q < P; ++q)
+    if (first[q] < 0) return 0;   // a parameter no op uses: keep the plain pipeline
+  std::sort(cand.begin(), cand.end());
+  // plan the few best cuts of the op-count proxy and keep the cheapest real plan
+  int best_cut = -1;
+  long long best = p->fwd_cost;
+  for (size_t k = 0; k < cand.size() && k < 6; ++k) {
+    if (!bidir_build(p, cand[k].second, first, last)) continue;
+    if (p->bi_cost < best) { best = p->bi_cost; best_cut = cand[k].second; }
+  }
+  if (best_cut < 0 || best * 10 > p->fwd_cost * 9) {   // < 10 % gain: not worth the extra launches
+    bidir_free(p);
+    return 0;
+  }
+  if (p->bi_cut != best_cut && !bidir_build(p, best_cut, first, last)) bidir_free(p);
+  return 0;
+}
+
 extern "C" int pqc_program_destroy(pqc_program* prog) {
   if (!prog) return 0;
+  bidir_free(prog);
+  if (prog->d_bi_cols) cudaFree(prog->d_bi_cols);
+  if (prog->d_bi_inv) cudaFree(prog->d_bi_inv);
   if (prog->d_ops) cudaFree(prog->d_ops);
   if (prog->d_gens) cudaFree(prog->d_gens);
   if (prog->d_mops) cudaFree(prog->d_mops);
@@ -157,7 +297,7 @@ extern "C" int pqc_gradients_batch(const pqc_program* prog, const double* d_angl
     PQC_CUDA(cudaMallocAsync(&scratch, bytes, st));
     const bool even = (pqc_v1_n_passes(prog, true) % 2) == 0;
     c128* fin = nullptr;
-    int rc = pqc_v1_derivatives(prog, d_angles, ld, S, (const c128*)d_init,
+    int rc = pqc_v1_derivatives(prog, d_angles, ld, S, (const c128*)d_init, 0,
                                 even ? (c128*)d_out : scratch, even ? scratch : (c128*)d_out,
                                 nullptr, false, true, &fin, st);
     if (rc == 0 && fin != (c128*)d_out)
@@ -244,8 +384,17 @@ static int forward_derivatives(const pqc_program* prog, const double* d_angles, 
 // Overlaps are taken at spawn time: every later gate is a unitary applied to both
 // vectors, so <d_p|d_q> and <psi|d_p> do not change afterwards.
 // ---------------------------------------------------------------------------------
+static bool use_bidir(const pqc_program* prog) {
+  return prog->bi_cut >= 0 && prog->v1_grad_ok && !pqc_use_v0() && pqc_v1_gram_ok(prog) &&
+         bidir_enabled();
+}
+
 static int64_t qfim_bytes_per_sample(const pqc_program* prog) {
   const int64_t D = 1ll << prog->n;
+  if (use_bidir(prog))   // ping-pong pairs of both pipelines, psi(T), permuted angles, Gram
+    return (2 * (int64_t)(prog->P + 2) + 1) * D * (int64_t)sizeof(c128) +
+           pqc_v1_gpart_elems(prog, 1) * (int64_t)sizeof(c128) +
+           (int64_t)((prog->P * sizeof(double) + 255) & ~(size_t)255);
   if (prog->v1_grad_ok && !pqc_use_v0())   // two ping-pong copies + per-tile Gram partials
     return 2 * (int64_t)(prog->P + 1) * D * (int64_t)sizeof(c128) +
            pqc_v1_gpart_elems(prog, 1) * (int64_t)sizeof(c128);
@@ -263,6 +412,61 @@ static int64_t qfim_chunk_target() {
     if (v < 1) v = 256;
   }
   return v;
+}
+
+// out[s][v] = angles[s][cols[v]]: the sub-programs number their parameters in spawn order
+__global__ void k_permute_cols(const double* __restrict__ angles, long long ld, long long S, int P,
+                               const int* __restrict__ cols, double* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S * P) return;
+  out[e] = angles[(e / P) * ld + cols[e % P]];
+}
+
+static int qfim_bidir(const pqc_program* prog, const double* d_angles, int64_t ld, int64_t S,
+                      const c128* d_init, c128* work, int64_t C, double* d_qfim,
+                      c128* d_states_out, cudaStream_t st) {
+  const int P = prog->P, n = prog->n, PF = prog->bi_PF, PB = prog->bi_PB;
+  const int64_t D = 1ll << n;
+  if (!prog->d_bi_cols) {
+    pqc_program* mp = const_cast<pqc_program*>(prog);
+    PQC_CUDA(cudaMalloc(&mp->d_bi_cols, sizeof(int) * P));
+    PQC_CUDA(cudaMalloc(&mp->d_bi_inv, sizeof(int) * P));
+    PQC_CUDA(cudaMemcpy(mp->d_bi_cols, prog->bi_cols.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+    PQC_CUDA(cudaMemcpy(mp->d_bi_inv, prog->bi_inv.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+  }
+  for (int64_t c0 = 0; c0 < S; c0 += C) {
+    const int64_t c = std::min<int64_t>(C, S - c0);
+    c128* fa = work;
+    c128* fb = fa + c * (int64_t)(PF + 1) * D;
+    c128* ba = fb + c * (int64_t)(PF + 1) * D;
+    c128* bb = ba + c * (int64_t)(PB + 1) * D;
+    c128* psiT = bb + c * (int64_t)(PB + 1) * D;
+    c128* G = psiT + c * D;
+    double* ang = (double*)(G + pqc_v1_gpart_elems(prog, c));
+    const double* a0 = d_angles + c0 * ld;
+    {
+      const long long tot = c * P;
+      k_permute_cols<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a0, ld, c, P, prog->d_bi_cols, ang);
+      PQC_LAUNCH_CHECK();
+    }
+    c128 *ffin = nullptr, *bfin = nullptr;
+    // need_final: psi must reach the cut even if the last spawn is earlier
+    int rc = pqc_v1_derivatives(prog->bi_F, ang, P, c, d_init, 0, fa, fb, nullptr, false, true,
+                                &ffin, st);
+    if (rc) return rc;
+    rc = pqc_v1_run(prog->bi_M, a0, ld, c, ffin, (int64_t)(PF + 1) * D, psiT, st);
+    if (rc) return rc;
+    rc = pqc_v1_derivatives(prog->bi_B, ang + PF, P, c, psiT, D, ba, bb, nullptr, false, true,
+                            &bfin, st);
+    if (rc) return rc;
+    rc = pqc_v1_gram_qfim2(prog, ffin, PF + 1, PF + 1, bfin, PB + 1, prog->d_bi_inv, c, G,
+                           d_qfim + c0 * (int64_t)P * P, st);
+    if (rc) return rc;
+    if (d_states_out)
+      PQC_CUDA(cudaMemcpyAsync(d_states_out + c0 * D, psiT, sizeof(c128) * c * D,
+                               cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
 }
 
 extern "C" int pqc_qfim_workspace_bytes(const pqc_program* prog, int64_t S, int64_t* bytes) {
@@ -289,6 +493,11 @@ extern "C" int pqc_qfim_batch(const pqc_program* prog, const double* d_angles, i
   int64_t C = usable / per;
   if (C < 1) PQC_FAIL(-1, "QFIM workspace too small for one sample");
   C = std::min<int64_t>(C, S);
+  if (use_bidir(prog)) {
+    C = std::min<int64_t>(C, qfim_chunk_target());
+    return qfim_bidir(prog, d_angles, ld, S, (const c128*)d_init, (c128*)w0, C, d_qfim,
+                      (c128*)d_states_out, st);
+  }
   if (prog->v1_grad_ok && !pqc_use_v0()) {
     C = std::min<int64_t>(C, qfim_chunk_target());
     for (int64_t c0 = 0; c0 < S; c0 += C) {
@@ -300,7 +509,7 @@ extern "C" int pqc_qfim_batch(const pqc_program* prog, const double* d_angles, i
       // Gram mode: run the pipeline without in-pass Gram partials, then ONE batched V^H V
       // on the FP64 tensor cores at the common time all vectors have reached
       const bool gram = pqc_v1_gram_ok(prog);
-      int rc = pqc_v1_derivatives(prog, d_angles + c0 * ld, ld, c, (const c128*)d_init, buf_a,
+      int rc = pqc_v1_derivatives(prog, d_angles + c0 * ld, ld, c, (const c128*)d_init, 0, buf_a,
                                   buf_b, G, !gram, d_states_out != nullptr, &fin, st);
       if (rc) return rc;
       rc = gram ? pqc_v1_gram_qfim(prog, fin, c, G, d_qfim + c0 * (int64_t)P * P, st)

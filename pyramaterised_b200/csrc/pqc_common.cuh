@@ -183,6 +183,19 @@ struct pqc_program {
   std::string grad_reason;
   DOp* d_ops = nullptr;                        // all passes' ops
   GenTerm* d_gens = nullptr;
+  // ---- meet-in-the-middle QFIM plan (pqc_api.cu): the op list is cut at `bi_cut`; the
+  // parameters before the cut are differentiated by the forward sub-program bi_F, those after
+  // it by bi_B = the inverted tail run backwards from psi(T) (made by bi_M); every vector ends
+  // at the cut, where the Gram matrix is taken.
+  pqc_program* bi_F = nullptr;
+  pqc_program* bi_M = nullptr;
+  pqc_program* bi_B = nullptr;
+  int bi_cut = -1, bi_PF = 0, bi_PB = 0;
+  std::vector<int> bi_cols;                    // Gram column v (F params then B params) -> parameter
+  std::vector<int> bi_inv;                     // parameter -> v | (sign bit: backward vector)
+  long long bi_cost = 0, fwd_cost = 0;         // vector-passes of either plan
+  int* d_bi_cols = nullptr;
+  int* d_bi_inv = nullptr;
 };
 
 // ------------------------------------------------------------------ small device helpers
@@ -223,8 +236,10 @@ int pqc_program_upload(const pqc_program* prog);   // idempotent; needs a CUDA d
 int pqc_v1_run(const pqc_program* prog, const double* d_angles, long long ld, long long S,
                const c128* d_init, long long init_stride, c128* d_out, cudaStream_t st);
 int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long long ld, long long S,
-                       const c128* d_init, c128* buf_a, c128* buf_b, c128* d_gpart,
-                       bool want_dots, bool need_final, c128** final_buf, cudaStream_t st);
+                       const c128* d_init, long long init_stride, c128* buf_a, c128* buf_b,
+                       c128* d_gpart, bool want_dots, bool need_final, c128** final_buf,
+                       cudaStream_t st);
+long long pqc_v1_plan_cost(const pqc_program* prog);   // vector-passes of the QFIM plan
 int pqc_v1_n_passes(const pqc_program* prog, bool need_final);
 long long pqc_v1_gpart_elems(const pqc_program* prog, long long S);
 int pqc_v1_qfim_reduce(const pqc_program* prog, const c128* d_gpart, long long S, double* d_F,
@@ -233,6 +248,9 @@ bool pqc_use_v0();
 bool pqc_v1_gram_ok(const pqc_program* prog);
 int pqc_v1_gram_qfim(const pqc_program* prog, const c128* buf, long long S, c128* d_gpart,
                      double* d_F, cudaStream_t st);
+int pqc_v1_gram_qfim2(const pqc_program* prog, const c128* buf, int slots1, int M1,
+                      const c128* buf2, int slots2, const int* d_inv, long long S, c128* d_gpart,
+                      double* d_F, cudaStream_t st);
 int pqc_prof_launch_begin(double bytes, cudaStream_t st);
 void pqc_prof_launch_end(int h, cudaStream_t st);
 int pqc_pauli_apply_slots(const c128* src, c128* dst, int n, long long S, int slots_total,

@@ -717,6 +717,20 @@ extern "C" PQC_API int pqc_program_describe(const pqc_program* prog, char* out, 
     snprintf(buf, sizeof(buf), "v0 plan: %d run passes\n", (int)prog->run_passes.size());
     s += buf;
   }
+  if (prog->bi_cut >= 0) {
+    auto count = [](const pqc_program* q, int type) {
+      int k = 0;
+      for (const V1Stage& sg : q->v1_grad) k += sg.type == type;
+      return k;
+    };
+    snprintf(buf, sizeof(buf),
+             "BIDIR cut=%d/%d PF=%d PB=%d vector-passes %lld -> %lld | F passes=%d gathers=%d | "
+             "M passes=%d | B passes=%d gathers=%d\n",
+             prog->bi_cut, (int)prog->ops.size(), prog->bi_PF, prog->bi_PB, prog->fwd_cost,
+             prog->bi_cost, count(prog->bi_F, 0), count(prog->bi_F, 1),
+             (int)prog->bi_M->v1_run.size(), count(prog->bi_B, 0), count(prog->bi_B, 1));
+    s += buf;
+  }
   if ((int64_t)s.size() + 1 > cap) s.resize((size_t)cap - 1);
   memcpy(out, s.c_str(), s.size() + 1);
   return 0;
@@ -1446,8 +1460,12 @@ static int gram_ksplit(int n) {
 // loads each row-block fragment ONCE per step and feeds up to 16 tiles x 4 DMMAs from it.
 // Each CTA covers a short K slice (<= 1024 amplitudes), so every DMMA accumulation chain is
 // at most 64 long and the slices are added afterwards in a fixed order (blocked summation).
+// Rows 0..M1-1 are slots 0.. of `buf` (slots_total per parameter set); rows M1.. are slots
+// 1.. of `buf2` (slots2 per set; its slot 0 is the backward pipeline's copy of psi).
 __global__ void __launch_bounds__(384) k_gram_dmma(const c128* __restrict__ buf, int n,
-                                                   int slots_total, int M, int M8, int ksplit,
+                                                   int slots_total, int M1,
+                                                   const c128* __restrict__ buf2, int slots2,
+                                                   int M, int M8, int ksplit,
                                                    c128* __restrict__ gpart) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int NT = blockDim.x;
@@ -1458,6 +1476,7 @@ __global__ void __launch_bounds__(384) k_gram_dmma(const c128* __restrict__ buf,
   const int ks = blockIdx.x % ksplit;
   const long long D = 1ll << n, kbeg = (D / ksplit) * ks, nk = (D / ksplit) / GR_K;
   const c128* V = buf + ((s * slots_total) << n);
+  const c128* V2 = buf2 + ((s * slots2 + 1 - M1) << n);
   const int T = M8 / 8, ntile = T * (T + 1) / 2;
   const int t_begin = grp * GR_TPW, t_end = min(ntile, t_begin + GR_TPW);
   // tile index -> (row block, col block), 4 bits each, upper triangle row-major
@@ -1479,7 +1498,7 @@ __global__ void __launch_bounds__(384) k_gram_dmma(const c128* __restrict__ buf,
       const int r = e / GR_K, kk = e % GR_K;
       const unsigned sa = (unsigned)__cvta_generic_to_shared(sm + (b * M8 + r) * GR_ROW + kk);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa),
-                   "l"(V + ((long long)r << n) + k0 + kk));
+                   "l"((r < M1 ? V : V2) + ((long long)r << n) + k0 + kk));
     }
     asm volatile("cp.async.commit_group;");
   };
@@ -1555,13 +1574,22 @@ __global__ void __launch_bounds__(384) k_gram_dmma(const c128* __restrict__ buf,
 
 // F_pq = 4 Re(G[1+p][1+q] - conj(G[0][1+p]) G[0][1+q]), p <= q, mirrored; K slices summed in
 // a fixed order.
+// `inv` (meet-in-the-middle plan): parameter -> Gram column, sign bit set for the vectors of the
+// backward pipeline, which carry -d_p (their gates run with negated angles).
 __global__ void k_qfim_from_gram(const c128* __restrict__ gpart, long long S, int P, int ksplit,
-                                 double* __restrict__ F) {
+                                 const int* __restrict__ inv, double* __restrict__ F) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= S * P * P) return;
   const int M = P + 1;
   const long long s = e / ((long long)P * P);
-  const int r = (int)((e / P) % P), c = (int)(e % P);
+  int r = (int)((e / P) % P), c = (int)(e % P);
+  double sign = 1.0;
+  if (inv) {
+    const int ir = inv[r], ic = inv[c];
+    if ((ir ^ ic) < 0) sign = -1.0;
+    r = ir & 0x7fffffff;
+    c = ic & 0x7fffffff;
+  }
   const int p = r < c ? r : c, q = r < c ? c : r;
   auto G = [&](int row, int col) -> c128 {
     double re = 0.0, im = 0.0;
@@ -1573,7 +1601,7 @@ __global__ void k_qfim_from_gram(const c128* __restrict__ gpart, long long S, in
     return make_double2(re, im);
   };
   const c128 sp = G(0, 1 + p), sq = G(0, 1 + q), d = G(1 + p, 1 + q);
-  F[e] = 4.0 * (d.x - (sp.x * sq.x + sp.y * sq.y));
+  F[e] = sign * 4.0 * (d.x - (sp.x * sq.x + sp.y * sq.y));
 }
 
 bool pqc_v1_gram_ok(const pqc_program* prog) {
@@ -1590,6 +1618,13 @@ bool pqc_v1_gram_ok(const pqc_program* prog) {
 
 int pqc_v1_gram_qfim(const pqc_program* prog, const c128* buf, long long S, c128* d_gpart,
                      double* d_F, cudaStream_t st) {
+  return pqc_v1_gram_qfim2(prog, buf, prog->P + 1, prog->P + 1, buf, prog->P + 1, nullptr, S,
+                           d_gpart, d_F, st);
+}
+
+int pqc_v1_gram_qfim2(const pqc_program* prog, const c128* buf, int slots1, int M1,
+                      const c128* buf2, int slots2, const int* d_inv, long long S, c128* d_gpart,
+                      double* d_F, cudaStream_t st) {
   const int P = prog->P, M = P + 1, M8 = (M + 7) & ~7;
   const int T = M8 / 8, ntile = T * (T + 1) / 2, ngrp = (ntile + GR_TPW - 1) / GR_TPW;
   const int nthreads = 128 * ngrp;
@@ -1602,11 +1637,12 @@ int pqc_v1_gram_qfim(const pqc_program* prog, const c128* buf, long long S, c128
     attr_set = true;
   }
   if (S * ksplit > 0x7fffffffLL) PQC_FAIL(-1, "gram grid too large");
-  k_gram_dmma<<<(unsigned)(S * ksplit), nthreads, smem, st>>>(buf, prog->n, P + 1, M, M8, ksplit,
-                                                              d_gpart);
+  k_gram_dmma<<<(unsigned)(S * ksplit), nthreads, smem, st>>>(buf, prog->n, slots1, M1, buf2,
+                                                              slots2, M, M8, ksplit, d_gpart);
   PQC_LAUNCH_CHECK();
   const long long tot = S * P * P;
-  k_qfim_from_gram<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_gpart, S, P, ksplit, d_F);
+  k_qfim_from_gram<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_gpart, S, P, ksplit, d_inv,
+                                                                  d_F);
   PQC_LAUNCH_CHECK();
   return 0;
 }
@@ -1727,6 +1763,25 @@ static size_t last_spawn_stage(const pqc_program* prog) {
   return last;
 }
 
+// vector-passes (tile loads + stores of one vector) the QFIM pipeline spends on this plan
+long long pqc_v1_plan_cost(const pqc_program* prog) {
+  const size_t end = last_spawn_stage(prog);
+  long long cost = 0;
+  int nlive = 1;
+  for (size_t i = 0; i < end; ++i) {
+    const V1Stage& sg = prog->v1_grad[i];
+    if (sg.type == 0) {
+      const V1Pass& ps = prog->v1_passes[sg.pass];
+      cost += nlive + (long long)ps.spawn_param.size();
+      for (int p : ps.spawn_param) nlive = std::max(nlive, p + 2);
+    } else if (sg.type == 1) {
+      for (int p : sg.gather_params) nlive = std::max(nlive, p + 2);
+      cost += (long long)sg.gather_params.size();
+    }
+  }
+  return cost;
+}
+
 int pqc_v1_n_passes(const pqc_program* prog, bool need_final) {
   const size_t end = need_final ? prog->v1_grad.size() : last_spawn_stage(prog);
   int k = 0;
@@ -1739,19 +1794,20 @@ int pqc_v1_n_passes(const pqc_program* prog, bool need_final) {
 // without it (QFIM) those unitary passes are skipped because they cannot change an overlap.
 // *final_buf receives the buffer holding the vectors after the last executed pass.
 int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long long ld, long long S,
-                       const c128* d_init, c128* buf_a, c128* buf_b, c128* d_gpart,
-                       bool want_dots, bool need_final, c128** final_buf, cudaStream_t st) {
+                       const c128* d_init, long long init_stride, c128* buf_a, c128* buf_b,
+                       c128* d_gpart, bool want_dots, bool need_final, c128** final_buf,
+                       cudaStream_t st) {
   const int P = prog->P, n = prog->n;
   const int slots_total = P + 1;
   c128* pp[2] = {buf_a, buf_b};
   int cur = 0;                       // buffer holding the current vectors
   int nlive = 1;
-  const int mode = !d_init ? 1 : 2;
+  const int mode = !d_init ? 1 : (init_stride == 0 ? 2 : 3);
   const int ntiles = 1 << std::max(0, n - V1_LOCAL_BITS);
   bool first = true;
   if (pqc_program_upload(prog)) return -2;
   {
-    const int rc = launch_init(pp[0], mode, d_init, 0, S, slots_total, n, st);
+    const int rc = launch_init(pp[0], mode, d_init, init_stride, S, slots_total, n, st);
     if (rc) return rc;
   }
   const size_t end = need_final ? prog->v1_grad.size() : last_spawn_stage(prog);

@@ -259,6 +259,27 @@ def test_multi_pass_qfim_vs_oracle(kind, n, p):
         assert rel(F[s].cpu().numpy(), orc.qfi(ref_st[s], gr[s])) < RTOL
 
 
+@pytest.mark.parametrize("kind,n,p", [("TFIM", 13, 8), ("XXZ", 12, 3), ("generic_HE", 12, 3),
+                                      ("NPQC", 12, 4), ("Circuit_9", 11, 3)])
+def test_meet_in_the_middle_qfim_matches_forward_plan_and_oracle(kind, n, p, monkeypatch):
+    """The default QFIM plan differentiates the two halves of the circuit from both ends and takes
+    the Gram matrix at the cut; PQC_BIDIR=0 runs the forward-only plan.  Both must agree with
+    each other and with the oracle's literal measure.py:33-71."""
+    qc = pyqc.templates.generate_circuit(kind, n, p, shuffle=False)
+    assert "BIDIR" in qc.program.describe()
+    specs, init = orc.generate_circuit(kind, n, p)
+    ang = np.random.default_rng(7 * n + p).random((3, orc.n_params(specs))) * 2 * np.pi
+    F, st = qc.qfim_batch(ang, want_states=True)
+    monkeypatch.setenv("PQC_BIDIR", "0")
+    F0, st0 = qc.qfim_batch(ang, want_states=True)
+    monkeypatch.delenv("PQC_BIDIR")
+    assert np.abs((st - st0).cpu().numpy()).max() < ATOL
+    assert rel(F.cpu().numpy(), F0.cpu().numpy()) < 1e-12
+    ref_st = orc.run(specs, n, ang[:1], init)
+    gr = orc.gradients(specs, n, ang[:1], init)
+    assert rel(F[0].cpu().numpy(), orc.qfi(ref_st[0], gr[0])) < RTOL
+
+
 def test_eigvalsh_vs_lapack():
     rng = np.random.default_rng(11)
     for P in (1, 2, 5, 12, 32, 33, 64):

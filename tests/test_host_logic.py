@@ -158,3 +158,19 @@ def test_planner_runs_without_gpu_and_fuses_tfim_layers():
     assert small.n_passes <= 22 and small.grad_supported
     tiny = pyqc.templates.generate_circuit("NPQC", 4, 4).program     # n < 8: v0 tile plan
     assert "v0 plan" in tiny.describe()
+
+
+def test_planner_meet_in_the_middle_qfim_plan():
+    """QFIM plan: the circuit is cut in the middle, the second half is differentiated backwards
+    from psi(T); the vector-pass count (what the HBM traffic is proportional to) drops ~1.6x."""
+    import re
+    d = pyqc.templates.generate_circuit("TFIM", 16, 16).program.describe()
+    m = re.search(r"BIDIR cut=(\d+)/(\d+) PF=(\d+) PB=(\d+) vector-passes (\d+) -> (\d+)", d)
+    assert m, d[-300:]
+    cut, nops, pf, pb, fwd, bi = map(int, m.groups())
+    assert (cut, nops, pf, pb) == (272, 528, 16, 16)          # H layer + 8 of 16 layers
+    assert fwd == 289 and bi <= 185
+    # circuits with a gate that is not inverted by negating its angle keep the forward plan
+    assert "BIDIR" not in pyqc.templates.generate_circuit("fsim", 12, 2).program.describe()
+    # too few parameters / qubits: forward plan
+    assert "BIDIR" not in pyqc.templates.generate_circuit("TFIM", 8, 4).program.describe()
