@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpqc_b200.so")
+# PQC_LIB_PATH: developer override used by tools/microbench.py to A/B kernel build variants.
+LIB_PATH = os.environ.get("PQC_LIB_PATH") or os.path.join(HERE, "libpqc_b200.so")
 
 # opcodes (enum pqc_opcode)
 OP_RX, OP_RY, OP_RZ, OP_H, OP_X, OP_S, OP_T, OP_CNOT, OP_CZ, OP_SQRTISWAP, OP_RXX, OP_RYY, \

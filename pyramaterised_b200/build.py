@@ -51,5 +51,32 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines, verbose=False):
+    """Developer A/B builds: pyramaterised_b200/variants/lib<name>.so with extra -D flags."""
+    vdir = os.path.join(HERE, "variants")
+    os.makedirs(os.path.join(vdir, name), exist_ok=True)
+    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")] + ["-D" + d for d in defines]
+    objs, procs = [], []
+    for src in sources():
+        obj = os.path.join(vdir, name, os.path.basename(src)[:-3] + ".o")
+        cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(obj)
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stdout.write(out.decode())
+        if p.returncode:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    lib = os.path.join(vdir, "lib%s.so" % name)
+    subprocess.check_call([NVCC, "-shared", "-o", lib] + objs +
+                          ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:], verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

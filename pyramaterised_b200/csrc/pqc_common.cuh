@@ -102,8 +102,9 @@ struct MOp {               // one micro-op inside a sweep
   int l0, l1;              // local tile position of the bit, -1 if outside the tile
   int b0, b1;              // global bit positions
   int trig;                // first trig slot
-  int aux0, aux1;          // ZZSUM: zz-term offset / count;  GEN: in-pass spawn index
-  int npairs;              // ZZSUM: number of pairs
+  int aux0, aux1;          // ZZSUM / GEN: aux1 = offset of the op's linear-form table in `wtab`;
+                           // GEN: aux0 = in-pass spawn index
+  int npairs;              // ZZSUM: number of pairs;  GEN: number of generator terms
   int subk;                // LAYER_*4: gate on register bit K in byte K: 0 none, else opcode+1
   int subt[4];             // LAYER_*4: trig slot of the gate on register bit K
 };
@@ -115,12 +116,24 @@ struct SweepD {
   unsigned char tl[8];     // local position fed by thread bit t (the 8 non-register positions)
   unsigned char tg[8];     // global amplitude bit of that position, 255 = item bit (n < 12)
   unsigned short sz[4];    // swizzled shared-memory mask of register bit k
+  unsigned gm[4];          // global amplitude-index mask of register bit k
+  unsigned char gb[4];     // global bit number of register bit k
+  // thread -> tile position / amplitude bits, split by nibble of tid so the kernel needs two
+  // table reads instead of an 8-step bit deposit:
+  unsigned short tpos[2][16];   // base(tid) = tpos[0][tid & 15] | tpos[1][tid >> 4]
+  unsigned tamp[2][16];         // amp bits  = tamp[0][tid & 15] | tamp[1][tid >> 4]
 };
 struct TrigJob {           // per-item trig table entry (or run of entries) to fill
   int kind, param, param2, slot, npairs, pad;
   double scale, offset;
 };
-struct ZZTerm { uint32_t mask; int shift; };   // count += popc((x ^ (x >> shift)) & mask)
+// Linear forms over GF(2) for ZZSUM / GEN ops: a table of V1_WTAB words per op; word b holds,
+// in bit k, whether global index bit b takes part in term k (ZZSUM: pair k = {b0, b1}; GEN:
+// z-mask of generator term k).  w(x) = XOR of the words of x's set bits, and the number of
+// anti-aligned pairs (odd-parity terms) of basis state x is popc(w(x)).  Word 32 is zero.
+#define V1_WTAB 33
+#define V1_MAX_TERMS 32
+#define V1_MAX_WT 8          // linear-form tables per pass (staged in shared memory)
 
 struct V1Pass {
   int tb, low_run;
@@ -129,6 +142,8 @@ struct V1Pass {
   int sweep_off, nsweeps;  // into the program's device arrays
   int mop_off, nmops;
   int tj_off, ntjobs, ntrig;
+  int trig_goff;           // first slot of this pass in its plan's per-sample trig table
+  int wt_off, nwt;         // linear-form tables of this pass (V1_WTAB words each) in `wtab`
   // in-pass diagonal spawns, in order of their K_GEN micro-ops
   std::vector<int> spawn_param;
   bool direct_ok;
@@ -162,17 +177,22 @@ struct pqc_program {
   std::vector<int> v1_run;                   // pass indices of the plain run plan
   std::vector<V1Stage> v1_grad;              // stages of the derivative / QFIM plan
   std::vector<int> v1_gen_diag_off;          // per parameter: offset/count of diagonal terms
+  // trig jobs / per-sample trig-table slots of the run plan and of the derivative plan
+  int v1_run_tj0 = 0, v1_run_ntj = 0, v1_run_slots = 0;
+  int v1_grad_tj0 = 0, v1_grad_ntj = 0, v1_grad_slots = 0;
+  double2* d_trig = nullptr;                 // library-owned scratch: trig table [S][slots]
+  size_t trig_cap = 0;                       // (one stream at a time per program)
   // host copies of the device arrays (uploaded lazily by pqc_program_upload)
   std::vector<MOp> h_mops;
   std::vector<SweepD> h_sweeps;
   std::vector<TrigJob> h_tjobs;
-  std::vector<ZZTerm> h_zz;
+  std::vector<uint32_t> h_zz;                 // linear-form tables (V1_WTAB words each)
   std::vector<DOp> h_dops;
   bool uploaded = false;
   MOp* d_mops = nullptr;
   SweepD* d_sweeps = nullptr;
   TrigJob* d_tjobs = nullptr;
-  ZZTerm* d_zz = nullptr;
+  uint32_t* d_zz = nullptr;
   // forward plan over the whole op list (PQC.run)
   std::vector<Pass> run_passes;
   // QFIM / gradient plan: one segment of passes per parameter, plus the trailing ops

@@ -109,7 +109,7 @@ void fuse_group(std::vector<COp>& run) {
     std::vector<size_t> mem;
     for (size_t j = i; j < run.size(); ++j)
       if (!dead[j] && run[j].kind == PQC_OP_RZZ && same_angle(run[i], run[j])) mem.push_back(j);
-    if (mem.size() < 2 || mem.size() > 48) continue;
+    if (mem.size() < 2 || mem.size() > V1_MAX_TERMS) continue;
     bool dup = false;                      // RR_block on 2 qubits lists its pair twice (quirk Q9)
     for (size_t u = 0; u < mem.size(); ++u)
       for (size_t v = u + 1; v < mem.size(); ++v)
@@ -164,7 +164,7 @@ struct Builder {
   std::vector<MOp>& mops;
   std::vector<SweepD>& sweeps;
   std::vector<TrigJob>& tjobs;
-  std::vector<ZZTerm>& zz;
+  std::vector<uint32_t>& zz;
   std::vector<V1Pass>& passes;
 
   // current pass
@@ -179,6 +179,8 @@ struct Builder {
   std::vector<int> spawn_param;
   bool open = false;
   int nmops_cur = 0;
+  int wt_begin = 0;                        // first linear-form table of the current pass
+  int plan_slots = 0;                      // trig slots used by the finished passes of this plan
 
   uint32_t lowmask() const { return n >= 4 ? 0xfu : ((1u << n) - 1u); }
 
@@ -192,7 +194,9 @@ struct Builder {
     spawn_param.clear();
     open = true;
     nmops_cur = 0;
+    wt_begin = (int)zz.size();
   }
+  int n_tables() const { return ((int)zz.size() - wt_begin) / V1_WTAB; }
   int room(int g, uint32_t need) const {   // free slots of group g for bits of `need`
     int r = 4 - (int)grp[g].size();
     if (g == 0) {                          // keep space for low bits that are still unplaced
@@ -230,6 +234,7 @@ struct Builder {
 
   int priority(const COp& c) const {       // lower is better; 99 = cannot take now
     if (!trig_fits(c) || sws.size() >= 30 || nmops_cur >= 150) return 99;
+    if (c.kind == PQC_K_ZZSUM && n_tables() >= V1_MAX_WT) return 99;
     if (!c.mix) return 0;
     const int g = target_group(c.mix);
     if (g < 0) return 99;
@@ -298,19 +303,15 @@ struct Builder {
       ntrig += te;
     }
     if (c.kind == PQC_K_ZZSUM) {
+      // linear-form table: bit k of word b <=> index bit b belongs to pair k
       m.npairs = (int)c.pairs.size();
-      m.aux0 = (int)zz.size();
-      // group the pairs by bit distance: count += popc((x ^ (x >> d)) & mask_d)
-      std::vector<std::pair<int, uint32_t>> terms;
-      for (auto& pr : c.pairs) {
-        const int lo = std::min(pr.first, pr.second), d = std::abs(pr.first - pr.second);
-        bool found = false;
-        for (auto& t : terms)
-          if (t.first == d) { t.second |= 1u << lo; found = true; }
-        if (!found) terms.push_back({d, 1u << lo});
+      m.aux1 = (int)zz.size() - wt_begin;
+      zz.resize(zz.size() + V1_WTAB, 0u);
+      uint32_t* w = zz.data() + wt_begin + m.aux1;
+      for (size_t k = 0; k < c.pairs.size(); ++k) {
+        w[c.pairs[k].first] ^= 1u << k;
+        w[c.pairs[k].second] ^= 1u << k;
       }
-      for (auto& t : terms) zz.push_back(ZZTerm{t.second, t.first});
-      m.aux1 = (int)terms.size();
     }
     return m;
   }
@@ -347,6 +348,15 @@ struct Builder {
     m.k0 = m.k1 = m.l0 = m.l1 = m.b0 = m.b1 = -1;
     m.trig = -1;
     m.aux0 = (int)spawn_param.size();
+    // linear-form table of the generator's z-masks: bit t of word b = bit b of z_t
+    m.aux1 = (int)zz.size() - wt_begin;
+    zz.resize(zz.size() + V1_WTAB, 0u);
+    uint32_t* w = zz.data() + wt_begin + m.aux1;
+    const int g0 = prog->gen_off[param], g1 = prog->gen_off[param + 1];
+    m.npairs = g1 - g0;
+    for (int t = g0; t < g1; ++t)
+      for (int b = 0; b < 32; ++b)
+        if ((prog->gens[t].zmask >> b) & 1u) w[b] |= 1u << (t - g0);
     spawn_param.push_back(param);
     ++nmops_cur;
     if (sws.empty() || !sws.back().post.empty()) sws.push_back(SW{-1, {}, {}, {}});
@@ -423,6 +433,21 @@ struct Builder {
           d.tg[t] = posn < cap ? (unsigned char)ps.lbit[posn] : (unsigned char)255;
           ++t;
         }
+        for (int k = 0; k < 4; ++k) {
+          d.gb[k] = (unsigned char)ps.lbit[rb[k]];
+          d.gm[k] = 1u << ps.lbit[rb[k]];
+        }
+        for (int h = 0; h < 2; ++h)
+          for (int v = 0; v < 16; ++v) {
+            unsigned pos = 0, amp = 0;
+            for (int i = 0; i < 4; ++i)
+              if ((v >> i) & 1) {
+                pos |= 1u << d.tl[4 * h + i];
+                if (d.tg[4 * h + i] < 32) amp |= 1u << d.tg[4 * h + i];
+              }
+            d.tpos[h][v] = (unsigned short)pos;
+            d.tamp[h][v] = amp;
+          }
       }
       d.mop_begin = (int)mops.size() - ps.mop_off;
       auto emit = [&](std::vector<MOp>& list) {
@@ -480,9 +505,16 @@ struct Builder {
     ps.io_first = sweeps[ps.sweep_off].io;
     ps.io_last = sweeps[ps.sweep_off + ps.nsweeps - 1].io;
     ps.tj_off = (int)tjobs.size();
-    for (auto& j : tj) tjobs.push_back(j);
     ps.ntjobs = (int)tj.size();
     ps.ntrig = std::max(1, ntrig);
+    ps.trig_goff = plan_slots;
+    for (auto j : tj) {
+      j.slot += plan_slots;                 // slot in the plan's per-sample table
+      tjobs.push_back(j);
+    }
+    plan_slots += ps.ntrig;
+    ps.wt_off = wt_begin;
+    ps.nwt = n_tables();
     ps.spawn_param = spawn_param;
     passes.push_back(ps);
     open = false;
@@ -554,17 +586,18 @@ int pqc_plan_v1(pqc_program* prog) {
         ci = prog->gens[t].im;
       }
       if (prog->gen_off[p + 1] == prog->gen_off[p]) param_diag[p] = false;
+      if (prog->gen_off[p + 1] - prog->gen_off[p] > V1_MAX_TERMS) param_diag[p] = false;
     }
 
   std::vector<MOp> mops;
   std::vector<SweepD> sweeps;
   std::vector<TrigJob> tjobs;
-  std::vector<ZZTerm> zz;
+  std::vector<uint32_t> zz;
   const int cap = std::min(n, V1_LOCAL_BITS);
   const int ipc = 1 << (V1_LOCAL_BITS - cap);
 
   // one planning routine, with or without derivative markers
-  auto plan = [&](bool markers, std::vector<int>* run_out, std::vector<V1Stage>* stages) {
+  auto plan = [&](bool markers, std::vector<int>* run_out, std::vector<V1Stage>* stages) -> int {
     Builder B{prog, n, cap, ipc, mops, sweeps, tjobs, zz, prog->v1_passes};
     std::vector<bool> spawned(P, false);
     std::vector<int> pending_dots;
@@ -633,7 +666,10 @@ int pqc_plan_v1(pqc_program* prog) {
           if (param_block[p] == (int)bi && !spawned[p]) {
             if (param_diag[p] && onload) {
               if (!B.open) B.begin();
-              if ((int)B.spawn_param.size() >= V1_MAX_SPAWN) { emit_pass(); B.begin(); }
+              if ((int)B.spawn_param.size() >= V1_MAX_SPAWN || B.n_tables() >= V1_MAX_WT) {
+                emit_pass();
+                B.begin();
+              }
               B.take_gen(p);
               spawned[p] = true;
             } else {
@@ -658,12 +694,17 @@ int pqc_plan_v1(pqc_program* prog) {
       d.partners = pending_dots;
       stages->push_back(d);
     }
+    return B.plan_slots;
   };
 
-  plan(false, &prog->v1_run, nullptr);
+  prog->v1_run_tj0 = 0;
+  prog->v1_run_slots = plan(false, &prog->v1_run, nullptr);
+  prog->v1_run_ntj = (int)tjobs.size();
   prog->v1_ok = true;
   if (grad_ok && P > 0) {
-    plan(true, nullptr, &prog->v1_grad);
+    prog->v1_grad_tj0 = (int)tjobs.size();
+    prog->v1_grad_slots = plan(true, nullptr, &prog->v1_grad);
+    prog->v1_grad_ntj = (int)tjobs.size() - prog->v1_grad_tj0;
     prog->v1_grad_ok = true;
   }
 
@@ -739,17 +780,79 @@ extern "C" PQC_API int pqc_program_describe(const pqc_program* prog, char* out, 
 // =====================================================================================
 // sweep kernel
 // =====================================================================================
+// Per-sample trig table of one plan: entry [sample][slot] for every TrigJob.  Computed once
+// per batch so the pass kernel's prologue is a plain 16-byte load per entry (no sincos, no
+// dependent angle loads in front of the first barrier).
+__global__ void __launch_bounds__(256) k_trig_fill(const TrigJob* __restrict__ jobs, int njobs,
+                                                   const double* __restrict__ angles, long long ld,
+                                                   long long S, int nslots,
+                                                   double2* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= S * njobs) return;
+  const long long sample = e / njobs;
+  const TrigJob jb = jobs[e - sample * njobs];
+  double2* t = out + sample * nslots + jb.slot;
+  double th = jb.offset, s, c;
+  if (jb.kind == PQC_OP_FSIM || jb.kind == PQC_OP_FIXED_FSIM) {
+    if (jb.param >= 0) th += angles[sample * ld + jb.param];
+    sincos(th, &s, &c);
+    t[0] = make_double2(c, s);
+    const double ph = jb.param2 >= 0 ? angles[sample * ld + jb.param2] : jb.scale;
+    sincos(ph, &s, &c);
+    t[1] = make_double2(c, s);
+  } else {
+    if (jb.param >= 0) th += jb.scale * angles[sample * ld + jb.param];
+    if (jb.kind == PQC_K_ZZSUM) {
+      // entry[k] = exp(-i th/2 (npairs - 2k)), k = jb.pad = number of anti-aligned pairs
+      sincos(-0.5 * th * (double)(jb.npairs - 2 * jb.pad), &s, &c);
+      t[0] = make_double2(c, s);
+    } else if (jb.kind == PQC_K_RXY) {
+      sincos(th, &s, &c);                      // rx-like rotation by the FULL angle
+      t[0] = make_double2(c, s);
+    } else if (jb.pad == 1) {                  // member of a 1-qubit layer op: (tan, cos)
+      sincos(0.5 * th, &s, &c);
+      t[0] = make_double2(s / c, c);
+    } else {
+      sincos(0.5 * th, &s, &c);
+      t[0] = make_double2(c, s);
+    }
+  }
+}
+
+// grow-only scratch for the trig table of `prog` and one fill launch
+static int trig_prepare(const pqc_program* cprog, int tj0, int ntj, int nslots,
+                        const double* d_angles, long long ld, long long S, cudaStream_t st) {
+  pqc_program* prog = const_cast<pqc_program*>(cprog);
+  const size_t need = (size_t)std::max<long long>(1, S) * std::max(1, nslots);
+  if (prog->trig_cap < need) {
+    if (prog->d_trig) {
+      PQC_CUDA(cudaStreamSynchronize(st));
+      PQC_CUDA(cudaFree(prog->d_trig));
+      prog->d_trig = nullptr;
+      prog->trig_cap = 0;
+    }
+    PQC_CUDA(cudaMalloc(&prog->d_trig, need * sizeof(double2)));
+    prog->trig_cap = need;
+  }
+  const long long tot = S * ntj;
+  if (tot <= 0) return 0;
+  if ((tot + 255) / 256 > 0x7fffffffLL) PQC_FAIL(-1, "trig grid too large; split the batch");
+  k_trig_fill<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(prog->d_tjobs + tj0, ntj, d_angles, ld,
+                                                             S, nslots, prog->d_trig);
+  PQC_LAUNCH_CHECK();
+  return 0;
+}
+
 struct V1Args {
   const c128* src;           // buffer read by normal items (ping) -- may equal dst (in place)
   c128* dst;                 // buffer written (pong)
-  const double* angles;
-  long long ld;
   const MOp* mops;
   const SweepD* sweeps;
   int nsweeps;
-  const TrigJob* tjobs;
-  int ntjobs, ntrig;
-  const ZZTerm* zz;
+  const double2* gtrig;      // per-sample trig table [S][tstride], filled by k_trig_fill
+  int tstride, toff, ntrig;  // this pass' entries: gtrig[sample * tstride + toff + 0..ntrig)
+  const uint32_t* wtab;      // this pass' linear-form tables (nwt x V1_WTAB words)
+  int nwt;
   const GenTerm* gens;
   int n, tb, items_log2, low_run;
   int lbit[V1_LOCAL_BITS];
@@ -762,6 +865,7 @@ struct V1Args {
   c128* gpart;               // [S][P+1][P][ntiles]
   int P, ntiles;
   int sweeps_nmops, sweep0_io, last_io;
+  int pf_dist;               // L2 prefetch distance in CTAs (0 = off)
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t i) {
@@ -871,6 +975,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
   __shared__ double red[32];
   __shared__ MOp s_mops[V1_MAX_MOPS];
   __shared__ SweepD s_sweeps[V1_MAX_SWEEPS];
+  __shared__ uint32_t s_wt[V1_MAX_WT * V1_WTAB];
   const int tid = threadIdx.x;
   const int tiles_log2 = A.n - A.tb;
   const long long blk = blockIdx.x;
@@ -922,18 +1027,33 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
   c128 a[16];
   bool preloaded = false;
   if (!DOTS && direct_load && ipc == 1) {     // (the in-pass Gram path loads + dots together)
-    const SweepD sw = A.sweeps[0];
-    if ((sw.pad & 0xffff) == 0) {
-      uint32_t amp0 = tbase;
+    const SweepD* sw = A.sweeps;
+    if ((sw->pad & 0xffff) == 0) {
+      const uint32_t amp0 = tbase | __ldg(&sw->tamp[0][tid & 15]) | __ldg(&sw->tamp[1][tid >> 4]);
+      const uint32_t g0 = sw->gm[0], g1 = sw->gm[1], g2 = sw->gm[2], g3 = sw->gm[3];
+      const c128* sp = A.src + ((my_sample * A.slots_total + my_src) << A.n) + amp0;
 #pragma unroll
-      for (int t = 0; t < 8; ++t)
-        amp0 |= sw.tg[t] < 32 ? ((((uint32_t)tid >> t) & 1u) << sw.tg[t]) : 0u;
-      const uint32_t g0 = 1u << A.lbit[sw.rb[0]], g1 = 1u << A.lbit[sw.rb[1]],
-                     g2 = 1u << A.lbit[sw.rb[2]], g3 = 1u << A.lbit[sw.rb[3]];
-      const c128* sp = A.src + ((my_sample * A.slots_total + my_src) << A.n);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) a[j] = sp[amp0 ^ XSEL4R(j, g0, g1, g2, g3)];
+      for (int j = 0; j < 16; ++j) a[j] = sp[XSEL4R(j, g0, g1, g2, g3)];
       preloaded = true;
+    }
+  }
+
+  // ---- L2 prefetch of the tile a later CTA (blockIdx + pf_dist, about one wave ahead) will
+  // load: one 256-byte run per thread, fire and forget.  Turns that CTA's HBM latency into an
+  // L2 hit; the data waits in the 126 MB L2 for roughly one CTA lifetime.
+  if (A.pf_dist > 0 && ipc == 1 && A.tb == V1_LOCAL_BITS) {
+    const long long blk2 = blk + A.pf_dist;
+    if (blk2 < (long long)gridDim.x) {
+      const long long item2 = blk2 >> tiles_log2;
+      const uint32_t tile2 = (uint32_t)(blk2 & ((1ll << tiles_log2) - 1));
+      uint32_t amp2 = 0;
+      for (int j = 0; j < tiles_log2; ++j) amp2 |= ((tile2 >> j) & 1u) << A.obit[j];
+      amp2 |= local_to_amp((uint32_t)tid << 4);
+      const long long sample2 = item2 / ips;
+      const int r2 = (int)(item2 - sample2 * ips);
+      const int slot2 = (!GEN || r2 < A.active) ? r2 : 0;
+      const c128* pa = A.src + ((sample2 * A.slots_total + slot2) << A.n) + amp2;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], 256;" ::"l"(pa) : "memory");
     }
   }
 
@@ -947,38 +1067,12 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     const int* g2 = reinterpret_cast<const int*>(A.sweeps);
     for (int e = tid; e < A.nsweeps * (int)(sizeof(SweepD) / 4); e += 256) d2[e] = g2[e];
   }
-  for (int e = tid; e < ipc * A.ntjobs; e += 256) {
-    const int li = e / A.ntjobs;
-    const TrigJob jb = A.tjobs[e - li * A.ntjobs];
+  for (int e = tid; e < A.nwt * V1_WTAB; e += 256) s_wt[e] = A.wtab[e];
+  for (int e = tid; e < ipc * A.ntrig; e += 256) {
+    const int li = e / A.ntrig;
     const long long item = item0 + li;
     if (item >= A.n_items) continue;
-    const long long sample = item / ips;
-    double2* t = trig + (size_t)li * A.ntrig + jb.slot;
-    double th = jb.offset, s, c;
-    if (jb.kind == PQC_OP_FSIM || jb.kind == PQC_OP_FIXED_FSIM) {
-      if (jb.param >= 0) th += A.angles[sample * A.ld + jb.param];
-      sincos(th, &s, &c);
-      t[0] = make_double2(c, s);
-      const double ph = jb.param2 >= 0 ? A.angles[sample * A.ld + jb.param2] : jb.scale;
-      sincos(ph, &s, &c);
-      t[1] = make_double2(c, s);
-    } else {
-      if (jb.param >= 0) th += jb.scale * A.angles[sample * A.ld + jb.param];
-      if (jb.kind == PQC_K_ZZSUM) {
-        // entry[k] = exp(-i th/2 (npairs - 2k)), k = jb.pad = number of anti-aligned pairs
-        sincos(-0.5 * th * (double)(jb.npairs - 2 * jb.pad), &s, &c);
-        t[0] = make_double2(c, s);
-      } else if (jb.kind == PQC_K_RXY) {
-        sincos(th, &s, &c);                      // rx-like rotation by the FULL angle
-        t[0] = make_double2(c, s);
-      } else if (jb.pad == 1) {                  // member of a 1-qubit layer op: (tan, cos)
-        sincos(0.5 * th, &s, &c);
-        t[0] = make_double2(s / c, c);
-      } else {
-        sincos(0.5 * th, &s, &c);
-        t[0] = make_double2(c, s);
-      }
-    }
+    trig[e] = A.gtrig[(item / ips) * A.tstride + A.toff + (e - li * A.ntrig)];
   }
 
   // ---- staged load (global -> swizzled shared) when the first sweep cannot load directly -------
@@ -1020,11 +1114,13 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
   __syncthreads();
 
   // ---- sweeps ------------------------------------------------------------------------------------
+  // product of the cos factors of the tangent-form layer ops; a scalar, so with one item per
+  // CTA it is carried across sweeps and multiplied in once before the final store
+  double fscale = 1.0;
   for (int si = 0; si < A.nsweeps; ++si) {
-    const SweepD sw = s_sweeps[si];
-    const uint32_t m0 = 1u << sw.rb[0], m1 = 1u << sw.rb[1], m2 = 1u << sw.rb[2], m3 = 1u << sw.rb[3];
-    const uint32_t rmask = m0 | m1 | m2 | m3;
-    // the 8 thread bits go to the non-register local positions (table from the planner)
+    const SweepD& sw = s_sweeps[si];
+    // the 8 thread bits go to the non-register local positions (tables from the planner)
+#ifdef V1_ALU_PROLOGUE
     uint32_t base = 0, amp0 = tbase;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
@@ -1032,12 +1128,14 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
       base |= bit << sw.tl[t];
       amp0 |= sw.tg[t] < 32 ? (bit << sw.tg[t]) : 0u;
     }
-    (void)rmask;
+#else
+    const uint32_t base = (uint32_t)sw.tpos[0][tid & 15] | (uint32_t)sw.tpos[1][tid >> 4];
+    const uint32_t amp0 = tbase | sw.tamp[0][tid & 15] | sw.tamp[1][tid >> 4];
+#endif
     // swz is linear over GF(2): swz(base | sel) = swz(base) ^ swz(sel)
     const uint32_t sb = swz(base), s0 = sw.sz[0], s1 = sw.sz[1], s2 = sw.sz[2], s3 = sw.sz[3];
     // global amplitude index of register j = amp0 | (selected g-masks)
-    const uint32_t g0 = 1u << A.lbit[sw.rb[0]], g1 = 1u << A.lbit[sw.rb[1]],
-                   g2 = 1u << A.lbit[sw.rb[2]], g3 = 1u << A.lbit[sw.rb[3]];
+    const uint32_t g0 = sw.gm[0], g1 = sw.gm[1], g2 = sw.gm[2], g3 = sw.gm[3];
     // X / CNOT are affine maps of the 4-bit register index: pi(j) = XOR_{k in j} col[k] ^ v.
     // They cost nothing per amplitude: they only change the load / store address constants.
     const int npre = sw.pad & 0xffff, npost = sw.pad >> 16;
@@ -1061,6 +1159,19 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     };
 #define LIN4(x, a0, a1, a2, a3) \
   ((((x)&1u) ? (a0) : 0u) ^ (((x)&2u) ? (a1) : 0u) ^ (((x)&4u) ? (a2) : 0u) ^ (((x)&8u) ? (a3) : 0u))
+    // w(amp0) and the words of the 4 register bits for a linear-form table (ZZSUM / GEN)
+    auto lin_words = [&](const uint32_t* wt, const SweepD& d, uint32_t& w0, uint32_t& w1,
+                         uint32_t& w2, uint32_t& w3, uint32_t& w4) {
+      uint32_t w = 0u;
+      for (int jb = 0; jb < tiles_log2; ++jb) w ^= ((tile >> jb) & 1u) ? wt[A.obit[jb]] : 0u;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int gbit = min((int)d.tg[t], 32);
+        w ^= ((tid >> t) & 1) ? wt[gbit] : 0u;
+      }
+      w0 = w;
+      w1 = wt[d.gb[0]]; w2 = wt[d.gb[1]]; w3 = wt[d.gb[2]]; w4 = wt[d.gb[3]];
+    };
     const int li = (int)(base >> A.tb);
     long long sample = my_sample;
     int src_slot = my_src, dst_slot = my_dst, gen = my_gen;
@@ -1131,10 +1242,17 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
       for (int j = 0; j < 16; ++j) a[j] = sm[lsb ^ XSEL4(j, ls0, ls1, ls2, ls3)];
     }
 
-    double fscale = 1.0;      // product of the cos factors of this sweep's tangent-form layers
     for (int mi = sw.mop_begin + npre; mi < sw.mop_end - npost; ++mi) {
       const MOp& m = s_mops[mi];
+#if defined(V1_ABL_NOOPS)           // timing ablations (tools/microbench.py); results are wrong
+      const int kind = PQC_OP_IDENT; (void)m;
+#elif defined(V1_ABL_NORX)
+      const int kind = m.kind == PQC_K_LAYER_RX4 ? PQC_OP_IDENT : m.kind;
+#elif defined(V1_ABL_NOZZ)
+      const int kind = m.kind == PQC_K_ZZSUM ? PQC_OP_IDENT : m.kind;
+#else
       const int kind = m.kind;
+#endif
       if (kind == PQC_K_LAYER_RX4) {
         // straight-line over the 4 register bits; absent gates are the identity (t 0, c 1).
         // trig entries of layer ops hold (tan, cos) of the half angle.
@@ -1162,36 +1280,15 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
 #undef REAL_SLOT
         fscale *= f;
       } else if (kind == PQC_K_ZZSUM) {
-        // count of anti-aligned pairs; <= 4 (mask, shift) terms, loaded once
-        uint32_t zm[4];
-        int zs[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const bool on = t < m.aux1;
-          const ZZTerm z = A.zz[m.aux0 + (on ? t : 0)];
-          zm[t] = on ? z.mask : 0u;
-          zs[t] = z.shift;
-        }
+        // phase = table[number of anti-aligned pairs of x] = table[popc(w(x))], w linear
+        uint32_t w0, w1, w2, w3, w4;
+        lin_words(s_wt + m.aux1, sw, w0, w1, w2, w3, w4);
         const double2* tz = tg + m.trig;
-        if (m.aux1 <= 2) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const uint32_t x = amp0 | SEL4(j, g0, g1, g2, g3);
-            const int cnt = __popc((x ^ (x >> zs[0])) & zm[0]) + __popc((x ^ (x >> zs[1])) & zm[1]);
-            const double2 ph = tz[cnt];
-            const c128 v = a[j];
-            a[j] = make_double2(v.x * ph.x - v.y * ph.y, v.y * ph.x + v.x * ph.y);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const uint32_t x = amp0 | SEL4(j, g0, g1, g2, g3);
-            const int cnt = __popc((x ^ (x >> zs[0])) & zm[0]) + __popc((x ^ (x >> zs[1])) & zm[1]) +
-                            __popc((x ^ (x >> zs[2])) & zm[2]) + __popc((x ^ (x >> zs[3])) & zm[3]);
-            const double2 ph = tz[cnt];
-            const c128 v = a[j];
-            a[j] = make_double2(v.x * ph.x - v.y * ph.y, v.y * ph.x + v.x * ph.y);
-          }
+        for (int j = 0; j < 16; ++j) {
+          const double2 ph = tz[__popc(w0 ^ XSEL4(j, w1, w2, w3, w4))];
+          const c128 v = a[j];
+          a[j] = make_double2(v.x * ph.x - v.y * ph.y, v.y * ph.x + v.x * ph.y);
         }
       } else if (kind == PQC_OP_RZ || kind == PQC_OP_S || kind == PQC_OP_T) {
         double c = 1.0, s = 0.0;
@@ -1237,22 +1334,17 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
       } else if (kind == PQC_K_GEN) {
         if (GEN && gen == m.aux0) {
           // uniform-coefficient diagonal generator: c0 * sum_t (-1)^{popc(x & z_t)}
-          const int goff = A.spawn_goff[gen], gcnt = A.spawn_gcnt[gen];
-          int sg[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) sg[j] = 0;
-          for (int t = 0; t < gcnt; ++t) {
-            const uint32_t zmask = A.gens[goff + t].zmask;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              sg[j] += 1 - 2 * (__popc((amp0 | SEL4(j, g0, g1, g2, g3)) & zmask) & 1);
-          }
-          const double cr = A.gens[goff].re, ci = A.gens[goff].im;
+          //   = c0 * (nterms - 2 popc(w(x)))
+          uint32_t w0, w1, w2, w3, w4;
+          lin_words(s_wt + m.aux1, sw, w0, w1, w2, w3, w4);
+          const double cr = A.gens[A.spawn_goff[gen]].re, ci = A.gens[A.spawn_goff[gen]].im;
+          const int nt = m.npairs;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const double f = (double)sg[j];
+            const double f = (double)(nt - 2 * __popc(w0 ^ XSEL4(j, w1, w2, w3, w4)));
+            const double fr = f * cr, fi = f * ci;
             const c128 v = a[j];
-            a[j] = make_double2(f * (v.x * cr - v.y * ci), f * (v.y * cr + v.x * ci));
+            a[j] = make_double2(v.x * fr - v.y * fi, v.y * fr + v.x * fi);
           }
         }
       } else if (kind != PQC_OP_IDENT) {
@@ -1277,7 +1369,14 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
       }
     }
 
-    if (fscale != 1.0) op_scale(a, fscale);       // uniform per item
+#ifdef V1_SCALE_PER_SWEEP
+    if (fscale != 1.0) {
+#else
+    if (fscale != 1.0 && (ipc > 1 || si + 1 == A.nsweeps)) {   // uniform per item
+#endif
+      op_scale(a, fscale);
+      fscale = 1.0;
+    }
     const bool ds = (si + 1 == A.nsweeps) && (sw.io & 2);
     uint32_t sc[4] = {1u, 2u, 4u, 8u}, sv = 0u;
     if (npost) affine(sw.mop_end - npost, sw.mop_end, false, sc, sv);
@@ -1333,10 +1432,15 @@ struct GatherArgs {
   int n, cb, slots_total;
   int nparams;
   int slot[V1_MAX_SPAWN], goff[V1_MAX_SPAWN], gcnt[V1_MAX_SPAWN];
+  unsigned char purex[V1_MAX_SPAWN];   // every term is an X-string with one common coefficient
   const GenTerm* gens;
 };
 
-__global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs A) {
+__device__ __forceinline__ double flip_sign(double v, uint32_t s31) {
+  return __hiloint2double(__double2hiint(v) ^ (int)s31, __double2loint(v));
+}
+
+__global__ void __launch_bounds__(256, 2) k_tile_gather(const GatherArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
   c128* sm = reinterpret_cast<c128*>(smraw);
   const int chunks_log2 = A.n - A.cb;
@@ -1348,35 +1452,70 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs A) {
   __syncthreads();
   for (int p = 0; p < A.nparams; ++p) {
     c128* out = A.buf + ((s * A.slots_total + A.slot[p]) << A.n);
+    const GenTerm* terms = A.gens + A.goff[p];
+    const int nt = A.gcnt[p];
     // 16 outputs per thread (element e = tid + 256 r); terms visited once each
     for (uint32_t i0 = threadIdx.x; i0 < csize; i0 += 256 * 16) {
       double are[16], aim[16];
 #pragma unroll
       for (int r = 0; r < 16; ++r) are[r] = aim[r] = 0.0;
-      for (int t = 0; t < A.gcnt[p]; ++t) {
-        const GenTerm g = A.gens[A.goff[p] + t];
-        const bool far = (g.xmask >> A.cb) != 0;
-        const int ny = __popc(g.xmask & g.zmask);
+      if (A.purex[p]) {
+        // sum_t psi[x ^ xmask_t], scaled once at the end: 2 adds per term and amplitude
+        for (int t = 0; t < nt; ++t) {
+          const uint32_t xm = terms[t].xmask;
+          if (xm >> A.cb) {
+            const uint32_t xb = (c0 + i0) ^ xm;
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+              if (i0 + 256u * r < csize) {
+                const c128 v = psi[xb ^ (256u * r)];
+                are[r] += v.x;
+                aim[r] += v.y;
+              }
+          } else {
+            const uint32_t b = i0 ^ (xm & 255u), hx = xm >> 8;
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+              if (i0 + 256u * r < csize) {
+                const c128 v = sm[b + 256u * ((uint32_t)r ^ hx)];
+                are[r] += v.x;
+                aim[r] += v.y;
+              }
+          }
+        }
+        const double cr = terms[0].re, ci = terms[0].im;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const uint32_t i = i0 + 256u * r;
-          if (i >= csize) continue;
-          const uint32_t x = (c0 + i) ^ g.xmask;
-          const c128 v = far ? psi[x] : sm[x - c0];
-          const int ph = (ny + 2 * __popc(x & g.zmask)) & 3;
-          c128 w;
-          if (ph == 0) w = v;
-          else if (ph == 1) w = make_double2(-v.y, v.x);
-          else if (ph == 2) w = make_double2(-v.x, -v.y);
-          else w = make_double2(v.y, -v.x);
-          are[r] += g.re * w.x - g.im * w.y;
-          aim[r] += g.re * w.y + g.im * w.x;
+          if (i < csize) out[c0 + i] = make_double2(are[r] * cr - aim[r] * ci, are[r] * ci + aim[r] * cr);
         }
-      }
+      } else {
+        for (int t = 0; t < nt; ++t) {
+          const GenTerm g = terms[t];
+          const bool far = (g.xmask >> A.cb) != 0;
+          // coefficient times i^(number of Y factors)
+          const int ny = __popc(g.xmask & g.zmask) & 3;
+          double cr = g.re, ci = g.im;
+          if (ny == 1) { cr = -g.im; ci = g.re; }
+          else if (ny == 2) { cr = -g.re; ci = -g.im; }
+          else if (ny == 3) { cr = g.im; ci = -g.re; }
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const uint32_t i = i0 + 256u * r;
-        if (i < csize) out[c0 + i] = make_double2(are[r], aim[r]);
+          for (int r = 0; r < 16; ++r) {
+            const uint32_t i = i0 + 256u * r;
+            if (i >= csize) continue;
+            const uint32_t x = (c0 + i) ^ g.xmask;
+            const c128 v = far ? psi[x] : sm[x - c0];
+            const uint32_t sg = ((uint32_t)__popc(x & g.zmask) & 1u) << 31;
+            const double vx = flip_sign(v.x, sg), vy = flip_sign(v.y, sg);
+            are[r] = fma(cr, vx, fma(-ci, vy, are[r]));
+            aim[r] = fma(cr, vy, fma(ci, vx, aim[r]));
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const uint32_t i = i0 + 256u * r;
+          if (i < csize) out[c0 + i] = make_double2(are[r], aim[r]);
+        }
       }
     }
   }
@@ -1433,17 +1572,27 @@ __global__ void k_qfim_reduce(const c128* __restrict__ gpart, long long S, int P
 }
 
 // =====================================================================================
-// Batched Gram matrix on the FP64 tensor cores: G_s = V_s^H V_s for the M = P + 1 live
-// vectors (psi, d_0 psi .. d_{P-1} psi) of every parameter set, all taken at ONE common
-// time (overlaps are invariant under the later unitary gates, measure.py:50-63 needs exactly
-// <psi|d_p> and <d_p|d_q>).  One CTA per (sample, K slice); 8 warps share the upper-triangular
-// 8x8 output tiles; K streamed 16 amplitudes at a time through cp.async double buffers.
+// QFIM Gram matrix on the FP64 tensor cores.  measure.py:55-70 needs only
+//   F_pq = 4 (Re<d_p|d_q> - Re(conj<psi|d_p> <psi|d_q>)),
+// and Re<d_p|d_q> is the REAL inner product of the two vectors read as 2 D doubles.  So the
+// P x P block is one real symmetric Gram V^T V over K = 2 D (half the DMMAs of the complex
+// product, and no padding row for psi), while the P complex overlaps <psi|d_p> are taken by
+// the CUDA cores from the same shared-memory stages.  All vectors are taken at ONE common
+// time (overlaps are invariant under the later unitary gates).
+// One CTA per (parameter set, K slice of 1024 amplitudes); warp (kw, grp) owns the k4-steps
+// kw, kw + ksh, .. of every 64-amplitude stage for the upper-triangular 8x8 tiles
+// [grp*16, grp*16+16); stages arrive through cp.async double buffers; the K shares and the K
+// slices are added in a fixed order (bitwise reproducible).
+// Rows 0..PF-1 are slots 1.. of `buf` (slot 0 = psi), rows PF.. are slots 1.. of `buf2`.
 // =====================================================================================
-#define GR_K 64                   // amplitudes per stage: 1 KB contiguous per vector row
-#define GR_ROW (GR_K + 4)         // padded complex per smem row (bank-conflict-free fragments)
+#define GR_K 32                   // amplitudes per stage: 512 B contiguous per vector row
+#define GR_NS 4                   // cp.async ring depth (3 stages in flight while one is used)
+#define GR_ROW (GR_K + 2)         // padded complex per smem row: the 8 rows of a fragment load
+                                  // (8 B per lane) fall into distinct banks
 #define GR_TPW 16                 // 8x8 output tiles per warp (one "tile group")
-#define GR_SLICE 1024             // amplitudes per CTA: DMMA chains stay <= 64 long
+#define GR_SLICE 1024             // amplitudes per CTA
 #define GR_MAXSPLIT 64
+#define GR_PSIROWS 9              // <psi|d_p> rows per warp (P <= 72, >= 8 warps)
 
 __device__ __forceinline__ void gr_dmma(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -1455,33 +1604,31 @@ static int gram_ksplit(int n) {
   return (int)std::max<long long>(1, std::min<long long>(GR_MAXSPLIT, D / GR_SLICE));
 }
 
-// Block = 4 K-shares x NG tile groups warps.  Warp (kw, grp) owns the upper-triangular tiles
-// [grp*GR_TPW, (grp+1)*GR_TPW) and the k4-steps kw, kw+4, .. of every 64-amplitude stage: it
-// loads each row-block fragment ONCE per step and feeds up to 16 tiles x 4 DMMAs from it.
-// Each CTA covers a short K slice (<= 1024 amplitudes), so every DMMA accumulation chain is
-// at most 64 long and the slices are added afterwards in a fixed order (blocked summation).
-// Rows 0..M1-1 are slots 0.. of `buf` (slots_total per parameter set); rows M1.. are slots
-// 1.. of `buf2` (slots2 per set; its slot 0 is the backward pipeline's copy of psi).
-__global__ void __launch_bounds__(384) k_gram_dmma(const c128* __restrict__ buf, int n,
-                                                   int slots_total, int M1,
-                                                   const c128* __restrict__ buf2, int slots2,
-                                                   int M, int M8, int ksplit,
-                                                   c128* __restrict__ gpart) {
+// SMALL: P <= 32 (at most 4 row blocks, 10 tiles, one tile group of 8 K-share warps): the 4
+// row-block fragments of a k4-step are loaded once and feed all tiles from registers.
+template <int NTMAX, int MINB, bool SMALL>
+__global__ void __launch_bounds__(NTMAX, MINB) k_gram_real(const c128* __restrict__ buf, int n,
+                                                           int slots_total, int PF,
+                                                           const c128* __restrict__ buf2, int slots2,
+                                                           int P, int P8, int ksplit, int ksh,
+                                                           double* __restrict__ gpart) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int NT = blockDim.x;
-  c128* sm = reinterpret_cast<c128*>(smraw);                       // [2][M8][GR_ROW]
+  const int NT = blockDim.x, nw = NT >> 5;
+  c128* sm = reinterpret_cast<c128*>(smraw);                       // [GR_NS][P8 + 1][GR_ROW]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-  const int kw = warp & 3, grp = warp >> 2;
+  const int kw = warp % ksh, grp = warp / ksh;
   const long long s = blockIdx.x / ksplit;
   const int ks = blockIdx.x % ksplit;
-  const long long D = 1ll << n, kbeg = (D / ksplit) * ks, nk = (D / ksplit) / GR_K;
+  const long long D = 1ll << n, kbeg = (D / ksplit) * ks;
+  const int nk = (int)((D / ksplit) / GR_K);
   const c128* V = buf + ((s * slots_total) << n);
-  const c128* V2 = buf2 + ((s * slots2 + 1 - M1) << n);
-  const int T = M8 / 8, ntile = T * (T + 1) / 2;
+  const c128* V2 = buf2 + (s * slots2 + 1 - PF) * D;   // row r >= PF: V2 + r D
+  const int rows = P8 + 1;                     // smem rows per stage; row P8 holds psi
+  const int T = P8 / 8, ntile = T * (T + 1) / 2;
   const int t_begin = grp * GR_TPW, t_end = min(ntile, t_begin + GR_TPW);
   // tile index -> (row block, col block), 4 bits each, upper triangle row-major
   unsigned long long tij_lo = 0, tij_hi = 0;   // 16 tiles x 8 bits
-  {
+  if (!SMALL) {
     int idx = 0;
     for (int i = 0; i < T; ++i)
       for (int j = i; j < T; ++j, ++idx)
@@ -1491,96 +1638,147 @@ __global__ void __launch_bounds__(384) k_gram_dmma(const c128* __restrict__ buf,
           if (q < 8) tij_lo |= v; else tij_hi |= v;
         }
   }
-  for (int e = tid; e < 2 * M8 * GR_ROW; e += NT) sm[e] = make_double2(0.0, 0.0);   // pad rows
+  for (int e = tid; e < GR_NS * rows * GR_ROW; e += NT) sm[e] = make_double2(0.0, 0.0);   // pad rows
   __syncthreads();
-  auto stage_load = [&](int b, long long k0) {
-    for (int e = tid; e < M * GR_K; e += NT) {
-      const int r = e / GR_K, kk = e % GR_K;
-      const unsigned sa = (unsigned)__cvta_generic_to_shared(sm + (b * M8 + r) * GR_ROW + kk);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa),
-                   "l"((r < M1 ? V : V2) + ((long long)r << n) + k0 + kk));
+  auto stage_load = [&](int it) {
+    if (it < nk) {
+      const int b = it % GR_NS;
+      const long long k0 = kbeg + (long long)it * GR_K;
+      for (int e = tid; e < (P + 1) * GR_K; e += NT) {
+        const int r = e / GR_K, kk = e % GR_K;
+        const c128* src = r == P ? V : (r < PF ? V + ((long long)(r + 1) << n)
+                                               : V2 + ((long long)r << n));
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(
+            sm + (b * rows + (r == P ? P8 : r)) * GR_ROW + kk);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + k0 + kk));
+      }
     }
-    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.commit_group;");    // (possibly empty: keeps the group count uniform)
   };
-  double re[GR_TPW][2], im[GR_TPW][2];
+  double acc[GR_TPW][2];
 #pragma unroll
-  for (int q = 0; q < GR_TPW; ++q) re[q][0] = re[q][1] = im[q][0] = im[q][1] = 0.0;
-  stage_load(0, kbeg);
-  for (long long it = 0; it < nk; ++it) {
-    const int b = (int)(it & 1);
-    if (it + 1 < nk) {
-      stage_load(b ^ 1, kbeg + (it + 1) * GR_K);
-      asm volatile("cp.async.wait_group 1;");
-    } else {
-      asm volatile("cp.async.wait_group 0;");
-    }
-    __syncthreads();
-    for (int kk = kw; kk < GR_K / 4; kk += 4) {
-      const c128* a_s = sm + (b * M8 + g) * GR_ROW + kk * 4 + t4;
+  for (int q = 0; q < GR_TPW; ++q) acc[q][0] = acc[q][1] = 0.0;
+  double sre[GR_PSIROWS], sim[GR_PSIROWS];
 #pragma unroll
-      for (int q = 0; q < GR_TPW; ++q) {
-        if (t_begin + q < t_end) {          // warp-uniform
-          const unsigned ij = (unsigned)(((q < 8 ? tij_lo : tij_hi) >> (8 * (q & 7))) & 0xff);
-          // fragments straight from shared memory: 2 LDS.128 per 4 DMMAs
-          const c128 fa = a_s[(ij & 15u) * (8 * GR_ROW)];
-          const c128 fb = a_s[(ij >> 4) * (8 * GR_ROW)];
-          gr_dmma(re[q][0], re[q][1], fa.x, fb.x);
-          gr_dmma(re[q][0], re[q][1], fa.y, fb.y);
-          gr_dmma(im[q][0], im[q][1], fa.x, fb.y);
-          gr_dmma(im[q][0], im[q][1], -fa.y, fb.x);
+  for (int m = 0; m < GR_PSIROWS; ++m) sre[m] = sim[m] = 0.0;
+#pragma unroll
+  for (int i = 0; i < GR_NS - 1; ++i) stage_load(i);
+  for (int it = 0; it < nk; ++it) {
+    const int b = it % GR_NS;
+    asm volatile("cp.async.wait_group %0;" ::"n"(GR_NS - 2));
+    __syncthreads();                 // stage `it` visible; everyone is done with stage it - 1
+    stage_load(it + GR_NS - 1);      // refill the buffer stage it - 1 used
+    // real Gram: k4-step kk covers the 4 doubles (2 amplitudes) 4 kk .. 4 kk + 3 of every row
+    for (int kk = kw; kk < GR_K / 2; kk += ksh) {
+      const double* a_s = reinterpret_cast<const double*>(sm + (b * rows + g) * GR_ROW) + 4 * kk + t4;
+      if (SMALL) {
+        double f[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[i] = i < T ? a_s[i * (8 * GR_ROW * 2)] : 0.0;
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = i; j < 4; ++j, ++q)
+            if (j < T) gr_dmma(acc[q][0], acc[q][1], f[i], f[j]);     // warp-uniform
+      } else {
+#pragma unroll
+        for (int q = 0; q < GR_TPW; ++q) {
+          if (t_begin + q < t_end) {          // warp-uniform
+            const unsigned ij = (unsigned)(((q < 8 ? tij_lo : tij_hi) >> (8 * (q & 7))) & 0xff);
+            const double fa = a_s[(ij & 15u) * (8 * GR_ROW * 2)];
+            const double fb = a_s[(ij >> 4) * (8 * GR_ROW * 2)];
+            gr_dmma(acc[q][0], acc[q][1], fa, fb);
+          }
         }
       }
     }
-    __syncthreads();
+    // <psi|d_p> for the rows p = warp, warp + nw, ..: one amplitude of the stage per lane
+    {
+      const c128 y = sm[(b * rows + P8) * GR_ROW + lane];
+#pragma unroll
+      for (int m = 0; m < GR_PSIROWS; ++m) {
+        const int p = warp + nw * m;
+        if ((!SMALL || m < 4) && p < P) {
+          const c128 x = sm[(b * rows + p) * GR_ROW + lane];
+          sre[m] += y.x * x.x + y.y * x.y;
+          sim[m] += y.x * x.y - y.y * x.x;
+        }
+      }
+    }
   }
-  // add the 4 K-shares of every tile group in a fixed order through the (now idle) stage
-  // buffers: scratch [grp][q][4][32] doubles
+  asm volatile("cp.async.wait_group 0;");
+  __syncthreads();
+  // add the K shares of every tile group in a fixed order through the (now idle) stage
+  // buffers: scratch [grp][q][2][32] doubles
   double* scr = reinterpret_cast<double*>(sm);
-  for (int r = 1; r < 4; ++r) {
+  for (int r = 1; r < ksh; ++r) {
     if (kw == r) {
-      double* o = scr + (size_t)grp * GR_TPW * 4 * 32 + lane;
+      double* o = scr + (size_t)grp * GR_TPW * 2 * 32 + lane;
 #pragma unroll
       for (int q = 0; q < GR_TPW; ++q) {
-        o[(q * 4 + 0) * 32] = re[q][0]; o[(q * 4 + 1) * 32] = re[q][1];
-        o[(q * 4 + 2) * 32] = im[q][0]; o[(q * 4 + 3) * 32] = im[q][1];
+        o[(q * 2 + 0) * 32] = acc[q][0];
+        o[(q * 2 + 1) * 32] = acc[q][1];
       }
     }
     __syncthreads();
     if (kw == 0) {
-      const double* o = scr + (size_t)grp * GR_TPW * 4 * 32 + lane;
+      const double* o = scr + (size_t)grp * GR_TPW * 2 * 32 + lane;
 #pragma unroll
       for (int q = 0; q < GR_TPW; ++q) {
-        re[q][0] += o[(q * 4 + 0) * 32]; re[q][1] += o[(q * 4 + 1) * 32];
-        im[q][0] += o[(q * 4 + 2) * 32]; im[q][1] += o[(q * 4 + 3) * 32];
+        acc[q][0] += o[(q * 2 + 0) * 32];
+        acc[q][1] += o[(q * 2 + 1) * 32];
       }
     }
     __syncthreads();
   }
-  c128* out = gpart + (s * ksplit + ks) * (long long)M * M;
+  double* out = gpart + (s * ksplit + ks) * ((long long)P * P + 2 * P);
   if (kw == 0) {
+    if (SMALL) {
+      int q = 0;
 #pragma unroll
-    for (int q = 0; q < GR_TPW; ++q)
-      if (t_begin + q < t_end) {
-        const unsigned ij = (unsigned)(((q < 8 ? tij_lo : tij_hi) >> (8 * (q & 7))) & 0xff);
-        const int ti = ij & 15, tj = ij >> 4;
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int row = 8 * ti + g, col = 8 * tj + 2 * t4 + c;
-          if (row < M && col < M) out[(long long)row * M + col] = make_double2(re[q][c], im[q][c]);
+        for (int j = i; j < 4; ++j, ++q)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int row = 8 * i + g, col = 8 * j + 2 * t4 + c;
+            if (row < P && col < P) out[(long long)row * P + col] = acc[q][c];
+          }
+    } else {
+#pragma unroll
+      for (int q = 0; q < GR_TPW; ++q)
+        if (t_begin + q < t_end) {
+          const unsigned ij = (unsigned)(((q < 8 ? tij_lo : tij_hi) >> (8 * (q & 7))) & 0xff);
+          const int ti = ij & 15, tj = ij >> 4;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int row = 8 * ti + g, col = 8 * tj + 2 * t4 + c;
+            if (row < P && col < P) out[(long long)row * P + col] = acc[q][c];
+          }
         }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < GR_PSIROWS; ++m) {
+    const int p = warp + nw * m;
+    if ((!SMALL || m < 4) && p < P) {          // warp-uniform
+      const double re = warp_sum(sre[m]), im = warp_sum(sim[m]);
+      if (lane == 0) {
+        out[(long long)P * P + p] = re;
+        out[(long long)P * P + P + p] = im;
       }
+    }
   }
 }
 
-// F_pq = 4 Re(G[1+p][1+q] - conj(G[0][1+p]) G[0][1+q]), p <= q, mirrored; K slices summed in
-// a fixed order.
-// `inv` (meet-in-the-middle plan): parameter -> Gram column, sign bit set for the vectors of the
+// F_pq = 4 (R[p][q] - Re(conj(s_p) s_q)), p <= q, mirrored; K slices summed in a fixed order.
+// `inv` (meet-in-the-middle plan): parameter -> Gram row, sign bit set for the vectors of the
 // backward pipeline, which carry -d_p (their gates run with negated angles).
-__global__ void k_qfim_from_gram(const c128* __restrict__ gpart, long long S, int P, int ksplit,
+__global__ void k_qfim_from_gram(const double* __restrict__ gpart, long long S, int P, int ksplit,
                                  const int* __restrict__ inv, double* __restrict__ F) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= S * P * P) return;
-  const int M = P + 1;
   const long long s = e / ((long long)P * P);
   int r = (int)((e / P) % P), c = (int)(e % P);
   double sign = 1.0;
@@ -1591,17 +1789,17 @@ __global__ void k_qfim_from_gram(const c128* __restrict__ gpart, long long S, in
     c = ic & 0x7fffffff;
   }
   const int p = r < c ? r : c, q = r < c ? c : r;
-  auto G = [&](int row, int col) -> c128 {
-    double re = 0.0, im = 0.0;
-    for (int ks = 0; ks < ksplit; ++ks) {
-      const c128 v = gpart[((s * ksplit + ks) * M + row) * M + col];
-      re += v.x;
-      im += v.y;
-    }
-    return make_double2(re, im);
-  };
-  const c128 sp = G(0, 1 + p), sq = G(0, 1 + q), d = G(1 + p, 1 + q);
-  F[e] = sign * 4.0 * (d.x - (sp.x * sq.x + sp.y * sq.y));
+  const long long stride = (long long)P * P + 2 * P;
+  double R = 0.0, pr = 0.0, pi = 0.0, qr = 0.0, qi = 0.0;
+  for (int ks = 0; ks < ksplit; ++ks) {
+    const double* o = gpart + (s * ksplit + ks) * stride;
+    R += o[(long long)p * P + q];
+    pr += o[(long long)P * P + p];
+    pi += o[(long long)P * P + P + p];
+    qr += o[(long long)P * P + q];
+    qi += o[(long long)P * P + P + q];
+  }
+  F[e] = sign * 4.0 * (R - (pr * qr + pi * qi));
 }
 
 bool pqc_v1_gram_ok(const pqc_program* prog) {
@@ -1610,10 +1808,8 @@ bool pqc_v1_gram_ok(const pqc_program* prog) {
     const char* e = getenv("PQC_QFIM_GRAM");
     off = (e && strcmp(e, "0") == 0) ? 1 : 0;
   }
-  const int M8 = (prog->P + 1 + 7) & ~7;
-  const int T = M8 / 8;
-  // T <= 9 row blocks (P <= 71): 45 tiles = 3 tile groups x 4 K-shares = 12 warps
-  return !off && prog->n >= 7 && T <= 9;
+  // T <= 9 row blocks (P <= 72): 45 tiles = 3 tile groups of 16
+  return !off && prog->n >= 7 && prog->P >= 1 && (prog->P + 7) / 8 <= 9;
 }
 
 int pqc_v1_gram_qfim(const pqc_program* prog, const c128* buf, long long S, c128* d_gpart,
@@ -1622,27 +1818,37 @@ int pqc_v1_gram_qfim(const pqc_program* prog, const c128* buf, long long S, c128
                            d_gpart, d_F, st);
 }
 
+// M1 = rows taken from `buf` including psi (slot 0); the other derivative rows are slots 1..
+// of `buf2`.
 int pqc_v1_gram_qfim2(const pqc_program* prog, const c128* buf, int slots1, int M1,
                       const c128* buf2, int slots2, const int* d_inv, long long S, c128* d_gpart,
                       double* d_F, cudaStream_t st) {
-  const int P = prog->P, M = P + 1, M8 = (M + 7) & ~7;
-  const int T = M8 / 8, ntile = T * (T + 1) / 2, ngrp = (ntile + GR_TPW - 1) / GR_TPW;
-  const int nthreads = 128 * ngrp;
+  const int P = prog->P, P8 = (P + 7) & ~7, PF = M1 - 1;
+  const int T = P8 / 8, ntile = T * (T + 1) / 2, ngrp = (ntile + GR_TPW - 1) / GR_TPW;
+  const int ksh = ngrp == 1 ? 8 : 4;            // K shares: at least 8 warps per CTA
+  const int nthreads = 32 * ksh * ngrp;
   const int ksplit = gram_ksplit(prog->n);
-  const size_t smem = std::max((size_t)2 * M8 * GR_ROW * sizeof(c128),
-                               (size_t)ngrp * GR_TPW * 4 * 32 * sizeof(double));
+  const size_t smem = std::max((size_t)GR_NS * (P8 + 1) * GR_ROW * sizeof(c128),
+                               (size_t)ngrp * GR_TPW * 2 * 32 * sizeof(double));
   static bool attr_set = false;
   if (!attr_set) {
-    PQC_CUDA(cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PQC_CUDA(cudaFuncSetAttribute(k_gram_real<256, 2, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    PQC_CUDA(cudaFuncSetAttribute(k_gram_real<384, 1, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   if (S * ksplit > 0x7fffffffLL) PQC_FAIL(-1, "gram grid too large");
-  k_gram_dmma<<<(unsigned)(S * ksplit), nthreads, smem, st>>>(buf, prog->n, slots1, M1, buf2,
-                                                              slots2, M, M8, ksplit, d_gpart);
+  double* gp = reinterpret_cast<double*>(d_gpart);
+  if (T <= 4)
+    k_gram_real<256, 2, true><<<(unsigned)(S * ksplit), nthreads, smem, st>>>(
+        buf, prog->n, slots1, PF, buf2, slots2, P, P8, ksplit, ksh, gp);
+  else
+    k_gram_real<384, 1, false><<<(unsigned)(S * ksplit), nthreads, smem, st>>>(
+        buf, prog->n, slots1, PF, buf2, slots2, P, P8, ksplit, ksh, gp);
   PQC_LAUNCH_CHECK();
   const long long tot = S * P * P;
-  k_qfim_from_gram<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_gpart, S, P, ksplit, d_inv,
-                                                                  d_F);
+  k_qfim_from_gram<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(gp, S, P, ksplit, d_inv, d_F);
   PQC_LAUNCH_CHECK();
   return 0;
 }
@@ -1657,10 +1863,11 @@ static int fill_pass_args(const pqc_program* prog, const V1Pass& ps, V1Args& a) 
   a.sweeps_nmops = ps.nmops;
   a.sweep0_io = ps.io_first;
   a.last_io = ps.io_last;
-  a.tjobs = prog->d_tjobs + ps.tj_off;
-  a.ntjobs = ps.ntjobs;
+  a.gtrig = prog->d_trig;
+  a.toff = ps.trig_goff;
   a.ntrig = ps.ntrig;
-  a.zz = prog->d_zz;
+  a.wtab = prog->d_zz + ps.wt_off;
+  a.nwt = ps.nwt;
   a.gens = prog->d_gens;
   a.n = prog->n;
   a.tb = ps.tb;
@@ -1680,7 +1887,18 @@ static int launch_init(c128* buf, int mode, const c128* init, long long init_str
   return 0;
 }
 
-static int launch_v1(const V1Args& a, cudaStream_t st) {
+static int prefetch_dist() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PQC_PREFETCH");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+static int launch_v1(const V1Args& a_in, cudaStream_t st) {
+  V1Args a = a_in;
+  a.pf_dist = (a.low_run >= 4) ? prefetch_dist() : 0;
   static bool attr_set = false;
   if (!attr_set) {
     PQC_CUDA(cudaFuncSetAttribute(k_sweep_pass<false, false>,
@@ -1715,23 +1933,32 @@ int pqc_v1_run(const pqc_program* prog, const double* d_angles, long long ld, lo
                const c128* d_init, long long init_stride, c128* d_out, cudaStream_t st) {
   const int mode = !d_init ? 1 : (init_stride == 0 ? 2 : 3);
   if (pqc_program_upload(prog)) return -2;
-  {
-    const int rc = launch_init(d_out, mode, d_init, init_stride, S, 1, prog->n, st);
+  // sample chunks keep the library-owned trig table below 256 MB
+  const long long D = 1ll << prog->n;
+  const long long per = (long long)std::max(1, prog->v1_run_slots) * (long long)sizeof(double2);
+  const long long chunk = std::max<long long>(1, (256ll << 20) / per);
+  for (long long c0 = 0; c0 < S; c0 += chunk) {
+    const long long c = std::min(chunk, S - c0);
+    const double* ang = d_angles ? d_angles + c0 * ld : nullptr;
+    c128* out = d_out + c0 * D;
+    int rc = trig_prepare(prog, prog->v1_run_tj0, prog->v1_run_ntj, prog->v1_run_slots, ang, ld, c, st);
     if (rc) return rc;
-  }
-  for (int pi : prog->v1_run) {
-    V1Args a;
-    memset(&a, 0, sizeof(a));
-    fill_pass_args(prog, prog->v1_passes[pi], a);
-    a.src = d_out;
-    a.dst = d_out;
-    a.angles = d_angles;
-    a.ld = ld;
-    a.n_items = S;
-    a.slots_total = 1;
-    a.active = 1;
-    const int rc = launch_v1(a, st);
+    rc = launch_init(out, mode, mode == 3 ? d_init + c0 * init_stride : d_init, init_stride, c, 1,
+                     prog->n, st);
     if (rc) return rc;
+    for (int pi : prog->v1_run) {
+      V1Args a;
+      memset(&a, 0, sizeof(a));
+      fill_pass_args(prog, prog->v1_passes[pi], a);
+      a.tstride = prog->v1_run_slots;
+      a.src = out;
+      a.dst = out;
+      a.n_items = c;
+      a.slots_total = 1;
+      a.active = 1;
+      rc = launch_v1(a, st);
+      if (rc) return rc;
+    }
   }
   return 0;
 }
@@ -1807,7 +2034,10 @@ int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long lon
   bool first = true;
   if (pqc_program_upload(prog)) return -2;
   {
-    const int rc = launch_init(pp[0], mode, d_init, init_stride, S, slots_total, n, st);
+    int rc = trig_prepare(prog, prog->v1_grad_tj0, prog->v1_grad_ntj, prog->v1_grad_slots, d_angles,
+                          ld, S, st);
+    if (rc) return rc;
+    rc = launch_init(pp[0], mode, d_init, init_stride, S, slots_total, n, st);
     if (rc) return rc;
   }
   const size_t end = need_final ? prog->v1_grad.size() : last_spawn_stage(prog);
@@ -1825,8 +2055,7 @@ int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long lon
       fill_pass_args(prog, ps, a);
       a.src = pp[cur];
       a.dst = pp[cur ^ 1];
-      a.angles = d_angles;
-      a.ld = ld;
+      a.tstride = prog->v1_grad_slots;
       a.slots_total = slots_total;
       a.active = nlive;
       a.nspawn = (int)ps.spawn_param.size();
@@ -1876,6 +2105,13 @@ int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long lon
           g.slot[k] = 1 + p;
           g.goff[k] = prog->gen_off[p];
           g.gcnt[k] = prog->gen_off[p + 1] - prog->gen_off[p];
+          bool pure = g.gcnt[k] > 0;
+          for (int t = g.goff[k]; t < g.goff[k] + g.gcnt[k]; ++t) {
+            const GenTerm& a = prog->gens[t];
+            const GenTerm& a0 = prog->gens[g.goff[k]];
+            if (a.zmask || a.re != a0.re || a.im != a0.im) pure = false;
+          }
+          g.purex[k] = pure ? 1 : 0;
         }
         const long long grid = S << (n - g.cb);
         if (grid > 0x7fffffffLL) PQC_FAIL(-1, "gather grid too large");
