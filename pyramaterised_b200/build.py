@@ -77,6 +77,7 @@ def build_variant(name, defines, verbose=False):
 if __name__ == "__main__":
     if "--variant" in sys.argv:
         i = sys.argv.index("--variant")
-        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:], verbose="-v" in sys.argv))
+        print(build_variant(sys.argv[i + 1], [d for d in sys.argv[i + 2:] if not d.startswith("-")],
+                            verbose="-v" in sys.argv))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -92,7 +92,11 @@ struct GenTerm {             // one Pauli term of a parameter's generator sum
 #define PQC_K_LAYER_RX4 35    // rx-type gate on each of the 4 register bits (identity = c 1, s 0)
 #define PQC_K_LAYER_REAL4 36  // real 2x2 on each register bit: RY, H or identity
 
+#ifndef V1_LOCAL_BITS
 #define V1_LOCAL_BITS 12          // 4096 amplitudes per CTA = 256 threads x 16 registers
+#endif
+#define V1_TBITS (V1_LOCAL_BITS - 4)   // thread bits: every thread holds 16 amplitudes
+#define V1_NT (1 << V1_TBITS)          // threads per CTA of the sweep kernel
 #define V1_MAX_SPAWN 32
 #define V1_MAX_PART 64
 

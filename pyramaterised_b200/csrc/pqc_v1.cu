@@ -440,7 +440,7 @@ struct Builder {
         for (int h = 0; h < 2; ++h)
           for (int v = 0; v < 16; ++v) {
             unsigned pos = 0, amp = 0;
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4 && 4 * h + i < V1_TBITS; ++i)
               if ((v >> i) & 1) {
                 pos |= 1u << d.tl[4 * h + i];
                 if (d.tg[4 * h + i] < 32) amp |= 1u << d.tg[4 * h + i];
@@ -968,7 +968,7 @@ __global__ void __launch_bounds__(256) k_init_slot0(c128* __restrict__ buf, int 
 // DOTS: take Gram partials against `partner_slot[]` while loading; GEN: the pass carries
 // in-pass diagonal-generator spawn items.
 template <bool DOTS, bool GEN>
-__global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
+__global__ void __launch_bounds__(V1_NT, 512 / V1_NT) k_sweep_pass(const V1Args A) {
   extern __shared__ __align__(16) unsigned char smraw[];
   c128* sm = reinterpret_cast<c128*>(smraw);
   double2* trig = reinterpret_cast<double2*>(sm + (1u << V1_LOCAL_BITS));
@@ -1008,14 +1008,15 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     for (int j = A.low_run; j < A.tb; ++j) r |= ((i >> j) & 1u) << A.lbit[j];
     return r;
   };
-  // staged (global <-> swizzled shared) element r of this thread: local index tid | r << 8
+  // staged (global <-> swizzled shared) element r of this thread: local index tid | r << V1_TBITS
   const uint32_t st_amp_tid = tbase | local_to_amp((uint32_t)tid & amask);
   uint32_t st_h[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) st_h[k] = (8 + k < A.tb) ? (1u << A.lbit[8 + k]) : 0u;
+  for (int k = 0; k < 4; ++k) st_h[k] = (V1_TBITS + k < A.tb) ? (1u << A.lbit[V1_TBITS + k]) : 0u;
   const uint32_t st_s_tid = swz((uint32_t)tid);
-  const uint32_t st_s[4] = {swz(1u << 8), swz(1u << 9), swz(1u << 10), swz(1u << 11)};
-  const int st_item_shift = A.tb - 8;          // li = r >> (tb - 8)   (tb >= 8)
+  const uint32_t st_s[4] = {swz(1u << V1_TBITS), swz(2u << V1_TBITS), swz(4u << V1_TBITS),
+                            swz(8u << V1_TBITS)};
+  const int st_item_shift = A.tb - V1_TBITS;    // li = r >> (tb - V1_TBITS)   (tb >= 8)
 
   const bool direct_load = (A.sweep0_io & 1) != 0;
   long long my_sample = 0;
@@ -1062,13 +1063,13 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
     const int nm = A.sweeps_nmops;
     int* d = reinterpret_cast<int*>(s_mops);
     const int* g = reinterpret_cast<const int*>(A.mops);
-    for (int e = tid; e < nm * (int)(sizeof(MOp) / 4); e += 256) d[e] = g[e];
+    for (int e = tid; e < nm * (int)(sizeof(MOp) / 4); e += V1_NT) d[e] = g[e];
     int* d2 = reinterpret_cast<int*>(s_sweeps);
     const int* g2 = reinterpret_cast<const int*>(A.sweeps);
-    for (int e = tid; e < A.nsweeps * (int)(sizeof(SweepD) / 4); e += 256) d2[e] = g2[e];
+    for (int e = tid; e < A.nsweeps * (int)(sizeof(SweepD) / 4); e += V1_NT) d2[e] = g2[e];
   }
-  for (int e = tid; e < A.nwt * V1_WTAB; e += 256) s_wt[e] = A.wtab[e];
-  for (int e = tid; e < ipc * A.ntrig; e += 256) {
+  for (int e = tid; e < A.nwt * V1_WTAB; e += V1_NT) s_wt[e] = A.wtab[e];
+  for (int e = tid; e < ipc * A.ntrig; e += V1_NT) {
     const int li = e / A.ntrig;
     const long long item = item0 + li;
     if (item >= A.n_items) continue;
@@ -1097,14 +1098,14 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
         if (my_src > ps) continue;
         const c128* pv = A.src + ((my_sample * A.slots_total + ps) << A.n);
         double re = 0.0, im = 0.0;
-        for (uint32_t i = tid; i < (1u << V1_LOCAL_BITS); i += 256) {
+        for (uint32_t i = tid; i < (1u << V1_LOCAL_BITS); i += V1_NT) {
           const uint32_t amp = tbase | local_to_amp(i);
           const c128 x = own[amp], y = pv[amp];
           re += x.x * y.x + x.y * y.y;
           im += x.x * y.y - x.y * y.x;
         }
-        re = block_sum<256>(re, red);
-        im = block_sum<256>(im, red);
+        re = block_sum<V1_NT>(re, red);
+        im = block_sum<V1_NT>(im, red);
         if (tid == 0)
           A.gpart[((my_sample * (A.P + 1) + my_src) * A.P + (ps - 1)) * A.ntiles + tile] =
               make_double2(re, im);
@@ -1123,7 +1124,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
 #ifdef V1_ALU_PROLOGUE
     uint32_t base = 0, amp0 = tbase;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < V1_TBITS; ++t) {
       const uint32_t bit = ((uint32_t)tid >> t) & 1u;
       base |= bit << sw.tl[t];
       amp0 |= sw.tg[t] < 32 ? (bit << sw.tg[t]) : 0u;
@@ -1165,7 +1166,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
       uint32_t w = 0u;
       for (int jb = 0; jb < tiles_log2; ++jb) w ^= ((tile >> jb) & 1u) ? wt[A.obit[jb]] : 0u;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
+      for (int t = 0; t < V1_TBITS; ++t) {
         const int gbit = min((int)d.tg[t], 32);
         w ^= ((tid >> t) & 1) ? wt[gbit] : 0u;
       }
@@ -1201,7 +1202,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
         a[j] = live ? sp[lgb ^ XSEL4(j, lg0, lg1, lg2, lg3)] : make_double2(0.0, 0.0);
       if (DOTS && gen < 0) {
         // Gram partials against every pending partner: per-warp shuffles, then ONE barrier
-        __shared__ double dred[8][2 * V1_MAX_PART];
+        __shared__ double dred[V1_NT / 32][2 * V1_MAX_PART];
         const int w = tid >> 5, l = tid & 31;
         for (int q = 0; q < A.npartners; ++q) {
           const int ps = A.partner_slot[q];
@@ -1224,7 +1225,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_pass(const V1Args A) {
           if (src_slot <= ps) {
             double v = 0.0;
 #pragma unroll
-            for (int ww = 0; ww < 8; ++ww) v += dred[ww][tid];
+            for (int ww = 0; ww < V1_NT / 32; ++ww) v += dred[ww][tid];
             double* g = reinterpret_cast<double*>(
                 A.gpart + ((sample * (A.P + 1) + src_slot) * A.P + (ps - 1)) * A.ntiles + tile);
             g[tid & 1] = v;
@@ -1443,6 +1444,7 @@ __device__ __forceinline__ double flip_sign(double v, uint32_t s31) {
 __global__ void __launch_bounds__(256, 2) k_tile_gather(const GatherArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
   c128* sm = reinterpret_cast<c128*>(smraw);
+  __shared__ uint32_t s_xm[64];
   const int chunks_log2 = A.n - A.cb;
   const long long s = blockIdx.x >> chunks_log2;
   const uint32_t c0 = (uint32_t)(blockIdx.x & ((1ll << chunks_log2) - 1)) << A.cb;
@@ -1460,9 +1462,13 @@ __global__ void __launch_bounds__(256, 2) k_tile_gather(const GatherArgs A) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) are[r] = aim[r] = 0.0;
       if (A.purex[p]) {
-        // sum_t psi[x ^ xmask_t], scaled once at the end: 2 adds per term and amplitude
+        // sum_t psi[x ^ xmask_t], scaled once at the end: 2 adds per term and amplitude.
+        // The masks are staged in shared memory so no iteration waits on a global load.
+        __syncthreads();
+        for (int t = threadIdx.x; t < nt && t < 64; t += 256) s_xm[t] = terms[t].xmask;
+        __syncthreads();
         for (int t = 0; t < nt; ++t) {
-          const uint32_t xm = terms[t].xmask;
+          const uint32_t xm = t < 64 ? s_xm[t] : terms[t].xmask;
           if (xm >> A.cb) {
             const uint32_t xb = (c0 + i0) ^ xm;
 #pragma unroll
@@ -1518,6 +1524,91 @@ __global__ void __launch_bounds__(256, 2) k_tile_gather(const GatherArgs A) {
         }
       }
     }
+  }
+}
+
+// Fast path of the gather for X-string generators with one common coefficient (the R_x / R_xx
+// layers of the Hamiltonian-variational templates), n >= 12: out = c * sum_t psi[x ^ xmask_t].
+// One CTA per (sample, 4096-amplitude chunk); thread tid owns elements tid + 256 r, r < 16,
+// r < 16.  Single-bit masks inside the chunk read it from shared memory with immediate offsets
+// (one LDS + two adds per amplitude), masks that leave the chunk read psi through L2.
+__global__ void __launch_bounds__(256, 2) k_xsum_gather(const GatherArgs A) {
+  extern __shared__ __align__(16) c128 xs_sm[];
+  __shared__ uint32_t s_xm[64];
+  const int tid = threadIdx.x;
+  const int chunks_log2 = A.n - 12;
+  const long long s = blockIdx.x >> chunks_log2;
+  const uint32_t c0 = (uint32_t)(blockIdx.x & ((1ll << chunks_log2) - 1)) << 12;
+  const c128* psi = A.buf + ((s * A.slots_total) << A.n);
+  {
+    c128 own[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) own[r] = psi[c0 + tid + 256 * r];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) xs_sm[tid + 256 * r] = own[r];
+  }
+  for (int p = 0; p < A.nparams; ++p) {
+    const GenTerm* terms = A.gens + A.goff[p];
+    const int nt = A.gcnt[p];
+    __syncthreads();
+    for (int t = tid; t < nt && t < 64; t += 256) s_xm[t] = terms[t].xmask;
+    __syncthreads();
+    double are[16], aim[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) are[r] = aim[r] = 0.0;
+    for (int t = 0; t < nt; ++t) {
+      const uint32_t xm = t < 64 ? s_xm[t] : terms[t].xmask;
+      const uint32_t lo = xm & 255u, hx = (xm >> 8) & 15u, far = xm >> 12;
+      if (far == 0 && lo == 0 && (hx & (hx - 1)) == 0) {
+        // one of the thread's own register bits
+#define XS_OWN(K)                                                              \
+  _Pragma("unroll") for (int r = 0; r < 16; ++r) {                             \
+    const c128 v = xs_sm[tid + 256 * (r ^ (1 << K))];                          \
+    are[r] += v.x;                                                             \
+    aim[r] += v.y;                                                             \
+  }
+        if (hx == 1) { XS_OWN(0) } else if (hx == 2) { XS_OWN(1) }
+        else if (hx == 4) { XS_OWN(2) } else { XS_OWN(3) }
+#undef XS_OWN
+      } else if (far == 0 && hx == 0) {
+        const c128* b = xs_sm + (tid ^ lo);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const c128 v = b[256 * r];
+          are[r] += v.x;
+          aim[r] += v.y;
+        }
+      } else if (far == 0) {
+        const uint32_t b = (uint32_t)tid ^ lo;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const c128 v = xs_sm[b + 256u * ((uint32_t)r ^ hx)];
+          are[r] += v.x;
+          aim[r] += v.y;
+        }
+      } else if ((xm & 0xfffu) == 0) {
+        const c128* b = psi + ((c0 ^ xm) + tid);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const c128 v = b[256 * r];
+          are[r] += v.x;
+          aim[r] += v.y;
+        }
+      } else {
+        const uint32_t xb = (c0 + tid) ^ xm;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const c128 v = psi[xb ^ (256u * r)];
+          are[r] += v.x;
+          aim[r] += v.y;
+        }
+      }
+    }
+    const double cr = terms[0].re, ci = terms[0].im;
+    c128* out = A.buf + ((s * A.slots_total + A.slot[p]) << A.n) + c0 + tid;
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      out[256 * r] = make_double2(are[r] * cr - aim[r] * ci, are[r] * ci + aim[r] * cr);
   }
 }
 
@@ -1833,7 +1924,7 @@ int pqc_v1_gram_qfim2(const pqc_program* prog, const c128* buf, int slots1, int 
   static bool attr_set = false;
   if (!attr_set) {
     PQC_CUDA(cudaFuncSetAttribute(k_gram_real<256, 2, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     PQC_CUDA(cudaFuncSetAttribute(k_gram_real<384, 1, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
@@ -1902,13 +1993,13 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     PQC_CUDA(cudaFuncSetAttribute(k_sweep_pass<false, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     PQC_CUDA(cudaFuncSetAttribute(k_sweep_pass<true, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     PQC_CUDA(cudaFuncSetAttribute(k_sweep_pass<false, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     PQC_CUDA(cudaFuncSetAttribute(k_sweep_pass<true, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
   const int ipc = 1 << a.items_log2;
@@ -1916,14 +2007,19 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
   const long long grid = groups << (a.n - a.tb);
   if (grid <= 0) return 0;
   if (grid > 0x7fffffffLL) PQC_FAIL(-1, "pass grid too large; split the batch");
+  static long smem_pad = -1;                 // developer knob: PQC_SMEM_PAD forces 1 CTA per SM
+  if (smem_pad < 0) {
+    const char* e = getenv("PQC_SMEM_PAD");
+    smem_pad = e ? atol(e) : 0;
+  }
   const size_t smem = ((size_t)1 << V1_LOCAL_BITS) * sizeof(c128) +
-                      (size_t)ipc * a.ntrig * sizeof(double2);
+                      (size_t)ipc * a.ntrig * sizeof(double2) + (size_t)smem_pad;
   const int h = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st);
   const bool dots = a.npartners > 0, gen = a.nspawn > 0;
-  if (dots && gen) k_sweep_pass<true, true><<<(unsigned)grid, 256, smem, st>>>(a);
-  else if (dots) k_sweep_pass<true, false><<<(unsigned)grid, 256, smem, st>>>(a);
-  else if (gen) k_sweep_pass<false, true><<<(unsigned)grid, 256, smem, st>>>(a);
-  else k_sweep_pass<false, false><<<(unsigned)grid, 256, smem, st>>>(a);
+  if (dots && gen) k_sweep_pass<true, true><<<(unsigned)grid, V1_NT, smem, st>>>(a);
+  else if (dots) k_sweep_pass<true, false><<<(unsigned)grid, V1_NT, smem, st>>>(a);
+  else if (gen) k_sweep_pass<false, true><<<(unsigned)grid, V1_NT, smem, st>>>(a);
+  else k_sweep_pass<false, false><<<(unsigned)grid, V1_NT, smem, st>>>(a);
   pqc_prof_launch_end(h, st);
   PQC_LAUNCH_CHECK();
   return 0;
@@ -2121,7 +2217,19 @@ int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long lon
                                         80 * 1024));
           gather_attr = true;
         }
-        k_tile_gather<<<(unsigned)grid, 256, ((size_t)1 << g.cb) * sizeof(c128), st>>>(g);
+        bool all_pure = n >= 12 && g.cb == 12;
+        for (int k = 0; k < g.nparams; ++k) all_pure = all_pure && g.purex[k];
+        if (all_pure) {
+          static bool xs_attr = false;
+          if (!xs_attr) {
+            PQC_CUDA(cudaFuncSetAttribute(k_xsum_gather, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          80 * 1024));
+            xs_attr = true;
+          }
+          k_xsum_gather<<<(unsigned)grid, 256, 4096 * sizeof(c128), st>>>(g);
+        } else {
+          k_tile_gather<<<(unsigned)grid, 256, ((size_t)1 << g.cb) * sizeof(c128), st>>>(g);
+        }
         PQC_LAUNCH_CHECK();
       }
     } else {
