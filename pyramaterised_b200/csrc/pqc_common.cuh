@@ -139,7 +139,28 @@ struct TrigJob {           // per-item trig table entry (or run of entries) to f
 #define V1_MAX_TERMS 32
 #define V1_MAX_WT 8          // linear-form tables per pass (staged in shared memory)
 
+// "Layer pass" fast path (k_layer_pass): a pass made of the aligned nibble sweeps
+// (registers = tile positions 8-11, then 0-3, then 4-7; or 8-11 then 4-7), loading and storing
+// global memory directly, whose ops are 1-qubit layer macro-ops, ZZSUM phases and in-pass
+// generator multiplies.  Its whole description travels in the kernel arguments (constant
+// bank): no staging of a micro-program, compile-time shared-memory addressing.
+#define FAST_MAX_OPS 4
+#define FAST_MAX_SPAWN 4
+struct FastOp {
+  int kind, subk;
+  int t[4];                // LAYER_*4: trig slot per register bit;  ZZSUM: t[0] = first table slot
+  int wt, nterms, spawn;   // ZZSUM / GEN: linear-form table index, term count; GEN: spawn index
+};
+struct FastPlan {
+  int ns;                  // 3: sweeps A, B, C;  2: sweeps A, C
+  int nops[3];
+  FastOp ops[3][FAST_MAX_OPS];
+};
+
 struct V1Pass {
+  bool fast_ok = false;
+  FastPlan fast;
+
   int tb, low_run;
   int lbit[V1_LOCAL_BITS];
   int obit[PQC_MAX_QUBITS];

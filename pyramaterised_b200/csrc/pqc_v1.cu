@@ -515,6 +515,47 @@ struct Builder {
     plan_slots += ps.ntrig;
     ps.wt_off = wt_begin;
     ps.nwt = n_tables();
+    // ---- layer-pass fast path eligibility -------------------------------------------------
+    ps.fast_ok = false;
+    memset(&ps.fast, 0, sizeof(ps.fast));
+    if (cap == V1_LOCAL_BITS && V1_LOCAL_BITS == 12 && ps.direct_ok && ps.low_run >= 4 &&
+        (ps.nsweeps == 2 || ps.nsweeps == 3) && (int)spawn_param.size() <= FAST_MAX_SPAWN &&
+        (ps.io_first & 1) && (ps.io_last & 2)) {
+      const int want3[3][4] = {{8, 9, 10, 11}, {0, 1, 2, 3}, {4, 5, 6, 7}};
+      const int want2[2][4] = {{8, 9, 10, 11}, {4, 5, 6, 7}};
+      bool ok = true;
+      ps.fast.ns = ps.nsweeps;
+      for (int si = 0; si < ps.nsweeps && ok; ++si) {
+        const SweepD& d = sweeps[ps.sweep_off + si];
+        const int* w = ps.nsweeps == 3 ? want3[si] : want2[si];
+        for (int k = 0; k < 4; ++k) ok = ok && d.rb[k] == w[k];
+        ok = ok && d.pad == 0 && d.mop_end - d.mop_begin <= FAST_MAX_OPS;
+        const int slot = ps.nsweeps == 3 ? si : (si == 0 ? 0 : 2);
+        ps.fast.nops[slot] = 0;
+        for (int mi = d.mop_begin; mi < d.mop_end && ok; ++mi) {
+          const MOp& m = mops[ps.mop_off + mi];
+          FastOp f;
+          memset(&f, 0, sizeof(f));
+          f.kind = m.kind;
+          f.subk = m.subk;
+          if (m.kind == PQC_K_LAYER_RX4 || m.kind == PQC_K_LAYER_REAL4) {
+            for (int k = 0; k < 4; ++k) f.t[k] = m.subt[k];
+          } else if (m.kind == PQC_K_ZZSUM) {
+            f.t[0] = m.trig;
+            f.wt = m.aux1 / V1_WTAB;
+            f.nterms = m.npairs;
+          } else if (m.kind == PQC_K_GEN) {
+            f.wt = m.aux1 / V1_WTAB;
+            f.nterms = m.npairs;
+            f.spawn = m.aux0;
+          } else {
+            ok = false;
+          }
+          ps.fast.ops[slot][ps.fast.nops[slot]++] = f;
+        }
+      }
+      ps.fast_ok = ok;
+    }
     ps.spawn_param = spawn_param;
     passes.push_back(ps);
     open = false;
@@ -866,6 +907,8 @@ struct V1Args {
   int P, ntiles;
   int sweeps_nmops, sweep0_io, last_io;
   int pf_dist;               // L2 prefetch distance in CTAs (0 = off)
+  const V1Pass* hpass;       // host side only: the pass (fast-path plan) and its program
+  const pqc_program* hprog;
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t i) {
@@ -1424,6 +1467,193 @@ __global__ void __launch_bounds__(V1_NT, 512 / V1_NT) k_sweep_pass(const V1Args 
 }
 
 // =====================================================================================
+// layer pass: the fast path for passes built from the three aligned nibble sweeps
+// (FastPlan, pqc_common.cuh).  Same arithmetic, same shared-memory swizzle and the same op
+// order as k_sweep_pass, but the pass description sits in the kernel arguments and the sweep
+// geometry is compile-time: shared-memory addresses are `base ^ constant`, the thread ->
+// amplitude maps are two 16-entry tables and the linear forms of the ZZSUM / GEN ops are
+// pre-folded per nibble value, so the per-amplitude integer work is one LOP3 + POPC.
+// =====================================================================================
+struct FastArgs {
+  const c128* src;
+  c128* dst;
+  const double2* gtrig;
+  int tstride, toff, ntrig;
+  const uint32_t* wtab;
+  int nwt;
+  int n;
+  int lbit[12];
+  int obit[PQC_MAX_QUBITS];
+  int slots_total, active, nspawn;
+  int spawn_slot[FAST_MAX_SPAWN];
+  double spawn_cr[FAST_MAX_SPAWN], spawn_ci[FAST_MAX_SPAWN];
+  FastPlan plan;
+};
+
+// the pass' ops on the 16 register amplitudes; RN = tile nibble held in registers, (NX, vx) and
+// (NY, vy) = the two nibbles fed by the thread index and this thread's values for them
+template <bool GEN, int RN, int NX, int NY>
+__device__ __forceinline__ void fast_ops(c128 (&a)[16], const FastArgs& A, int slot, int vx, int vy,
+                                         const double2* trig,
+                                         const uint32_t (*s_wn)[3][16], const uint32_t* s_wb,
+                                         int gen, double& fscale) {
+  const int nops = A.plan.nops[slot];
+  for (int oi = 0; oi < nops; ++oi) {
+    const FastOp& op = A.plan.ops[slot][oi];
+    const int kind = op.kind;
+    if (kind == PQC_K_LAYER_RX4) {
+      const int sk = op.subk;
+      double2 c0 = make_double2(0.0, 1.0), c1 = c0, c2 = c0, c3 = c0;
+      if (sk & 0xff) c0 = trig[op.t[0]];
+      if (sk & 0xff00) c1 = trig[op.t[1]];
+      if (sk & 0xff0000) c2 = trig[op.t[2]];
+      if (sk & 0xff000000) c3 = trig[op.t[3]];
+      op_rx_t<0>(a, c0.x);
+      op_rx_t<1>(a, c1.x);
+      op_rx_t<2>(a, c2.x);
+      op_rx_t<3>(a, c3.x);
+      fscale *= (c0.y * c1.y) * (c2.y * c3.y);
+    } else if (kind == PQC_K_LAYER_REAL4) {
+      const int sk = op.subk;
+      double f = 1.0;
+#define FAST_REAL_SLOT(K)                                                  \
+  {                                                                        \
+    const int kd = ((sk >> (8 * K)) & 0xff) - 1;                           \
+    if (kd == PQC_OP_RY) { const double2 tc = trig[op.t[K]]; op_ry_t<K>(a, tc.x); f *= tc.y; } \
+    else if (kd == PQC_OP_H) { op_h_u<K>(a); f *= 0.70710678118654752440; } \
+  }
+      FAST_REAL_SLOT(0) FAST_REAL_SLOT(1) FAST_REAL_SLOT(2) FAST_REAL_SLOT(3)
+#undef FAST_REAL_SLOT
+      fscale *= f;
+    } else {
+      // ZZSUM / GEN: w(x) = w(tile) ^ w(thread nibbles) ^ w(register nibble value j)
+      const uint32_t(*wn)[16] = s_wn[op.wt];
+      const uint32_t w0 = s_wb[op.wt] ^ wn[NX][vx] ^ wn[NY][vy];
+      const uint32_t w1 = wn[RN][1], w2 = wn[RN][2], w3 = wn[RN][4], w4 = wn[RN][8];
+      if (kind == PQC_K_ZZSUM) {
+        const double2* tz = trig + op.t[0];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const double2 ph = tz[__popc(w0 ^ XSEL4R(j, w1, w2, w3, w4))];
+          const c128 v = a[j];
+          a[j] = make_double2(v.x * ph.x - v.y * ph.y, v.y * ph.x + v.x * ph.y);
+        }
+      } else if (GEN && gen == op.spawn) {
+        const double cr = A.spawn_cr[gen], ci = A.spawn_ci[gen];
+        const int nt = op.nterms;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const double f = (double)(nt - 2 * __popc(w0 ^ XSEL4R(j, w1, w2, w3, w4)));
+          const double fr = f * cr, fi = f * ci;
+          const c128 v = a[j];
+          a[j] = make_double2(v.x * fr - v.y * fi, v.y * fr + v.x * fi);
+        }
+      }
+    }
+  }
+}
+
+template <int NS, bool GEN>
+__global__ void __launch_bounds__(256, 2) k_layer_pass(const FastArgs A) {
+  extern __shared__ __align__(16) c128 lp_sm[];
+  double2* trig = reinterpret_cast<double2*>(lp_sm + 4096);
+  __shared__ uint32_t s_ta[2][16];               // amplitude bits of tile nibbles 1 and 2
+  __shared__ uint32_t s_wn[V1_MAX_WT][3][16];    // linear forms per table, nibble, nibble value
+  __shared__ uint32_t s_wb[V1_MAX_WT];           // linear form of the tile index
+  const int tid = threadIdx.x, lo = tid & 15, hi = tid >> 4;
+  const int tiles_log2 = A.n - 12;
+  const long long item = (long long)blockIdx.x >> tiles_log2;
+  const uint32_t tile = (uint32_t)(blockIdx.x & ((1u << tiles_log2) - 1u));
+  uint32_t tbase = 0;
+  for (int j = 0; j < tiles_log2; ++j) tbase |= ((tile >> j) & 1u) << A.obit[j];
+  const int ips = A.active + A.nspawn;
+  const long long sample = item / ips;
+  const int r = (int)(item - sample * ips);
+  int src_slot = r, dst_slot = r, gen = -1;
+  if (GEN && r >= A.active) {
+    src_slot = 0;
+    gen = r - A.active;
+    dst_slot = A.spawn_slot[gen];
+  }
+  // ---- sweep A loads straight from global memory: registers = tile positions 8-11
+  c128 a[16];
+  {
+    const uint32_t ampA = tbase | (uint32_t)lo | ((uint32_t)(hi & 1) << A.lbit[4]) |
+                          ((uint32_t)((hi >> 1) & 1) << A.lbit[5]) |
+                          ((uint32_t)((hi >> 2) & 1) << A.lbit[6]) |
+                          ((uint32_t)((hi >> 3) & 1) << A.lbit[7]);
+    const uint32_t g0 = 1u << A.lbit[8], g1 = 1u << A.lbit[9], g2 = 1u << A.lbit[10],
+                   g3 = 1u << A.lbit[11];
+    const c128* sp = A.src + ((sample * A.slots_total + src_slot) << A.n) + ampA;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = sp[XSEL4R(j, g0, g1, g2, g3)];
+  }
+  // ---- tables (overlap the tile load)
+  if (tid < 32) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v |= (((uint32_t)lo >> i) & 1u) << A.lbit[4 + 4 * hi + i];
+    s_ta[hi][lo] = v;
+  }
+  for (int e = tid; e < A.nwt * 48; e += 256) {
+    const int tb = e / 48, rem = e - tb * 48, nib = rem >> 4, v = rem & 15;
+    const uint32_t* wt = A.wtab + tb * V1_WTAB;
+    uint32_t w = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w ^= ((v >> i) & 1) ? wt[A.lbit[4 * nib + i]] : 0u;
+    s_wn[tb][nib][v] = w;
+  }
+  if (tid < A.nwt) {
+    const uint32_t* wt = A.wtab + tid * V1_WTAB;
+    uint32_t w = 0;
+    for (int j = 0; j < tiles_log2; ++j) w ^= ((tile >> j) & 1u) ? wt[A.obit[j]] : 0u;
+    s_wb[tid] = w;
+  }
+  for (int e = tid; e < A.ntrig; e += 256) trig[e] = A.gtrig[sample * A.tstride + A.toff + e];
+  __syncthreads();
+
+  double fscale = 1.0;
+  // swizzled shared-memory index of register j: swz(base) ^ swz(j << shift)
+#define LP_CA(j) ((((j) << 8) ^ ((((j) << 2) ^ ((j) >> 1)) & 7)))   /* swz(j << 8) */
+#define LP_CB(j) (((j) ^ ((j) >> 3)))                               /* swz(j)      */
+#define LP_CC(j) ((((j) << 4) ^ ((((j) << 1) ^ ((j) >> 2)) & 7)))   /* swz(j << 4) */
+  fast_ops<GEN, 2, 0, 1>(a, A, 0, lo, hi, trig, s_wn, s_wb, gen, fscale);
+  {
+    const uint32_t sb = swz((uint32_t)tid);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) lp_sm[sb ^ LP_CA(j)] = a[j];
+  }
+  __syncthreads();
+  if (NS == 3) {
+    // sweep B: registers = positions 0-3, threads = positions 4-11
+    const uint32_t sb = swz((uint32_t)tid << 4);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = lp_sm[sb ^ LP_CB(j)];
+    fast_ops<GEN, 0, 1, 2>(a, A, 1, lo, hi, trig, s_wn, s_wb, gen, fscale);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) lp_sm[sb ^ LP_CB(j)] = a[j];
+    __syncthreads();
+  }
+  {
+    // sweep C: registers = positions 4-7, threads = positions 0-3 and 8-11; stores to global
+    const uint32_t sb = swz((uint32_t)lo | ((uint32_t)hi << 8));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = lp_sm[sb ^ LP_CC(j)];
+    fast_ops<GEN, 1, 0, 2>(a, A, 2, lo, hi, trig, s_wn, s_wb, gen, fscale);
+    if (fscale != 1.0) op_scale(a, fscale);
+    const uint32_t ampC = tbase | (uint32_t)lo | s_ta[1][hi];
+    const uint32_t g0 = 1u << A.lbit[4], g1 = 1u << A.lbit[5], g2 = 1u << A.lbit[6],
+                   g3 = 1u << A.lbit[7];
+    c128* dp = A.dst + ((sample * A.slots_total + dst_slot) << A.n) + ampC;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dp[XSEL4R(j, g0, g1, g2, g3)] = a[j];
+  }
+#undef LP_CA
+#undef LP_CB
+#undef LP_CC
+}
+
+// =====================================================================================
 // tile gather: dst slot <- (sum of Pauli terms) src slot 0, for one or more parameters.
 // One CTA per (sample, 4096-amplitude chunk); the chunk of psi sits in shared memory, terms
 // flipping only low bits read it from there, the others from global / L2.
@@ -1959,6 +2189,8 @@ static int fill_pass_args(const pqc_program* prog, const V1Pass& ps, V1Args& a) 
   a.ntrig = ps.ntrig;
   a.wtab = prog->d_zz + ps.wt_off;
   a.nwt = ps.nwt;
+  a.hpass = &ps;
+  a.hprog = prog;
   a.gens = prog->d_gens;
   a.n = prog->n;
   a.tb = ps.tb;
@@ -1987,6 +2219,15 @@ static int prefetch_dist() {
   return v;
 }
 
+static bool fast_enabled() {                 // PQC_FAST=0: always use the generic sweep kernel
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PQC_FAST");
+    v = (e && strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int launch_v1(const V1Args& a_in, cudaStream_t st) {
   V1Args a = a_in;
   a.pf_dist = (a.low_run >= 4) ? prefetch_dist() : 0;
@@ -2007,6 +2248,52 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
   const long long grid = groups << (a.n - a.tb);
   if (grid <= 0) return 0;
   if (grid > 0x7fffffffLL) PQC_FAIL(-1, "pass grid too large; split the batch");
+  if (a.hpass && a.hpass->fast_ok && a.npartners == 0 && a.nspawn <= FAST_MAX_SPAWN &&
+      fast_enabled()) {
+    FastArgs f;
+    memset(&f, 0, sizeof(f));
+    f.src = a.src;
+    f.dst = a.dst;
+    f.gtrig = a.gtrig;
+    f.tstride = a.tstride;
+    f.toff = a.toff;
+    f.ntrig = a.ntrig;
+    f.wtab = a.wtab;
+    f.nwt = a.nwt;
+    f.n = a.n;
+    memcpy(f.lbit, a.lbit, sizeof(f.lbit));
+    memcpy(f.obit, a.obit, sizeof(f.obit));
+    f.slots_total = a.slots_total;
+    f.active = a.active;
+    f.nspawn = a.nspawn;
+    for (int k = 0; k < a.nspawn; ++k) {
+      f.spawn_slot[k] = a.spawn_slot[k];
+      f.spawn_cr[k] = a.hprog->gens[a.spawn_goff[k]].re;
+      f.spawn_ci[k] = a.hprog->gens[a.spawn_goff[k]].im;
+    }
+    f.plan = a.hpass->fast;
+    static bool fattr = false;
+    if (!fattr) {
+      PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      fattr = true;
+    }
+    const size_t fsmem = 4096 * sizeof(c128) + (size_t)a.ntrig * sizeof(double2);
+    const int hh = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st);
+    const bool g = a.nspawn > 0;
+    if (f.plan.ns == 3) {
+      if (g) k_layer_pass<3, true><<<(unsigned)grid, 256, fsmem, st>>>(f);
+      else k_layer_pass<3, false><<<(unsigned)grid, 256, fsmem, st>>>(f);
+    } else {
+      if (g) k_layer_pass<2, true><<<(unsigned)grid, 256, fsmem, st>>>(f);
+      else k_layer_pass<2, false><<<(unsigned)grid, 256, fsmem, st>>>(f);
+    }
+    pqc_prof_launch_end(hh, st);
+    PQC_LAUNCH_CHECK();
+    return 0;
+  }
   static long smem_pad = -1;                 // developer knob: PQC_SMEM_PAD forces 1 CTA per SM
   if (smem_pad < 0) {
     const char* e = getenv("PQC_SMEM_PAD");
