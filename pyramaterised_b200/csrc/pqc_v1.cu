@@ -519,7 +519,7 @@ struct Builder {
     ps.fast_ok = false;
     memset(&ps.fast, 0, sizeof(ps.fast));
     if (cap == V1_LOCAL_BITS && V1_LOCAL_BITS == 12 && ps.direct_ok && ps.low_run >= 4 &&
-        (ps.nsweeps == 2 || ps.nsweeps == 3) && (int)spawn_param.size() <= FAST_MAX_SPAWN &&
+        ps.nsweeps >= 1 && ps.nsweeps <= 3 && (int)spawn_param.size() <= FAST_MAX_SPAWN &&
         (ps.io_first & 1) && (ps.io_last & 2)) {
       const int want3[3][4] = {{8, 9, 10, 11}, {0, 1, 2, 3}, {4, 5, 6, 7}};
       const int want2[2][4] = {{8, 9, 10, 11}, {4, 5, 6, 7}};
@@ -776,8 +776,8 @@ extern "C" PQC_API int pqc_program_describe(const pqc_program* prog, char* out, 
       }
       kinds += "]";
     }
-    snprintf(buf, sizeof(buf), "sweeps=%d mops=%d spawns=%d direct=%d/%d", ps.nsweeps, nm,
-             (int)ps.spawn_param.size(), ps.io_first & 1, (ps.io_last >> 1) & 1);
+    snprintf(buf, sizeof(buf), "sweeps=%d mops=%d spawns=%d direct=%d/%d fast=%d", ps.nsweeps, nm,
+             (int)ps.spawn_param.size(), ps.io_first & 1, (ps.io_last >> 1) & 1, ps.fast_ok ? 1 : 0);
     return std::string(buf) + kinds;
   };
   if (prog->v1_grad_ok) {
@@ -812,6 +812,26 @@ extern "C" PQC_API int pqc_program_describe(const pqc_program* prog, char* out, 
              prog->bi_cost, count(prog->bi_F, 0), count(prog->bi_F, 1),
              (int)prog->bi_M->v1_run.size(), count(prog->bi_B, 0), count(prog->bi_B, 1));
     s += buf;
+    // the three sub-programs of the meet-in-the-middle plan
+    const pqc_program* subs[3] = {prog->bi_F, prog->bi_M, prog->bi_B};
+    const char* names[3] = {"F", "M", "B"};
+    for (int k = 0; k < 3; ++k) {
+      const pqc_program* q = subs[k];
+      auto sub_line = [&](const V1Pass& ps) {
+        char b2[160];
+        snprintf(b2, sizeof(b2), "  %s PASS sweeps=%d spawns=%d direct=%d/%d fast=%d\n", names[k],
+                 ps.nsweeps, (int)ps.spawn_param.size(), ps.io_first & 1, (ps.io_last >> 1) & 1,
+                 ps.fast_ok ? 1 : 0);
+        s += b2;
+      };
+      if (k == 1) {
+        for (int pi : q->v1_run) sub_line(q->v1_passes[pi]);
+      } else {
+        for (const V1Stage& sg : q->v1_grad)
+          if (sg.type == 0) sub_line(q->v1_passes[sg.pass]);
+          else if (sg.type == 1) s += std::string("  ") + names[k] + " GATHER\n";
+      }
+    }
   }
   if ((int64_t)s.size() + 1 > cap) s.resize((size_t)cap - 1);
   memcpy(out, s.c_str(), s.size() + 1);
@@ -1487,6 +1507,7 @@ struct FastArgs {
   int slots_total, active, nspawn;
   int spawn_slot[FAST_MAX_SPAWN];
   double spawn_cr[FAST_MAX_SPAWN], spawn_ci[FAST_MAX_SPAWN];
+  int pf_dist;               // L2 prefetch distance in CTAs (0 = off)
   FastPlan plan;
 };
 
@@ -1588,6 +1609,23 @@ __global__ void __launch_bounds__(256, 2) k_layer_pass(const FastArgs A) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) a[j] = sp[XSEL4R(j, g0, g1, g2, g3)];
   }
+  // ---- L2 prefetch of the tile CTA blockIdx + pf_dist will load (one 256-byte run per thread)
+  if (A.pf_dist > 0) {
+    const long long blk2 = (long long)blockIdx.x + A.pf_dist;
+    if (blk2 < (long long)gridDim.x) {
+      const long long item2 = blk2 >> tiles_log2;
+      const uint32_t tile2 = (uint32_t)(blk2 & ((1ll << tiles_log2) - 1));
+      uint32_t amp2 = 0;
+      for (int j = 0; j < tiles_log2; ++j) amp2 |= ((tile2 >> j) & 1u) << A.obit[j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) amp2 |= (((uint32_t)tid >> i) & 1u) << A.lbit[4 + i];
+      const long long sample2 = item2 / ips;
+      const int r2 = (int)(item2 - sample2 * ips);
+      const int slot2 = (!GEN || r2 < A.active) ? r2 : 0;
+      const c128* pa = A.src + ((sample2 * A.slots_total + slot2) << A.n) + amp2;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], 256;" ::"l"(pa) : "memory");
+    }
+  }
   // ---- tables (overlap the tile load)
   if (tid < 32) {
     uint32_t v = 0;
@@ -1618,6 +1656,17 @@ __global__ void __launch_bounds__(256, 2) k_layer_pass(const FastArgs A) {
 #define LP_CB(j) (((j) ^ ((j) >> 3)))                               /* swz(j)      */
 #define LP_CC(j) ((((j) << 4) ^ ((((j) << 1) ^ ((j) >> 2)) & 7)))   /* swz(j << 4) */
   fast_ops<GEN, 2, 0, 1>(a, A, 0, lo, hi, trig, s_wn, s_wb, gen, fscale);
+  if (NS == 1) {
+    // single sweep: store the registers where they came from
+    if (fscale != 1.0) op_scale(a, fscale);
+    const uint32_t ampA = tbase | (uint32_t)lo | s_ta[0][hi];
+    const uint32_t g0 = 1u << A.lbit[8], g1 = 1u << A.lbit[9], g2 = 1u << A.lbit[10],
+                   g3 = 1u << A.lbit[11];
+    c128* dp = A.dst + ((sample * A.slots_total + dst_slot) << A.n) + ampA;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dp[XSEL4R(j, g0, g1, g2, g3)] = a[j];
+    return;
+  }
   {
     const uint32_t sb = swz((uint32_t)tid);
 #pragma unroll
@@ -2272,12 +2321,15 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
       f.spawn_ci[k] = a.hprog->gens[a.spawn_goff[k]].im;
     }
     f.plan = a.hpass->fast;
+    f.pf_dist = a.pf_dist;
     static bool fattr = false;
     if (!fattr) {
       PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       fattr = true;
     }
     const size_t fsmem = 4096 * sizeof(c128) + (size_t)a.ntrig * sizeof(double2);
@@ -2286,6 +2338,9 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
     if (f.plan.ns == 3) {
       if (g) k_layer_pass<3, true><<<(unsigned)grid, 256, fsmem, st>>>(f);
       else k_layer_pass<3, false><<<(unsigned)grid, 256, fsmem, st>>>(f);
+    } else if (f.plan.ns == 1) {
+      if (g) k_layer_pass<1, true><<<(unsigned)grid, 256, fsmem, st>>>(f);
+      else k_layer_pass<1, false><<<(unsigned)grid, 256, fsmem, st>>>(f);
     } else {
       if (g) k_layer_pass<2, true><<<(unsigned)grid, 256, fsmem, st>>>(f);
       else k_layer_pass<2, false><<<(unsigned)grid, 256, fsmem, st>>>(f);
