@@ -289,7 +289,7 @@ def run_b200(a):
     e2e = total * a.steps / (ms_e2e / 1e3)
     peak, peak_src = measured_peak_gbs()
     achieved = prof["bytes"] / (prof["ms"] / 1e3) / 1e9 if prof["ms"] > 0 else 0.0
-    kern = "k_sweep_pass"
+    kern = "k_layer_pass"     # the pass kernel of this workload (k_sweep_pass = its generic form)
     alg_per_launch = prof["bytes"] / max(1, prof["launches"])
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world,

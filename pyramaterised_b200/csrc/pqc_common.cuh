@@ -151,10 +151,15 @@ struct FastOp {
   int t[4];                // LAYER_*4: trig slot per register bit;  ZZSUM: t[0] = first table slot
   int wt, nterms, spawn;   // ZZSUM / GEN: linear-form table index, term count; GEN: spawn index
 };
+#define FAST_MAX_WT 4      // linear-form tables per fast pass
 struct FastPlan {
-  int ns;                  // 3: sweeps A, B, C;  2: sweeps A, C
+  int ns;                  // 3: sweeps A, B, C;  2: sweeps A, C;  1: sweep A only
   int nops[3];
   FastOp ops[3][FAST_MAX_OPS];
+  // linear forms folded per tile nibble (positions 0-3, 4-7, 8-11) and per out-of-tile bit, so
+  // the kernel's prologue copies them from the constant bank instead of chasing global tables
+  uint32_t wn[FAST_MAX_WT][3][16];
+  uint32_t wo[FAST_MAX_WT][PQC_MAX_QUBITS - 12];
 };
 
 struct V1Pass {

@@ -554,6 +554,20 @@ struct Builder {
           ps.fast.ops[slot][ps.fast.nops[slot]++] = f;
         }
       }
+      ok = ok && ps.nwt <= FAST_MAX_WT;
+      if (ok) {
+        for (int tb = 0; tb < ps.nwt; ++tb) {
+          const uint32_t* wt = zz.data() + ps.wt_off + tb * V1_WTAB;
+          for (int nib = 0; nib < 3; ++nib)
+            for (int v = 0; v < 16; ++v) {
+              uint32_t w = 0;
+              for (int i = 0; i < 4; ++i)
+                if ((v >> i) & 1) w ^= wt[ps.lbit[4 * nib + i]];
+              ps.fast.wn[tb][nib][v] = w;
+            }
+          for (int j = 0; j < n - V1_LOCAL_BITS; ++j) ps.fast.wo[tb][j] = wt[ps.obit[j]];
+        }
+      }
       ps.fast_ok = ok;
     }
     ps.spawn_param = spawn_param;
@@ -1494,6 +1508,13 @@ __global__ void __launch_bounds__(V1_NT, 512 / V1_NT) k_sweep_pass(const V1Args 
 // amplitude maps are two 16-entry tables and the linear forms of the ZZSUM / GEN ops are
 // pre-folded per nibble value, so the per-amplitude integer work is one LOP3 + POPC.
 // =====================================================================================
+#ifdef FAST_STREAM_HINTS     // A/B: evict-first hints on the streaming tile traffic
+#define LP_LD(p) __ldcs(p)
+#define LP_ST(p, v) __stcs(p, v)
+#else
+#define LP_LD(p) (*(p))
+#define LP_ST(p, v) (*(p) = (v))
+#endif
 struct FastArgs {
   const c128* src;
   c128* dst;
@@ -1579,8 +1600,8 @@ __global__ void __launch_bounds__(256, 2) k_layer_pass(const FastArgs A) {
   extern __shared__ __align__(16) c128 lp_sm[];
   double2* trig = reinterpret_cast<double2*>(lp_sm + 4096);
   __shared__ uint32_t s_ta[2][16];               // amplitude bits of tile nibbles 1 and 2
-  __shared__ uint32_t s_wn[V1_MAX_WT][3][16];    // linear forms per table, nibble, nibble value
-  __shared__ uint32_t s_wb[V1_MAX_WT];           // linear form of the tile index
+  __shared__ uint32_t s_wn[FAST_MAX_WT][3][16];  // linear forms per table, nibble, nibble value
+  __shared__ uint32_t s_wb[FAST_MAX_WT];         // linear form of the tile index
   const int tid = threadIdx.x, lo = tid & 15, hi = tid >> 4;
   const int tiles_log2 = A.n - 12;
   const long long item = (long long)blockIdx.x >> tiles_log2;
@@ -1607,7 +1628,7 @@ __global__ void __launch_bounds__(256, 2) k_layer_pass(const FastArgs A) {
                    g3 = 1u << A.lbit[11];
     const c128* sp = A.src + ((sample * A.slots_total + src_slot) << A.n) + ampA;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = sp[XSEL4R(j, g0, g1, g2, g3)];
+    for (int j = 0; j < 16; ++j) a[j] = LP_LD(sp + XSEL4R(j, g0, g1, g2, g3));
   }
   // ---- L2 prefetch of the tile CTA blockIdx + pf_dist will load (one 256-byte run per thread)
   if (A.pf_dist > 0) {
@@ -1633,18 +1654,10 @@ __global__ void __launch_bounds__(256, 2) k_layer_pass(const FastArgs A) {
     for (int i = 0; i < 4; ++i) v |= (((uint32_t)lo >> i) & 1u) << A.lbit[4 + 4 * hi + i];
     s_ta[hi][lo] = v;
   }
-  for (int e = tid; e < A.nwt * 48; e += 256) {
-    const int tb = e / 48, rem = e - tb * 48, nib = rem >> 4, v = rem & 15;
-    const uint32_t* wt = A.wtab + tb * V1_WTAB;
-    uint32_t w = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) w ^= ((v >> i) & 1) ? wt[A.lbit[4 * nib + i]] : 0u;
-    s_wn[tb][nib][v] = w;
-  }
+  for (int e = tid; e < A.nwt * 48; e += 256) (&s_wn[0][0][0])[e] = (&A.plan.wn[0][0][0])[e];
   if (tid < A.nwt) {
-    const uint32_t* wt = A.wtab + tid * V1_WTAB;
     uint32_t w = 0;
-    for (int j = 0; j < tiles_log2; ++j) w ^= ((tile >> j) & 1u) ? wt[A.obit[j]] : 0u;
+    for (int j = 0; j < tiles_log2; ++j) w ^= ((tile >> j) & 1u) ? A.plan.wo[tid][j] : 0u;
     s_wb[tid] = w;
   }
   for (int e = tid; e < A.ntrig; e += 256) trig[e] = A.gtrig[sample * A.tstride + A.toff + e];
@@ -1664,7 +1677,7 @@ __global__ void __launch_bounds__(256, 2) k_layer_pass(const FastArgs A) {
                    g3 = 1u << A.lbit[11];
     c128* dp = A.dst + ((sample * A.slots_total + dst_slot) << A.n) + ampA;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) dp[XSEL4R(j, g0, g1, g2, g3)] = a[j];
+    for (int j = 0; j < 16; ++j) LP_ST(dp + XSEL4R(j, g0, g1, g2, g3), a[j]);
     return;
   }
   {
@@ -1695,7 +1708,7 @@ __global__ void __launch_bounds__(256, 2) k_layer_pass(const FastArgs A) {
                    g3 = 1u << A.lbit[7];
     c128* dp = A.dst + ((sample * A.slots_total + dst_slot) << A.n) + ampC;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) dp[XSEL4R(j, g0, g1, g2, g3)] = a[j];
+    for (int j = 0; j < 16; ++j) LP_ST(dp + XSEL4R(j, g0, g1, g2, g3), a[j]);
   }
 #undef LP_CA
 #undef LP_CB
@@ -2269,12 +2282,8 @@ static int prefetch_dist() {
 }
 
 static bool fast_enabled() {                 // PQC_FAST=0: always use the generic sweep kernel
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PQC_FAST");
-    v = (e && strcmp(e, "0") == 0) ? 0 : 1;
-  }
-  return v == 1;
+  const char* e = getenv("PQC_FAST");        // (read per launch so tests can compare both paths)
+  return !(e && strcmp(e, "0") == 0);
 }
 
 static int launch_v1(const V1Args& a_in, cudaStream_t st) {

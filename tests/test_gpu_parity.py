@@ -280,6 +280,29 @@ def test_meet_in_the_middle_qfim_matches_forward_plan_and_oracle(kind, n, p, mon
     assert rel(F[0].cpu().numpy(), orc.qfi(ref_st[0], gr[0])) < RTOL
 
 
+@pytest.mark.parametrize("kind,n,p", [("TFIM", 16, 3), ("TFIM", 13, 4), ("TFIM_modified", 14, 2)])
+def test_layer_pass_fast_path_matches_generic_sweep_kernel(kind, n, p, monkeypatch):
+    """Passes made of aligned nibble sweeps run on k_layer_pass (plan lines say fast=1);
+    PQC_FAST=0 forces the generic k_sweep_pass.  Same arithmetic in the same order: states and
+    QFIMs must agree to rounding, and with the oracle."""
+    qc = pyqc.templates.generate_circuit(kind, n, p, shuffle=False)
+    assert "fast=1" in qc.program.describe()
+    specs, init = orc.generate_circuit(kind, n, p)
+    ang = np.random.default_rng(n + 31 * p).random((3, orc.n_params(specs))) * 2 * np.pi
+    st = qc.run_batch(ang)
+    F = qc.qfim_batch(ang)
+    monkeypatch.setenv("PQC_FAST", "0")
+    st0 = qc.run_batch(ang)
+    F0 = qc.qfim_batch(ang)
+    monkeypatch.delenv("PQC_FAST")
+    assert np.abs((st - st0).cpu().numpy()).max() < 1e-14
+    assert rel(F.cpu().numpy(), F0.cpu().numpy()) < 1e-12
+    ref = orc.run(specs, n, ang[:1], init)
+    assert np.abs(st[:1].cpu().numpy() - ref).max() < ATOL
+    gr = orc.gradients(specs, n, ang[:1], init)
+    assert rel(F[0].cpu().numpy(), orc.qfi(ref[0], gr[0])) < RTOL
+
+
 def test_eigvalsh_vs_lapack():
     rng = np.random.default_rng(11)
     for P in (1, 2, 5, 12, 32, 33, 64):

@@ -148,6 +148,7 @@ def test_planner_runs_without_gpu_and_fuses_tfim_layers():
     gathers = [l for l in lines if l.startswith("GATHER")]
     assert prog.n_qfim_passes == 17 and len(gathers) == 16
     assert all("direct=1/1" in l for l in passes)
+    assert all("fast=1" in l for l in passes)                  # aligned nibble sweeps: k_layer_pass
     assert sum("spawns=1" in l for l in passes) == 16          # R_zz rings: in-pass diagonal spawns
     assert all(l.count("[rb") <= 3 for l in passes[:17])        # three sweeps per pass
     # the 256 R_zz of the circuit became 16 fused phase ops (internal opcode 32)
