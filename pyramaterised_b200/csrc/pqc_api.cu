@@ -35,7 +35,7 @@ extern "C" int pqc_device_check(int* cc_major, int* cc_minor, int* n_sms) {
 static int plan_bidir(pqc_program* p);
 
 static int program_create(int n_qubits, int n_params, int n_ops, const pqc_op* h_ops,
-                          bool with_bidir, pqc_program** out) {
+                          bool with_bidir, pqc_program** out, int n_nodiff = 0) {
   if (!out) PQC_FAIL(-1, "null output handle");
   *out = nullptr;
   if (n_qubits < 1 || n_qubits > PQC_MAX_QUBITS) PQC_FAIL(-1, "n_qubits must be in [1, 30]");
@@ -55,6 +55,7 @@ static int program_create(int n_qubits, int n_params, int n_ops, const pqc_op* h
   pqc_program* p = new pqc_program();
   p->n = n_qubits;
   p->P = n_params;
+  p->n_nodiff = n_nodiff;
   p->ops.assign(h_ops, h_ops + n_ops);
   for (auto& op : p->ops) {
     const bool two = op.kind == PQC_OP_CNOT || op.kind == PQC_OP_CZ ||
@@ -92,6 +93,11 @@ extern "C" int pqc_program_create(int n_qubits, int n_params, int n_ops, const p
 // ---------------------------------------------------------------------------------
 static bool bidir_enabled() {
   const char* e = getenv("PQC_BIDIR");
+  return !(e && strcmp(e, "0") == 0);
+}
+
+static bool trailing_enabled() {             // PQC_BIDIR_TRAIL=0: F runs on to the cut
+  const char* e = getenv("PQC_BIDIR_TRAIL");
   return !(e && strcmp(e, "0") == 0);
 }
 
@@ -145,20 +151,48 @@ static bool bidir_build(pqc_program* p, int cut, const std::vector<int>& first,
   if (PF + PB != P || PB == 0 || PF == 0) return false;
   bidir_free(p);
   if (program_create(p->n, PF, (int)f_ops.size(), f_ops.data(), false, &p->bi_F)) return false;
-  if (program_create(p->n, P, nops - cut, p->ops.data() + cut, false, &p->bi_M)) return false;
-  if (program_create(p->n, PB, (int)b_ops.size(), b_ops.data(), false, &p->bi_B)) return false;
-  for (pqc_program* q : {p->bi_F, p->bi_B})
-    if (!q->v1_grad_ok || !q->grad_supported || q->v1_grad.empty() || q->v1_grad[0].type != 0)
-      return false;
+  if (!p->bi_F->v1_grad_ok || !p->bi_F->grad_supported || p->bi_F->v1_grad.empty() ||
+      p->bi_F->v1_grad[0].type != 0)
+    return false;
+  // F stops after its last spawn.  The ops of its pure-propagation tail (the closing pass that
+  // would finish e.g. the last R_x layer on every live vector) go to the front of M and, inverted,
+  // to the end of B, where they merge into passes that exist anyway.  B reads their angles from
+  // angle-only copies of the F parameters (appended columns).
+  std::vector<int> trail = trailing_enabled() ? pqc_v1_trailing_ops(p->bi_F) : std::vector<int>();
+  std::vector<pqc_op> m_ops;
+  for (int i : trail) m_ops.push_back(p->ops[i]);
+  m_ops.insert(m_ops.end(), p->ops.begin() + cut, p->ops.end());
+  std::vector<int> extra_loc(P, -1);
+  int n_extra = 0;
+  for (int k = (int)trail.size() - 1; k >= 0; --k) {
+    pqc_op op = p->ops[trail[k]];
+    op.scale = -op.scale;
+    op.offset = -op.offset;
+    if (op.param2 >= 0) return false;
+    if (op.param >= 0) {
+      if (extra_loc[op.param] < 0) { extra_loc[op.param] = PB + n_extra++; cols.push_back(op.param); }
+      op.param = extra_loc[op.param];
+    }
+    b_ops.push_back(op);
+  }
+  if (program_create(p->n, P, (int)m_ops.size(), m_ops.data(), false, &p->bi_M)) return false;
+  if (program_create(p->n, PB + n_extra, (int)b_ops.size(), b_ops.data(), false, &p->bi_B, n_extra))
+    return false;
+  if (!p->bi_B->v1_grad_ok || !p->bi_B->grad_supported || p->bi_B->v1_grad.empty() ||
+      p->bi_B->v1_grad[0].type != 0)
+    return false;
   if (!p->bi_M->v1_ok) return false;
   p->bi_cut = cut;
   p->bi_PF = PF;
   p->bi_PB = PB;
+  p->bi_ntrail = (int)trail.size();
+  p->bi_extra = n_extra;
   p->bi_cols = cols;
   p->bi_inv.assign(P, 0);
   for (int v = 0; v < P; ++v) p->bi_inv[cols[v]] = v | (v >= PF ? (int)0x80000000 : 0);
-  p->bi_cost = pqc_v1_plan_cost(p->bi_F) + pqc_v1_plan_cost(p->bi_B) +
-               (long long)p->bi_M->v1_run.size() + 2;
+  // B runs to its end (need_final): count all of its passes
+  long long bcost = pqc_v1_plan_cost(p->bi_B);
+  p->bi_cost = pqc_v1_plan_cost(p->bi_F) + bcost + (long long)p->bi_M->v1_run.size() + 2;
   (void)last;
   return true;
 }
@@ -393,9 +427,9 @@ static bool use_bidir(const pqc_program* prog) {
 static int64_t qfim_bytes_per_sample(const pqc_program* prog) {
   const int64_t D = 1ll << prog->n;
   if (use_bidir(prog))   // ping-pong pairs of both pipelines, psi(T), permuted angles, Gram
-    return (2 * (int64_t)(prog->P + 2) + 1) * D * (int64_t)sizeof(c128) +
+    return (2 * (int64_t)(prog->P + prog->bi_extra + 2) + 1) * D * (int64_t)sizeof(c128) +
            pqc_v1_gpart_elems(prog, 1) * (int64_t)sizeof(c128) +
-           (int64_t)((prog->P * sizeof(double) + 255) & ~(size_t)255);
+           (int64_t)(((prog->P + prog->bi_extra) * sizeof(double) + 255) & ~(size_t)255);
   if (prog->v1_grad_ok && !pqc_use_v0())   // two ping-pong copies + per-tile Gram partials
     return 2 * (int64_t)(prog->P + 1) * D * (int64_t)sizeof(c128) +
            pqc_v1_gpart_elems(prog, 1) * (int64_t)sizeof(c128);
@@ -430,37 +464,41 @@ static int qfim_bidir(const pqc_program* prog, const double* d_angles, int64_t l
   const int64_t D = 1ll << n;
   if (!prog->d_bi_cols) {
     pqc_program* mp = const_cast<pqc_program*>(prog);
-    PQC_CUDA(cudaMalloc(&mp->d_bi_cols, sizeof(int) * P));
+    PQC_CUDA(cudaMalloc(&mp->d_bi_cols, sizeof(int) * prog->bi_cols.size()));
     PQC_CUDA(cudaMalloc(&mp->d_bi_inv, sizeof(int) * P));
-    PQC_CUDA(cudaMemcpy(mp->d_bi_cols, prog->bi_cols.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+    PQC_CUDA(cudaMemcpy(mp->d_bi_cols, prog->bi_cols.data(), sizeof(int) * prog->bi_cols.size(),
+                        cudaMemcpyHostToDevice));
     PQC_CUDA(cudaMemcpy(mp->d_bi_inv, prog->bi_inv.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
   }
+  const int PA = P + prog->bi_extra;           // columns of the permuted angle array
+  const int PBx = PB + prog->bi_extra;         // B's parameters incl. the angle-only ones
   for (int64_t c0 = 0; c0 < S; c0 += C) {
     const int64_t c = std::min<int64_t>(C, S - c0);
     c128* fa = work;
     c128* fb = fa + c * (int64_t)(PF + 1) * D;
     c128* ba = fb + c * (int64_t)(PF + 1) * D;
-    c128* bb = ba + c * (int64_t)(PB + 1) * D;
-    c128* psiT = bb + c * (int64_t)(PB + 1) * D;
+    c128* bb = ba + c * (int64_t)(PBx + 1) * D;
+    c128* psiT = bb + c * (int64_t)(PBx + 1) * D;
     c128* G = psiT + c * D;
     double* ang = (double*)(G + pqc_v1_gpart_elems(prog, c));
     const double* a0 = d_angles + c0 * ld;
     {
-      const long long tot = c * P;
-      k_permute_cols<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a0, ld, c, P, prog->d_bi_cols, ang);
+      const long long tot = c * PA;
+      k_permute_cols<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a0, ld, c, PA, prog->d_bi_cols, ang);
       PQC_LAUNCH_CHECK();
     }
     c128 *ffin = nullptr, *bfin = nullptr;
-    // need_final: psi must reach the cut even if the last spawn is earlier
-    int rc = pqc_v1_derivatives(prog->bi_F, ang, P, c, d_init, 0, fa, fb, nullptr, false, true,
-                                &ffin, st);
+    // F stops after its last spawn when its tail was handed to M / B (bi_ntrail > 0); otherwise
+    // psi must reach the cut even if the last spawn is earlier
+    int rc = pqc_v1_derivatives(prog->bi_F, ang, PA, c, d_init, 0, fa, fb, nullptr, false,
+                                prog->bi_ntrail == 0, &ffin, st);
     if (rc) return rc;
     rc = pqc_v1_run(prog->bi_M, a0, ld, c, ffin, (int64_t)(PF + 1) * D, psiT, st);
     if (rc) return rc;
-    rc = pqc_v1_derivatives(prog->bi_B, ang + PF, P, c, psiT, D, ba, bb, nullptr, false, true,
+    rc = pqc_v1_derivatives(prog->bi_B, ang + PF, PA, c, psiT, D, ba, bb, nullptr, false, true,
                             &bfin, st);
     if (rc) return rc;
-    rc = pqc_v1_gram_qfim2(prog, ffin, PF + 1, PF + 1, bfin, PB + 1, prog->d_bi_inv, c, G,
+    rc = pqc_v1_gram_qfim2(prog, ffin, PF + 1, PF + 1, bfin, PBx + 1, prog->d_bi_inv, c, G,
                            d_qfim + c0 * (int64_t)P * P, st);
     if (rc) return rc;
     if (d_states_out)

@@ -176,6 +176,7 @@ struct V1Pass {
   int wt_off, nwt;         // linear-form tables of this pass (V1_WTAB words each) in `wtab`
   // in-pass diagonal spawns, in order of their K_GEN micro-ops
   std::vector<int> spawn_param;
+  std::vector<int> op_ids;       // program ops this pass executes
   bool direct_ok;
   int io_first, io_last;
 };
@@ -197,6 +198,7 @@ struct ParamSpawn {
 
 struct pqc_program {
   int n = 0, P = 0;
+  int n_nodiff = 0;              // the last n_nodiff parameters only supply angles (no derivative)
   std::vector<ParamSpawn> pspawn;
   std::vector<pqc_op> ops;
   int tile_bits = 12;
@@ -241,6 +243,10 @@ struct pqc_program {
   pqc_program* bi_M = nullptr;
   pqc_program* bi_B = nullptr;
   int bi_cut = -1, bi_PF = 0, bi_PB = 0;
+  // F stops after its last spawn; the ops of its pure-propagation tail (bi_ntrail of them) are
+  // run by M and undone at the end of B, whose bi_extra extra parameters are angle-only
+  // copies of the F parameters those ops use
+  int bi_ntrail = 0, bi_extra = 0;
   std::vector<int> bi_cols;                    // Gram column v (F params then B params) -> parameter
   std::vector<int> bi_inv;                     // parameter -> v | (sign bit: backward vector)
   long long bi_cost = 0, fwd_cost = 0;         // vector-passes of either plan
@@ -290,6 +296,7 @@ int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long lon
                        c128* d_gpart, bool want_dots, bool need_final, c128** final_buf,
                        cudaStream_t st);
 long long pqc_v1_plan_cost(const pqc_program* prog);   // vector-passes of the QFIM plan
+std::vector<int> pqc_v1_trailing_ops(const pqc_program* prog);
 int pqc_v1_n_passes(const pqc_program* prog, bool need_final);
 long long pqc_v1_gpart_elems(const pqc_program* prog, long long S);
 int pqc_v1_qfim_reduce(const pqc_program* prog, const c128* d_gpart, long long S, double* d_F,

@@ -43,6 +43,7 @@ struct COp {
   bool diag = false, pauli = false, two = false;
   uint32_t px = 0, pz = 0, px2 = 0, pz2 = 0;
   std::vector<std::pair<int, int>> pairs;   // ZZSUM
+  std::vector<int> ids;                     // indices of the program ops this op stands for
 };
 
 bool pauli_comm(uint32_t x1, uint32_t z1, uint32_t x2, uint32_t z2) {
@@ -62,8 +63,9 @@ bool commute(const COp& a, const COp& b) {
   return false;
 }
 
-COp make_cop(const pqc_op& op, int n) {
+COp make_cop(const pqc_op& op, int n, int idx) {
   COp c;
+  c.ids.push_back(idx);
   c.kind = op.kind;
   c.b0 = n - 1 - op.q0;
   c.b1 = op.q1 >= 0 ? n - 1 - op.q1 : -1;
@@ -121,9 +123,11 @@ void fuse_group(std::vector<COp>& run) {
     z.diag = true;
     z.mix = 0;
     z.support = 0;
+    z.ids.clear();
     for (size_t j : mem) {
       z.pairs.push_back({run[j].b0, run[j].b1});
       z.support |= run[j].support;
+      z.ids.insert(z.ids.end(), run[j].ids.begin(), run[j].ids.end());
       if (j != i) dead[j] = true;
     }
     run[i] = z;
@@ -138,6 +142,7 @@ void fuse_group(std::vector<COp>& run) {
       run[i].two = true;
       run[i].px2 = run[j].px;
       run[i].pz2 = run[j].pz;
+      run[i].ids.insert(run[i].ids.end(), run[j].ids.begin(), run[j].ids.end());
       dead[j] = true;
       break;
     }
@@ -179,6 +184,7 @@ struct Builder {
   std::vector<int> spawn_param;
   bool open = false;
   int nmops_cur = 0;
+  std::vector<int> cur_ids;                // program ops taken by the current pass
   int wt_begin = 0;                        // first linear-form table of the current pass
   int plan_slots = 0;                      // trig slots used by the finished passes of this plan
 
@@ -189,6 +195,7 @@ struct Builder {
     for (auto& g : grp) g.clear();
     for (int& g : grp_of) g = -1;
     sws.clear();
+    cur_ids.clear();
     tj.clear();
     ntrig = 0;
     spawn_param.clear();
@@ -318,6 +325,7 @@ struct Builder {
 
   void take(const COp& c) {
     MOp m = proto(c);
+    cur_ids.insert(cur_ids.end(), c.ids.begin(), c.ids.end());
     ++nmops_cur;
     if (!c.mix) {
       if (sws.empty() || !sws.back().post.empty()) sws.push_back(SW{-1, {}, {}, {}});
@@ -571,6 +579,7 @@ struct Builder {
       ps.fast_ok = ok;
     }
     ps.spawn_param = spawn_param;
+    ps.op_ids = cur_ids;
     passes.push_back(ps);
     open = false;
     return (int)passes.size() - 1;
@@ -593,12 +602,13 @@ int pqc_plan_v1(pqc_program* prog) {
       for (auto& c : run) cops.push_back(c);
       run.clear();
     };
-    for (const pqc_op& op : prog->ops) {
+    for (size_t oi = 0; oi < prog->ops.size(); ++oi) {
+      const pqc_op& op = prog->ops[oi];
       if (op.group != cur) {
         flush();
         cur = op.group;
       }
-      run.push_back(make_cop(op, n));
+      run.push_back(make_cop(op, n, (int)oi));
     }
     flush();
   }
@@ -655,6 +665,7 @@ int pqc_plan_v1(pqc_program* prog) {
   auto plan = [&](bool markers, std::vector<int>* run_out, std::vector<V1Stage>* stages) -> int {
     Builder B{prog, n, cap, ipc, mops, sweeps, tjobs, zz, prog->v1_passes};
     std::vector<bool> spawned(P, false);
+    for (int p = std::max(0, P - prog->n_nodiff); p < P; ++p) spawned[p] = true;   // angle only
     std::vector<int> pending_dots;
     const bool onload = (ipc == 1);
     auto emit_pass = [&]() {
@@ -2435,6 +2446,20 @@ static size_t last_spawn_stage(const pqc_program* prog) {
     if (sg.type == 1 || (sg.type == 0 && !prog->v1_passes[sg.pass].spawn_param.empty())) last = i + 1;
   }
   return last;
+}
+
+// program ops executed by the passes after the last spawn (pure propagation at the end of the
+// derivative plan), ascending
+std::vector<int> pqc_v1_trailing_ops(const pqc_program* prog) {
+  std::vector<int> ids;
+  for (size_t i = last_spawn_stage(prog); i < prog->v1_grad.size(); ++i) {
+    const V1Stage& sg = prog->v1_grad[i];
+    if (sg.type != 0) continue;
+    const V1Pass& ps = prog->v1_passes[sg.pass];
+    ids.insert(ids.end(), ps.op_ids.begin(), ps.op_ids.end());
+  }
+  std::sort(ids.begin(), ids.end());
+  return ids;
 }
 
 // vector-passes (tile loads + stores of one vector) the QFIM pipeline spends on this plan
