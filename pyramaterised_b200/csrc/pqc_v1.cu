@@ -1835,7 +1835,10 @@ __global__ void __launch_bounds__(256, 2) k_tile_gather(const GatherArgs A) {
 // One CTA per (sample, 4096-amplitude chunk); thread tid owns elements tid + 256 r, r < 16,
 // r < 16.  Single-bit masks inside the chunk read it from shared memory with immediate offsets
 // (one LDS + two adds per amplitude), masks that leave the chunk read psi through L2.
-__global__ void __launch_bounds__(256, 2) k_xsum_gather(const GatherArgs A) {
+#define XS_TB 8                   // thread bits: 256 threads x 16 outputs (512 x 8 measured 12 % slower)
+#define XS_NT (1 << XS_TB)
+#define XS_R (4096 / XS_NT)
+__global__ void __launch_bounds__(XS_NT, 2) k_xsum_gather(const GatherArgs A) {
   extern __shared__ __align__(16) c128 xs_sm[];
   __shared__ uint32_t s_xm[64];
   const int tid = threadIdx.x;
@@ -1844,64 +1847,64 @@ __global__ void __launch_bounds__(256, 2) k_xsum_gather(const GatherArgs A) {
   const uint32_t c0 = (uint32_t)(blockIdx.x & ((1ll << chunks_log2) - 1)) << 12;
   const c128* psi = A.buf + ((s * A.slots_total) << A.n);
   {
-    c128 own[16];
+    c128 own[XS_R];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) own[r] = psi[c0 + tid + 256 * r];
+    for (int r = 0; r < XS_R; ++r) own[r] = psi[c0 + tid + XS_NT * r];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) xs_sm[tid + 256 * r] = own[r];
+    for (int r = 0; r < XS_R; ++r) xs_sm[tid + XS_NT * r] = own[r];
   }
   for (int p = 0; p < A.nparams; ++p) {
     const GenTerm* terms = A.gens + A.goff[p];
     const int nt = A.gcnt[p];
     __syncthreads();
-    for (int t = tid; t < nt && t < 64; t += 256) s_xm[t] = terms[t].xmask;
+    for (int t = tid; t < nt && t < 64; t += XS_NT) s_xm[t] = terms[t].xmask;
     __syncthreads();
-    double are[16], aim[16];
+    double are[XS_R], aim[XS_R];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) are[r] = aim[r] = 0.0;
+    for (int r = 0; r < XS_R; ++r) are[r] = aim[r] = 0.0;
     for (int t = 0; t < nt; ++t) {
       const uint32_t xm = t < 64 ? s_xm[t] : terms[t].xmask;
-      const uint32_t lo = xm & 255u, hx = (xm >> 8) & 15u, far = xm >> 12;
+      const uint32_t lo = xm & (XS_NT - 1u), hx = (xm >> XS_TB) & (XS_R - 1u), far = xm >> 12;
       if (far == 0 && lo == 0 && (hx & (hx - 1)) == 0) {
-        // one of the thread's own register bits
+        // one of the thread's own register bits: immediate offsets
 #define XS_OWN(K)                                                              \
-  _Pragma("unroll") for (int r = 0; r < 16; ++r) {                             \
-    const c128 v = xs_sm[tid + 256 * (r ^ (1 << K))];                          \
+  _Pragma("unroll") for (int r = 0; r < XS_R; ++r) {                           \
+    const c128 v = xs_sm[tid + XS_NT * (r ^ (1 << K))];                        \
     are[r] += v.x;                                                             \
     aim[r] += v.y;                                                             \
   }
-        if (hx == 1) { XS_OWN(0) } else if (hx == 2) { XS_OWN(1) }
-        else if (hx == 4) { XS_OWN(2) } else { XS_OWN(3) }
+        if (hx == 1) { XS_OWN(0) } else if (hx == 2) { XS_OWN(1) } else if (hx == 4) { XS_OWN(2) }
+        else { XS_OWN(XS_R == 16 ? 3 : 2) }
 #undef XS_OWN
       } else if (far == 0 && hx == 0) {
         const c128* b = xs_sm + (tid ^ lo);
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const c128 v = b[256 * r];
+        for (int r = 0; r < XS_R; ++r) {
+          const c128 v = b[XS_NT * r];
           are[r] += v.x;
           aim[r] += v.y;
         }
       } else if (far == 0) {
         const uint32_t b = (uint32_t)tid ^ lo;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const c128 v = xs_sm[b + 256u * ((uint32_t)r ^ hx)];
+        for (int r = 0; r < XS_R; ++r) {
+          const c128 v = xs_sm[b + XS_NT * ((uint32_t)r ^ hx)];
           are[r] += v.x;
           aim[r] += v.y;
         }
       } else if ((xm & 0xfffu) == 0) {
         const c128* b = psi + ((c0 ^ xm) + tid);
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const c128 v = b[256 * r];
+        for (int r = 0; r < XS_R; ++r) {
+          const c128 v = b[XS_NT * r];
           are[r] += v.x;
           aim[r] += v.y;
         }
       } else {
         const uint32_t xb = (c0 + tid) ^ xm;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const c128 v = psi[xb ^ (256u * r)];
+        for (int r = 0; r < XS_R; ++r) {
+          const c128 v = psi[xb ^ ((uint32_t)XS_NT * r)];
           are[r] += v.x;
           aim[r] += v.y;
         }
@@ -1910,8 +1913,8 @@ __global__ void __launch_bounds__(256, 2) k_xsum_gather(const GatherArgs A) {
     const double cr = terms[0].re, ci = terms[0].im;
     c128* out = A.buf + ((s * A.slots_total + A.slot[p]) << A.n) + c0 + tid;
 #pragma unroll
-    for (int r = 0; r < 16; ++r)
-      out[256 * r] = make_double2(are[r] * cr - aim[r] * ci, are[r] * ci + aim[r] * cr);
+    for (int r = 0; r < XS_R; ++r)
+      out[XS_NT * r] = make_double2(are[r] * cr - aim[r] * ci, are[r] * ci + aim[r] * cr);
   }
 }
 
@@ -1975,12 +1978,13 @@ __global__ void k_qfim_reduce(const c128* __restrict__ gpart, long long S, int P
 // time (overlaps are invariant under the later unitary gates).
 // One CTA per (parameter set, K slice of 1024 amplitudes); warp (kw, grp) owns the k4-steps
 // kw, kw + ksh, .. of every 64-amplitude stage for the upper-triangular 8x8 tiles
-// [grp*16, grp*16+16); stages arrive through cp.async double buffers; the K shares and the K
-// slices are added in a fixed order (bitwise reproducible).
+// [grp*16, grp*16+16).  Stages arrive by TMA: one cp.async.bulk of 1 KB per vector row,
+// completion counted on an mbarrier per ring slot, so no thread spends issue slots on the
+// copies; the K shares and the K slices are added in a fixed order (bitwise reproducible).
 // Rows 0..PF-1 are slots 1.. of `buf` (slot 0 = psi), rows PF.. are slots 1.. of `buf2`.
 // =====================================================================================
-#define GR_K 32                   // amplitudes per stage: 512 B contiguous per vector row
-#define GR_NS 4                   // cp.async ring depth (3 stages in flight while one is used)
+#define GR_K 64                   // amplitudes per stage: 1 KB contiguous per vector row
+#define GR_NS_MAX 4               // TMA ring depth (ns - 1 stages in flight while one is used)
 #define GR_ROW (GR_K + 2)         // padded complex per smem row: the 8 rows of a fragment load
                                   // (8 B per lane) fall into distinct banks
 #define GR_TPW 16                 // 8x8 output tiles per warp (one "tile group")
@@ -2000,16 +2004,53 @@ static int gram_ksplit(int n) {
 
 // SMALL: P <= 32 (at most 4 row blocks, 10 tiles, one tile group of 8 K-share warps): the 4
 // row-block fragments of a k4-step are loaded once and feed all tiles from registers.
+__device__ __forceinline__ void gr_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void gr_mbar_expect(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gr_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void gr_mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "GR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra GR_DONE;\n"
+      "bra GR_WAIT;\n"
+      "GR_DONE:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void gr_bulk_load(void* dst, const void* src, unsigned bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes),
+      "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// SMALL: P <= 32 (at most 4 row blocks, 10 tiles, one tile group of 8 K-share warps): the 4
+// row-block fragments of a k4-step are loaded once and feed all tiles from registers.
 template <int NTMAX, int MINB, bool SMALL>
-__global__ void __launch_bounds__(NTMAX, MINB) k_gram_real(const c128* __restrict__ buf, int n,
+__global__ void __launch_bounds__(NTMAX + 32, MINB) k_gram_real(const c128* __restrict__ buf, int n,
                                                            int slots_total, int PF,
                                                            const c128* __restrict__ buf2, int slots2,
                                                            int P, int P8, int ksplit, int ksh,
-                                                           double* __restrict__ gpart) {
+                                                           int ns, double* __restrict__ gpart) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int NT = blockDim.x, nw = NT >> 5;
-  c128* sm = reinterpret_cast<c128*>(smraw);                       // [GR_NS][P8 + 1][GR_ROW]
+  __shared__ __align__(8) uint64_t full[GR_NS_MAX], empty[GR_NS_MAX];
+  // the last warp is the TMA producer; the others are consumers
+  const int NT = blockDim.x - 32, nw = NT >> 5;
+  c128* sm = reinterpret_cast<c128*>(smraw);                       // [ns][P8 + 1][GR_ROW]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const bool producer = warp == nw;
   const int kw = warp % ksh, grp = warp / ksh;
   const long long s = blockIdx.x / ksplit;
   const int ks = blockIdx.x % ksplit;
@@ -2032,82 +2073,94 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_gram_real(const c128* __restric
           if (q < 8) tij_lo |= v; else tij_hi |= v;
         }
   }
-  for (int e = tid; e < GR_NS * rows * GR_ROW; e += NT) sm[e] = make_double2(0.0, 0.0);   // pad rows
-  __syncthreads();
-  auto stage_load = [&](int it) {
-    if (it < nk) {
-      const int b = it % GR_NS;
-      const long long k0 = kbeg + (long long)it * GR_K;
-      for (int e = tid; e < (P + 1) * GR_K; e += NT) {
-        const int r = e / GR_K, kk = e % GR_K;
-        const c128* src = r == P ? V : (r < PF ? V + ((long long)(r + 1) << n)
-                                               : V2 + ((long long)r << n));
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(
-            sm + (b * rows + (r == P ? P8 : r)) * GR_ROW + kk);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + k0 + kk));
-      }
+  // pad rows P..P8-1 of every ring slot stay zero (TMA only writes rows < P and the psi row)
+  for (int e = tid; e < ns * (P8 - P) * GR_ROW; e += blockDim.x) {
+    const int b = e / ((P8 - P) * GR_ROW), rem = e - b * (P8 - P) * GR_ROW;
+    sm[(b * rows + P) * GR_ROW + rem] = make_double2(0.0, 0.0);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < ns; ++i) {
+      gr_mbar_init(&full[i], 1);
+      gr_mbar_init(&empty[i], nw);
     }
-    asm volatile("cp.async.commit_group;");    // (possibly empty: keeps the group count uniform)
-  };
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   double acc[GR_TPW][2];
 #pragma unroll
   for (int q = 0; q < GR_TPW; ++q) acc[q][0] = acc[q][1] = 0.0;
   double sre[GR_PSIROWS], sim[GR_PSIROWS];
 #pragma unroll
   for (int m = 0; m < GR_PSIROWS; ++m) sre[m] = sim[m] = 0.0;
+  if (producer) {
+    // runs ahead of the consumers by up to ns stages; lane l copies the rows l, l + 32, ..
+    for (int it = 0; it < nk; ++it) {
+      const int b = it % ns;
+      if (it >= ns) gr_mbar_wait(&empty[b], (unsigned)(((it / ns) - 1) & 1));
+      const long long k0 = kbeg + (long long)it * GR_K;
+      if (lane == 0) gr_mbar_expect(&full[b], (unsigned)((P + 1) * GR_K * sizeof(c128)));
+      __syncwarp();
+      for (int r = lane; r <= P; r += 32) {
+        const c128* src = r == P ? V : (r < PF ? V + ((long long)(r + 1) << n)
+                                               : V2 + ((long long)r << n));
+        gr_bulk_load(sm + (b * rows + (r == P ? P8 : r)) * GR_ROW, src + k0,
+                     (unsigned)(GR_K * sizeof(c128)), &full[b]);
+      }
+    }
+  } else {
+    for (int it = 0; it < nk; ++it) {
+      const int b = it % ns;
+      gr_mbar_wait(&full[b], (unsigned)((it / ns) & 1));
+      // real Gram: k4-step kk covers the 4 doubles (2 amplitudes) 4 kk .. 4 kk + 3 of every row
+      for (int kk = kw; kk < GR_K / 2; kk += ksh) {
+        const double* a_s = reinterpret_cast<const double*>(sm + (b * rows + g) * GR_ROW) + 4 * kk + t4;
+        if (SMALL) {
+          double f[4];
 #pragma unroll
-  for (int i = 0; i < GR_NS - 1; ++i) stage_load(i);
-  for (int it = 0; it < nk; ++it) {
-    const int b = it % GR_NS;
-    asm volatile("cp.async.wait_group %0;" ::"n"(GR_NS - 2));
-    __syncthreads();                 // stage `it` visible; everyone is done with stage it - 1
-    stage_load(it + GR_NS - 1);      // refill the buffer stage it - 1 used
-    // real Gram: k4-step kk covers the 4 doubles (2 amplitudes) 4 kk .. 4 kk + 3 of every row
-    for (int kk = kw; kk < GR_K / 2; kk += ksh) {
-      const double* a_s = reinterpret_cast<const double*>(sm + (b * rows + g) * GR_ROW) + 4 * kk + t4;
-      if (SMALL) {
-        double f[4];
+          for (int i = 0; i < 4; ++i) f[i] = i < T ? a_s[i * (8 * GR_ROW * 2)] : 0.0;
+          int q = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) f[i] = i < T ? a_s[i * (8 * GR_ROW * 2)] : 0.0;
-        int q = 0;
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int j = i; j < 4; ++j, ++q)
+              if (j < T) gr_dmma(acc[q][0], acc[q][1], f[i], f[j]);     // warp-uniform
+        } else {
 #pragma unroll
-          for (int j = i; j < 4; ++j, ++q)
-            if (j < T) gr_dmma(acc[q][0], acc[q][1], f[i], f[j]);     // warp-uniform
-      } else {
-#pragma unroll
-        for (int q = 0; q < GR_TPW; ++q) {
-          if (t_begin + q < t_end) {          // warp-uniform
-            const unsigned ij = (unsigned)(((q < 8 ? tij_lo : tij_hi) >> (8 * (q & 7))) & 0xff);
-            const double fa = a_s[(ij & 15u) * (8 * GR_ROW * 2)];
-            const double fb = a_s[(ij >> 4) * (8 * GR_ROW * 2)];
-            gr_dmma(acc[q][0], acc[q][1], fa, fb);
+          for (int q = 0; q < GR_TPW; ++q) {
+            if (t_begin + q < t_end) {          // warp-uniform
+              const unsigned ij = (unsigned)(((q < 8 ? tij_lo : tij_hi) >> (8 * (q & 7))) & 0xff);
+              const double fa = a_s[(ij & 15u) * (8 * GR_ROW * 2)];
+              const double fb = a_s[(ij >> 4) * (8 * GR_ROW * 2)];
+              gr_dmma(acc[q][0], acc[q][1], fa, fb);
+            }
           }
         }
       }
-    }
-    // <psi|d_p> for the rows p = warp, warp + nw, ..: one amplitude of the stage per lane
-    {
-      const c128 y = sm[(b * rows + P8) * GR_ROW + lane];
+      // <psi|d_p> for the rows p = warp, warp + nw, ..: two amplitudes of the stage per lane
+      {
+        const c128* ps = sm + (b * rows + P8) * GR_ROW;
+        const c128 y0 = ps[lane], y1 = ps[lane + 32];
 #pragma unroll
-      for (int m = 0; m < GR_PSIROWS; ++m) {
-        const int p = warp + nw * m;
-        if ((!SMALL || m < 4) && p < P) {
-          const c128 x = sm[(b * rows + p) * GR_ROW + lane];
-          sre[m] += y.x * x.x + y.y * x.y;
-          sim[m] += y.x * x.y - y.y * x.x;
+        for (int m = 0; m < GR_PSIROWS; ++m) {
+          const int p = warp + nw * m;
+          if ((!SMALL || m < 4) && p < P) {
+            const c128* d = sm + (b * rows + p) * GR_ROW;
+            const c128 x0 = d[lane], x1 = d[lane + 32];
+            sre[m] += y0.x * x0.x + y0.y * x0.y + y1.x * x1.x + y1.y * x1.y;
+            sim[m] += y0.x * x0.y - y0.y * x0.x + y1.x * x1.y - y1.y * x1.x;
+          }
         }
       }
+      __syncwarp();
+      if (lane == 0) gr_mbar_arrive(&empty[b]);   // this warp is done with the slot
     }
   }
-  asm volatile("cp.async.wait_group 0;");
   __syncthreads();
   // add the K shares of every tile group in a fixed order through the (now idle) stage
   // buffers: scratch [grp][q][2][32] doubles
   double* scr = reinterpret_cast<double*>(sm);
   for (int r = 1; r < ksh; ++r) {
-    if (kw == r) {
+    if (!producer && kw == r) {
       double* o = scr + (size_t)grp * GR_TPW * 2 * 32 + lane;
 #pragma unroll
       for (int q = 0; q < GR_TPW; ++q) {
@@ -2116,7 +2169,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_gram_real(const c128* __restric
       }
     }
     __syncthreads();
-    if (kw == 0) {
+    if (!producer && kw == 0) {
       const double* o = scr + (size_t)grp * GR_TPW * 2 * 32 + lane;
 #pragma unroll
       for (int q = 0; q < GR_TPW; ++q) {
@@ -2127,7 +2180,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_gram_real(const c128* __restric
     __syncthreads();
   }
   double* out = gpart + (s * ksplit + ks) * ((long long)P * P + 2 * P);
-  if (kw == 0) {
+  if (!producer && kw == 0) {
     if (SMALL) {
       int q = 0;
 #pragma unroll
@@ -2156,7 +2209,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_gram_real(const c128* __restric
 #pragma unroll
   for (int m = 0; m < GR_PSIROWS; ++m) {
     const int p = warp + nw * m;
-    if ((!SMALL || m < 4) && p < P) {          // warp-uniform
+    if (!producer && (!SMALL || m < 4) && p < P) {          // warp-uniform
       const double re = warp_sum(sre[m]), im = warp_sum(sim[m]);
       if (lane == 0) {
         out[(long long)P * P + p] = re;
@@ -2222,12 +2275,14 @@ int pqc_v1_gram_qfim2(const pqc_program* prog, const c128* buf, int slots1, int 
   const int ksh = ngrp == 1 ? 8 : 4;            // K shares: at least 8 warps per CTA
   const int nthreads = 32 * ksh * ngrp;
   const int ksplit = gram_ksplit(prog->n);
-  const size_t smem = std::max((size_t)GR_NS * (P8 + 1) * GR_ROW * sizeof(c128),
-                               (size_t)ngrp * GR_TPW * 2 * 32 * sizeof(double));
+  const size_t stage = (size_t)(P8 + 1) * GR_ROW * sizeof(c128);
+  // ring depth: P <= 32 runs 2 CTAs per SM with 3 slots each, larger P one CTA with 2-4 slots
+  const int ns = T <= 4 ? 3 : (int)std::max<size_t>(2, std::min<size_t>(GR_NS_MAX, (200 * 1024) / stage));
+  const size_t smem = std::max((size_t)ns * stage, (size_t)ngrp * GR_TPW * 2 * 32 * sizeof(double));
   static bool attr_set = false;
   if (!attr_set) {
     PQC_CUDA(cudaFuncSetAttribute(k_gram_real<256, 2, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     PQC_CUDA(cudaFuncSetAttribute(k_gram_real<384, 1, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
@@ -2235,11 +2290,11 @@ int pqc_v1_gram_qfim2(const pqc_program* prog, const c128* buf, int slots1, int 
   if (S * ksplit > 0x7fffffffLL) PQC_FAIL(-1, "gram grid too large");
   double* gp = reinterpret_cast<double*>(d_gpart);
   if (T <= 4)
-    k_gram_real<256, 2, true><<<(unsigned)(S * ksplit), nthreads, smem, st>>>(
-        buf, prog->n, slots1, PF, buf2, slots2, P, P8, ksplit, ksh, gp);
+    k_gram_real<256, 2, true><<<(unsigned)(S * ksplit), nthreads + 32, smem, st>>>(
+        buf, prog->n, slots1, PF, buf2, slots2, P, P8, ksplit, ksh, ns, gp);
   else
-    k_gram_real<384, 1, false><<<(unsigned)(S * ksplit), nthreads, smem, st>>>(
-        buf, prog->n, slots1, PF, buf2, slots2, P, P8, ksplit, ksh, gp);
+    k_gram_real<384, 1, false><<<(unsigned)(S * ksplit), nthreads + 32, smem, st>>>(
+        buf, prog->n, slots1, PF, buf2, slots2, P, P8, ksplit, ksh, ns, gp);
   PQC_LAUNCH_CHECK();
   const long long tot = S * P * P;
   k_qfim_from_gram<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(gp, S, P, ksplit, d_inv, d_F);
@@ -2602,7 +2657,7 @@ int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long lon
                                           80 * 1024));
             xs_attr = true;
           }
-          k_xsum_gather<<<(unsigned)grid, 256, 4096 * sizeof(c128), st>>>(g);
+          k_xsum_gather<<<(unsigned)grid, XS_NT, 4096 * sizeof(c128), st>>>(g);
         } else {
           k_tile_gather<<<(unsigned)grid, 256, ((size_t)1 << g.cb) * sizeof(c128), st>>>(g);
         }
