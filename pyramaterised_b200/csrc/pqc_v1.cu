@@ -1869,12 +1869,12 @@ __global__ void __launch_bounds__(XS_NT, 2) k_xsum_gather(const GatherArgs A) {
         // one of the thread's own register bits: immediate offsets
 #define XS_OWN(K)                                                              \
   _Pragma("unroll") for (int r = 0; r < XS_R; ++r) {                           \
-    const c128 v = xs_sm[tid + XS_NT * (r ^ (1 << K))];                        \
+    const c128 v = xs_sm[tid + XS_NT * (r ^ (1 << (K)))];                      \
     are[r] += v.x;                                                             \
     aim[r] += v.y;                                                             \
   }
         if (hx == 1) { XS_OWN(0) } else if (hx == 2) { XS_OWN(1) } else if (hx == 4) { XS_OWN(2) }
-        else { XS_OWN(XS_R == 16 ? 3 : 2) }
+        else { XS_OWN((XS_R == 16 ? 3 : 2)) }
 #undef XS_OWN
       } else if (far == 0 && hx == 0) {
         const c128* b = xs_sm + (tid ^ lo);
