@@ -75,7 +75,7 @@ def cpu_qfim_eqd(specs, n, ang_row, init, pool=None):
     res = pool.map(_cpu_one_derivative, jobs) if pool is not None else \
         [_cpu_one_derivative(j) for j in jobs]
     F = orc.qfi(res[0], np.stack(res[1:]))
-    return orc.eqd(F, CUTOFF)
+    return orc.eqd(F, CUTOFF), F
 
 
 def cpu_baseline(a):
@@ -84,9 +84,9 @@ def cpu_baseline(a):
     specs, init = orc.generate_circuit(a.circuit, a.qubits, a.layers)
     ang = angles_for(a, orc.n_params(specs), 0)
     t0 = time.perf_counter()
-    cpu_qfim_eqd(specs, a.qubits, ang[0], init)
+    _, F = cpu_qfim_eqd(specs, a.qubits, ang[0], init)
     dt = time.perf_counter() - t0
-    return {"value": 1.0 / dt, "unit": "samples/s", "cores": 1, "kind": "port",
+    return {"value": 1.0 / dt, "_qfim_row0": F, "unit": "samples/s", "cores": 1, "kind": "port",
             "sample": f"1 of the {a.samples} parameter sets (row 0), full {a.qubits}q x "
                       f"{a.layers} layers, literal {orc.n_params(specs)} re-simulations + QFIM "
                       f"+ eigh; {dt:.1f} s of numpy on one core; QuTiP itself is not "
@@ -327,6 +327,14 @@ def run_b200(a):
     ra["frac_by_layers"] = ra["by_template_layers_GBps"] / peak
     ra["frac_pass_kernel"] = ra["pass_kernel_GBps"] / peak
     if cpu is not None:
+        # the oracle's QFIM of row 0 (computed for the CPU baseline anyway) checks the GPU path
+        F0 = qc.qfim_batch(ang_dev[:1])[0].cpu().numpy()
+        R0 = cpu.pop("_qfim_row0")
+        err = float(np.abs(F0 - R0).max() / np.abs(R0).max())
+        line["parity_check"] = {"what": "QFIM of parameter set 0 vs the numpy oracle, max abs "
+                                        "error / max |F|", "value": err, "tolerance": 1e-8}
+        if not err < 1e-8:
+            raise SystemExit(f"bench: GPU QFIM differs from the oracle (rel {err:.3e})")
         line["cpu_baseline"] = cpu
     if rank == 0:
         print(json.dumps(line))

@@ -1,6 +1,8 @@
 """GPU parity: the CUDA engine (through the reference-facing API and the C ABI) against
 the reference-generated goldens and the numpy oracle.  Tolerances are BASELINE.json's:
 amplitudes / fidelities 1e-10 absolute, QFIM / magic 1e-8 relative, KL 1e-6."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -517,3 +519,21 @@ def test_example_script_flow():
     out_magic = cap.train(method="BFGS", angles=ang)
     assert out_magic[2][-1] >= out[2][-1] - 1e-6           # optimising for magic finds more magic
     assert "4 qubit, 3 layer deep PQC" in repr(ex)
+
+
+@pytest.mark.gpu
+def test_nccl_sample_sharding_matches_single_gpu():
+    """dist.py over NCCL on 2 GPUs (skipped on a 1-GPU box; the gloo tests cover the logic)."""
+    import json
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                        "29517", os.path.join(root, "tools", "dist_nccl_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["ok"]
