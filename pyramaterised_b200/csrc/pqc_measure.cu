@@ -746,6 +746,104 @@ __global__ void __launch_bounds__(256) k_magic(const MagicArgs a) {
   }
 }
 
+// n = 12 (BASELINE config 4): register-blocked FWHT.  256 threads x 16 points; the three
+// sweeps hold index bits 8-11, 0-3 and 4-7 in registers (four butterfly stages each, no memory
+// traffic) with two shared-memory transposes in between instead of twelve in-memory stages.
+// The thread's own amplitudes c_j stay in registers for all masks; only the partners c_{j^k}
+// are read from the shared-memory copy of the state.  The transpose buffer is XOR-swizzled,
+// sigma(i) = i ^ ((i >> 4) & 15), which makes all three access patterns conflict free for
+// 8-byte elements.
+template <int K>
+__device__ __forceinline__ void mg_bfly(double (&v)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j & (1 << K)) continue;
+    const double x = v[j], y = v[j | (1 << K)];
+    v[j] = x + y;
+    v[j | (1 << K)] = x - y;
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) k_magic12(const MagicArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  c128* sc = reinterpret_cast<c128*>(smraw);            // [4096] the state
+  double* u = reinterpret_cast<double*>(sc + 4096);     // [4096] transpose buffer (swizzled)
+  __shared__ double red[32];
+  const uint32_t D = 4096u;
+  const uint32_t tid = threadIdx.x, lo = tid & 15u, hi = tid >> 4;
+  const int slices = (int)((D + a.masks_per_cta - 1) / a.masks_per_cta);
+  const long long s = blockIdx.x / slices;
+  const int slice = blockIdx.x % slices;
+  const c128* psi = a.states + s * (long long)D;
+  c128 own[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) own[j] = psi[tid | ((uint32_t)j << 8)];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) sc[tid | ((uint32_t)j << 8)] = own[j];
+  __syncthreads();
+  double acc[MAGIC_MAX_ALPHA];
+#pragma unroll
+  for (int q = 0; q < MAGIC_MAX_ALPHA; ++q) acc[q] = 0.0;
+  // swizzled transpose-buffer index of register j in the three sweeps
+  const uint32_t ia = tid ^ hi;                 // | j << 8          (index bits 8-11 in registers)
+  const uint32_t ib = tid << 4;                 // | (j ^ lo)        (bits 0-3)
+  const uint32_t ic = hi << 8;                  // | j << 4 | lo ^ j (bits 4-7)
+  const uint32_t k_begin = (uint32_t)slice * a.masks_per_cta;
+  const uint32_t k_end = min(D, k_begin + (uint32_t)a.masks_per_cta);
+  for (uint32_t k = k_begin; k < k_end; ++k) {
+    const uint32_t pl = tid ^ (k & 255u), kh = k >> 8;
+    double v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const c128 y = sc[pl | (((uint32_t)j ^ kh) << 8)];
+      const double xr = own[j].x, xi = own[j].y;
+      // v = conj(c_j) c_{j^k};  u = Re v + Im v
+      v[j] = (xr * y.x + xi * y.y) + (xr * y.y - xi * y.x);
+    }
+    mg_bfly<0>(v); mg_bfly<1>(v); mg_bfly<2>(v); mg_bfly<3>(v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) u[ia | ((uint32_t)j << 8)] = v[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = u[ib | ((uint32_t)j ^ lo)];
+    mg_bfly<0>(v); mg_bfly<1>(v); mg_bfly<2>(v); mg_bfly<3>(v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) u[ib | ((uint32_t)j ^ lo)] = v[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = u[ic | ((uint32_t)j << 4) | (lo ^ (uint32_t)j)];
+    __syncthreads();                 // the buffer is free for the next mask
+    mg_bfly<0>(v); mg_bfly<1>(v); mg_bfly<2>(v); mg_bfly<3>(v);
+#pragma unroll
+    for (int q = 0; q < MAGIC_MAX_ALPHA; ++q) {
+      if (q < a.n_alpha) {
+        const double al = a.alpha[q];
+        double t = 0.0;
+        if (al == 2.0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { const double w2 = v[j] * v[j]; t = fma(w2, w2, t); }
+        } else if (al == 0.5) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t += fabs(v[j]);
+        } else if (al == 1.0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t = fma(v[j], v[j], t);
+        } else {
+          for (int j = 0; j < 16; ++j) {
+            const double w = fabs(v[j]);
+            t += (w == 0.0) ? 0.0 : pow(w, 2.0 * al);
+          }
+        }
+        acc[q] += t;
+      }
+    }
+  }
+  for (int q = 0; q < a.n_alpha; ++q) {
+    const double t = block_sum<256>(acc[q], red);
+    if (threadIdx.x == 0) atomicAdd(a.sums + (long long)q * a.S + s, t);
+  }
+}
+
 __global__ void k_magic_finalize(double* __restrict__ out, long long S, int n, int n_alpha,
                                  MagicArgs a) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -778,12 +876,29 @@ extern "C" int pqc_magic_batch(const pqc_c128* d_states, int64_t S, int n, int n
   long long slices = std::max<long long>(1, std::min<long long>(D, (148 * 4 + S - 1) / S));
   a.masks_per_cta = (int)((D + slices - 1) / slices);
   slices = (D + a.masks_per_cta - 1) / a.masks_per_cta;
-  const size_t smem = 3 * D * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     PQC_CUDA(cudaFuncSetAttribute(k_magic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PQC_CUDA(cudaFuncSetAttribute(k_magic12, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
   }
+  const char* mg = getenv("PQC_MAGIC");       // PQC_MAGIC=generic: in-memory FWHT for every n
+  const bool generic_only = mg && strcmp(mg, "generic") == 0;   // (read per call: tests compare)
+  if (n == 12 && !generic_only) {
+    // register-blocked kernel, 2 CTAs per SM: cut every sample's masks into enough slices for
+    // >= 8 waves so the tail of the last wave stays small
+    slices = std::max<long long>(1, std::min<long long>(64, (148 * 2 * 8 + S - 1) / S));
+    a.masks_per_cta = (int)((D + slices - 1) / slices);
+    slices = (D + a.masks_per_cta - 1) / a.masks_per_cta;
+    if (S * slices > 0x7fffffffLL) PQC_FAIL(-1, "magic grid too large; split the batch");
+    PQC_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * S * n_alpha, st));
+    k_magic12<<<(unsigned)(S * slices), 256, D * (sizeof(c128) + sizeof(double)), st>>>(a);
+    PQC_LAUNCH_CHECK();
+    k_magic_finalize<<<(unsigned)((S * n_alpha + 127) / 128), 128, 0, st>>>(d_out, S, n, n_alpha, a);
+    PQC_LAUNCH_CHECK();
+    return 0;
+  }
+  const size_t smem = 3 * D * sizeof(double);
   if (S * slices > 0x7fffffffLL) PQC_FAIL(-1, "magic grid too large; split the batch");
   PQC_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * S * n_alpha, st));
   k_magic<<<(unsigned)(S * slices), 256, smem, st>>>(a);

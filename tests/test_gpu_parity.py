@@ -230,6 +230,30 @@ def test_magic_12q_config4(golden):
         assert abs(mg[1, s] - orc.renyi_fwht(ref[s], 0.5)) < RTOL * 10
 
 
+def test_magic_register_blocked_kernel_matches_generic_and_oracle(monkeypatch):
+    """n = 12 runs the register-blocked FWHT kernel (k_magic12); PQC_MAGIC=generic forces the
+    in-memory FWHT used for every other n.  Both against the oracle's FWHT formulation of
+    measure.py:318-349 on random and on structured states, several alphas, ragged mask slices."""
+    rng = np.random.default_rng(12)
+    st = rng.normal(size=(5, 4096)) + 1j * rng.normal(size=(5, 4096))
+    st /= np.linalg.norm(st, axis=1, keepdims=True)
+    st[3] = 0
+    st[3, 77] = 1.0                                   # basis state: stabilizer, magic 0
+    st[4] = 1 / 64.0                                  # |+>^12: stabilizer, magic 0
+    dev = torch.as_tensor(st, device="cuda")
+    alphas = (2.0, 0.5, 3.0)
+    got = engine.magic(dev, alphas).cpu().numpy()
+    monkeypatch.setenv("PQC_MAGIC", "generic")
+    gen = engine.magic(dev, alphas).cpu().numpy()
+    monkeypatch.delenv("PQC_MAGIC")
+    assert np.abs(got - gen).max() < 1e-10
+    for q, s in ((0, 0), (1, 1), (2, 2), (0, 3), (1, 4)):
+        assert abs(got[q, s] - orc.renyi_fwht(st[s], alphas[q])) < 1e-9
+    assert np.abs(got[:, 3:]).max() < 1e-10
+    big = engine.magic(dev[:1].repeat(700, 1), (2.0,)).cpu().numpy()   # many CTAs per sample
+    assert np.abs(big - got[0, 0]).max() < 1e-10
+
+
 @pytest.mark.parametrize("kind,n,p", [("generic_HE", 13, 2), ("NPQC", 14, 3), ("TFIM", 16, 2),
                                       ("XXZ", 16, 1), ("qg_circuit", 15, 1), ("Circuit_2", 17, 1)])
 def test_multi_pass_states_vs_oracle(kind, n, p):
