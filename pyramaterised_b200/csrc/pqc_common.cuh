@@ -162,9 +162,25 @@ struct FastPlan {
   uint32_t wo[FAST_MAX_WT][PQC_MAX_QUBITS - 12];
 };
 
+// "Layer sequence" path (k_layer_seq): the same idea for passes that visit the aligned nibbles
+// in ANY order and up to SEQ_MAX_SWEEPS times (the XXZ template's XY bonds alternate between
+// nibbles), and whose ops may also be XY pair rotations (PQC_K_RXY) on two register bits.
+#define SEQ_MAX_SWEEPS 6
+#define SEQ_MAX_OPS 6
+struct SeqPlan {
+  int nsw;
+  int geom[SEQ_MAX_SWEEPS];          // registers hold tile positions 0: 8-11, 1: 0-3, 2: 4-7
+  int nops[SEQ_MAX_SWEEPS];
+  FastOp ops[SEQ_MAX_SWEEPS][SEQ_MAX_OPS];   // RXY: subk = ka * 4 + kb (ka < kb), t[0] = trig slot
+  uint32_t wn[FAST_MAX_WT][3][16];
+  uint32_t wo[FAST_MAX_WT][PQC_MAX_QUBITS - 12];
+};
+
 struct V1Pass {
   bool fast_ok = false;
   FastPlan fast;
+  bool seq_ok = false;
+  SeqPlan seq;
 
   int tb, low_run;
   int lbit[V1_LOCAL_BITS];

@@ -578,6 +578,71 @@ struct Builder {
       }
       ps.fast_ok = ok;
     }
+    // ---- layer-sequence path eligibility (any order of aligned nibble sweeps, XY pair ops) --
+    ps.seq_ok = false;
+    memset(&ps.seq, 0, sizeof(ps.seq));
+    if (!ps.fast_ok && cap == V1_LOCAL_BITS && V1_LOCAL_BITS == 12 && n >= V1_LOCAL_BITS &&
+        ps.nsweeps >= 2 && ps.nsweeps <= SEQ_MAX_SWEEPS &&
+        (int)spawn_param.size() <= FAST_MAX_SPAWN && ps.nwt <= FAST_MAX_WT) {
+      bool ok = true;
+      ps.seq.nsw = ps.nsweeps;
+      for (int si = 0; si < ps.nsweeps && ok; ++si) {
+        const SweepD& d = sweeps[ps.sweep_off + si];
+        int g = -1;
+        if (d.rb[0] == 8) g = 0; else if (d.rb[0] == 0) g = 1; else if (d.rb[0] == 4) g = 2;
+        ok = ok && g >= 0 && (si > 0 || g == 0);
+        for (int k = 0; k < 4 && ok; ++k) ok = d.rb[k] == d.rb[0] + k;
+        ok = ok && d.pad == 0 && d.mop_end - d.mop_begin <= SEQ_MAX_OPS;
+        if (!ok) {
+          if (getenv("PQC_PLAN_DEBUG"))
+            fprintf(stderr, "seq: sweep %d rb %d..%d pad %d nops %d rejected\n", si, d.rb[0], d.rb[3],
+                    d.pad, d.mop_end - d.mop_begin);
+          break;
+        }
+        ps.seq.geom[si] = g;
+        ps.seq.nops[si] = 0;
+        for (int mi = d.mop_begin; mi < d.mop_end && ok; ++mi) {
+          const MOp& m = mops[ps.mop_off + mi];
+          FastOp f;
+          memset(&f, 0, sizeof(f));
+          f.kind = m.kind;
+          f.subk = m.subk;
+          if (m.kind == PQC_K_LAYER_RX4 || m.kind == PQC_K_LAYER_REAL4) {
+            for (int k = 0; k < 4; ++k) f.t[k] = m.subt[k];
+          } else if (m.kind == PQC_K_ZZSUM) {
+            f.t[0] = m.trig;
+            f.wt = m.aux1 / V1_WTAB;
+            f.nterms = m.npairs;
+          } else if (m.kind == PQC_K_GEN) {
+            f.wt = m.aux1 / V1_WTAB;
+            f.nterms = m.npairs;
+            f.spawn = m.aux0;
+          } else if (m.kind == PQC_K_RXY && m.k0 >= 0 && m.k1 >= 0 && m.k0 != m.k1) {
+            f.t[0] = m.trig;
+            f.subk = std::min(m.k0, m.k1) * 4 + std::max(m.k0, m.k1);
+          } else {
+            if (getenv("PQC_PLAN_DEBUG"))
+              fprintf(stderr, "seq: sweep %d op kind %d k0 %d k1 %d rejected\n", si, m.kind, m.k0, m.k1);
+            ok = false;
+          }
+          ps.seq.ops[si][ps.seq.nops[si]++] = f;
+        }
+      }
+      if (ok) {
+        for (int tb = 0; tb < ps.nwt; ++tb) {
+          const uint32_t* wt = zz.data() + ps.wt_off + tb * V1_WTAB;
+          for (int nib = 0; nib < 3; ++nib)
+            for (int v = 0; v < 16; ++v) {
+              uint32_t w = 0;
+              for (int i = 0; i < 4; ++i)
+                if ((v >> i) & 1) w ^= wt[ps.lbit[4 * nib + i]];
+              ps.seq.wn[tb][nib][v] = w;
+            }
+          for (int j = 0; j < n - V1_LOCAL_BITS; ++j) ps.seq.wo[tb][j] = wt[ps.obit[j]];
+        }
+      }
+      ps.seq_ok = ok;
+    }
     ps.spawn_param = spawn_param;
     ps.op_ids = cur_ids;
     passes.push_back(ps);
@@ -802,7 +867,8 @@ extern "C" PQC_API int pqc_program_describe(const pqc_program* prog, char* out, 
       kinds += "]";
     }
     snprintf(buf, sizeof(buf), "sweeps=%d mops=%d spawns=%d direct=%d/%d fast=%d", ps.nsweeps, nm,
-             (int)ps.spawn_param.size(), ps.io_first & 1, (ps.io_last >> 1) & 1, ps.fast_ok ? 1 : 0);
+             (int)ps.spawn_param.size(), ps.io_first & 1, (ps.io_last >> 1) & 1,
+             ps.fast_ok ? 1 : (ps.seq_ok ? 2 : 0));
     return std::string(buf) + kinds;
   };
   if (prog->v1_grad_ok) {
@@ -846,7 +912,7 @@ extern "C" PQC_API int pqc_program_describe(const pqc_program* prog, char* out, 
         char b2[160];
         snprintf(b2, sizeof(b2), "  %s PASS sweeps=%d spawns=%d direct=%d/%d fast=%d\n", names[k],
                  ps.nsweeps, (int)ps.spawn_param.size(), ps.io_first & 1, (ps.io_last >> 1) & 1,
-                 ps.fast_ok ? 1 : 0);
+                 ps.fast_ok ? 1 : (ps.seq_ok ? 2 : 0));
         s += b2;
       };
       if (k == 1) {
@@ -1727,6 +1793,272 @@ __global__ void __launch_bounds__(256, 2) k_layer_pass(const FastArgs A) {
 }
 
 // =====================================================================================
+// layer sequence: k_layer_pass generalised to any order of the three aligned nibble sweeps and to
+// XY pair rotations on two register bits (SeqPlan, pqc_common.cuh) -- the passes of the XXZ
+// template, whose XY bonds alternate between nibbles.  Same arithmetic and op order as
+// k_sweep_pass; the first sweep (tile positions 8-11 in registers) loads global memory
+// directly; the last one stores directly when it holds positions 8-11 or 4-7, and through one
+// more shared-memory transposition when it holds positions 0-3 (lanes must cover the low bits).
+// =====================================================================================
+struct SeqArgs {
+  const c128* src;
+  c128* dst;
+  const double2* gtrig;
+  int tstride, toff, ntrig;
+  int nwt;
+  int n;
+  int lbit[12];
+  int obit[PQC_MAX_QUBITS];
+  int slots_total, active, nspawn;
+  int spawn_slot[FAST_MAX_SPAWN];
+  double spawn_cr[FAST_MAX_SPAWN], spawn_ci[FAST_MAX_SPAWN];
+  // staged ends (tile positions 0-2 are not the amplitude bits 0-2): global memory is accessed
+  // in amplitude order -- lane bits = amplitude bits 0-3 -- and the tile is scattered into /
+  // gathered from its swizzled shared-memory slots.  Thread bit t < 4 sits at tile position
+  // st_q[t], thread bit 4 + t at st_hi[t]; register r contributes the masks st_rs / st_ra.
+  int staged;
+  int st_q[4], st_hi[4];
+  uint32_t st_rs[4], st_ra[4];
+  SeqPlan plan;
+};
+
+// rotation of the odd-parity pair (01, 10) of register bits KA < KB by [[c, -i s], [-i s, c]]
+template <int KA, int KB>
+__device__ __forceinline__ void op_xy(c128 (&a)[16], double c, double s) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j & ((1 << KA) | (1 << KB))) continue;
+    const int j01 = j | (1 << KA), j10 = j | (1 << KB);
+    const c128 x = a[j01], y = a[j10];
+    a[j01] = make_double2(c * x.x + s * y.y, c * x.y - s * y.x);
+    a[j10] = make_double2(c * y.x + s * x.y, c * y.y - s * x.x);
+  }
+}
+
+template <bool GEN, int RN, int NX, int NY>
+__device__ __forceinline__ void seq_ops(c128 (&a)[16], const SeqArgs& A, int slot, int vx, int vy,
+                                        const double2* trig, const uint32_t (*s_wn)[3][16],
+                                        const uint32_t* s_wb, int gen, double& fscale) {
+  const int nops = A.plan.nops[slot];
+  for (int oi = 0; oi < nops; ++oi) {
+    const FastOp& op = A.plan.ops[slot][oi];
+    const int kind = op.kind;
+    if (kind == PQC_K_RXY) {
+      const double2 cs = trig[op.t[0]];
+      switch (op.subk) {
+        case 1: op_xy<0, 1>(a, cs.x, cs.y); break;
+        case 2: op_xy<0, 2>(a, cs.x, cs.y); break;
+        case 3: op_xy<0, 3>(a, cs.x, cs.y); break;
+        case 6: op_xy<1, 2>(a, cs.x, cs.y); break;
+        case 7: op_xy<1, 3>(a, cs.x, cs.y); break;
+        default: op_xy<2, 3>(a, cs.x, cs.y); break;
+      }
+    } else if (kind == PQC_K_LAYER_RX4) {
+      const int sk = op.subk;
+      double2 c0 = make_double2(0.0, 1.0), c1 = c0, c2 = c0, c3 = c0;
+      if (sk & 0xff) c0 = trig[op.t[0]];
+      if (sk & 0xff00) c1 = trig[op.t[1]];
+      if (sk & 0xff0000) c2 = trig[op.t[2]];
+      if (sk & 0xff000000) c3 = trig[op.t[3]];
+      op_rx_t<0>(a, c0.x);
+      op_rx_t<1>(a, c1.x);
+      op_rx_t<2>(a, c2.x);
+      op_rx_t<3>(a, c3.x);
+      fscale *= (c0.y * c1.y) * (c2.y * c3.y);
+    } else if (kind == PQC_K_LAYER_REAL4) {
+      const int sk = op.subk;
+      double f = 1.0;
+#define SEQ_REAL_SLOT(K)                                                   \
+  {                                                                        \
+    const int kd = ((sk >> (8 * K)) & 0xff) - 1;                           \
+    if (kd == PQC_OP_RY) { const double2 tc = trig[op.t[K]]; op_ry_t<K>(a, tc.x); f *= tc.y; } \
+    else if (kd == PQC_OP_H) { op_h_u<K>(a); f *= 0.70710678118654752440; } \
+  }
+      SEQ_REAL_SLOT(0) SEQ_REAL_SLOT(1) SEQ_REAL_SLOT(2) SEQ_REAL_SLOT(3)
+#undef SEQ_REAL_SLOT
+      fscale *= f;
+    } else {
+      // ZZSUM / GEN: w(x) = w(tile) ^ w(thread nibbles) ^ w(register nibble value j)
+      const uint32_t(*wn)[16] = s_wn[op.wt];
+      const uint32_t w0 = s_wb[op.wt] ^ wn[NX][vx] ^ wn[NY][vy];
+      const uint32_t w1 = wn[RN][1], w2 = wn[RN][2], w3 = wn[RN][4], w4 = wn[RN][8];
+      if (kind == PQC_K_ZZSUM) {
+        const double2* tz = trig + op.t[0];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const double2 ph = tz[__popc(w0 ^ XSEL4R(j, w1, w2, w3, w4))];
+          const c128 v = a[j];
+          a[j] = make_double2(v.x * ph.x - v.y * ph.y, v.y * ph.x + v.x * ph.y);
+        }
+      } else if (GEN && gen == op.spawn) {
+        const double cr = A.spawn_cr[gen], ci = A.spawn_ci[gen];
+        const int nt = op.nterms;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const double f = (double)(nt - 2 * __popc(w0 ^ XSEL4R(j, w1, w2, w3, w4)));
+          const double fr = f * cr, fi = f * ci;
+          const c128 v = a[j];
+          a[j] = make_double2(v.x * fr - v.y * fi, v.y * fr + v.x * fi);
+        }
+      }
+    }
+  }
+}
+
+template <bool GEN>
+__global__ void __launch_bounds__(256, 2) k_layer_seq(const SeqArgs A) {
+  extern __shared__ __align__(16) c128 lp_sm[];
+  double2* trig = reinterpret_cast<double2*>(lp_sm + 4096);
+  __shared__ uint32_t s_ta[2][16];               // amplitude bits of tile nibbles 1 and 2
+  __shared__ uint32_t s_wn[FAST_MAX_WT][3][16];  // linear forms per table, nibble, nibble value
+  __shared__ uint32_t s_wb[FAST_MAX_WT];         // linear form of the tile index
+  const int tid = threadIdx.x, lo = tid & 15, hi = tid >> 4;
+  const int tiles_log2 = A.n - 12;
+  const long long item = (long long)blockIdx.x >> tiles_log2;
+  const uint32_t tile = (uint32_t)(blockIdx.x & ((1u << tiles_log2) - 1u));
+  uint32_t tbase = 0;
+  for (int j = 0; j < tiles_log2; ++j) tbase |= ((tile >> j) & 1u) << A.obit[j];
+  const int ips = A.active + A.nspawn;
+  const long long sample = item / ips;
+  const int r = (int)(item - sample * ips);
+  int src_slot = r, dst_slot = r, gen = -1;
+  if (GEN && r >= A.active) {
+    src_slot = 0;
+    gen = r - A.active;
+    dst_slot = A.spawn_slot[gen];
+  }
+  // amplitude bits fed by `lo` (tile positions 0-3; position 3 need not be amplitude bit 3)
+  const uint32_t lo_amp = ((uint32_t)lo & 7u) | ((((uint32_t)lo >> 3) & 1u) << A.lbit[3]);
+  // staged ends: this thread's tile index / amplitude offset in amplitude order
+  uint32_t st_sm = 0, st_amp = 0;
+  if (A.staged) {
+    uint32_t bi = 0;
+    st_amp = tbase | (uint32_t)lo;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      bi |= (((uint32_t)lo >> t) & 1u) << A.st_q[t];
+      bi |= (((uint32_t)hi >> t) & 1u) << A.st_hi[t];
+      st_amp |= (((uint32_t)hi >> t) & 1u) << A.lbit[A.st_hi[t]];
+    }
+    st_sm = swz(bi);
+  }
+  // ---- sweep 0 loads straight from global memory: registers = tile positions 8-11
+  c128 a[16];
+  if (A.staged) {
+    const c128* sp = A.src + ((sample * A.slots_total + src_slot) << A.n) + st_amp;
+    const uint32_t r0 = A.st_ra[0], r1 = A.st_ra[1], r2 = A.st_ra[2], r3 = A.st_ra[3];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = sp[XSEL4R(j, r0, r1, r2, r3)];
+  } else {
+    const uint32_t ampA = tbase | lo_amp | ((uint32_t)(hi & 1) << A.lbit[4]) |
+                          ((uint32_t)((hi >> 1) & 1) << A.lbit[5]) |
+                          ((uint32_t)((hi >> 2) & 1) << A.lbit[6]) |
+                          ((uint32_t)((hi >> 3) & 1) << A.lbit[7]);
+    const uint32_t g0 = 1u << A.lbit[8], g1 = 1u << A.lbit[9], g2 = 1u << A.lbit[10],
+                   g3 = 1u << A.lbit[11];
+    const c128* sp = A.src + ((sample * A.slots_total + src_slot) << A.n) + ampA;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = sp[XSEL4R(j, g0, g1, g2, g3)];
+  }
+  // ---- tables (overlap the tile load)
+  if (tid < 32) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v |= (((uint32_t)lo >> i) & 1u) << A.lbit[4 + 4 * hi + i];
+    s_ta[hi][lo] = v;
+  }
+  for (int e = tid; e < A.nwt * 48; e += 256) (&s_wn[0][0][0])[e] = (&A.plan.wn[0][0][0])[e];
+  if (tid < A.nwt) {
+    uint32_t w = 0;
+    for (int j = 0; j < tiles_log2; ++j) w ^= ((tile >> j) & 1u) ? A.plan.wo[tid][j] : 0u;
+    s_wb[tid] = w;
+  }
+  for (int e = tid; e < A.ntrig; e += 256) trig[e] = A.gtrig[sample * A.tstride + A.toff + e];
+  if (A.staged) {
+    const uint32_t q0 = A.st_rs[0], q1 = A.st_rs[1], q2 = A.st_rs[2], q3 = A.st_rs[3];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) lp_sm[st_sm ^ XSEL4R(j, q0, q1, q2, q3)] = a[j];
+  }
+  __syncthreads();
+
+  double fscale = 1.0;
+#define LP_CA(j) ((((j) << 8) ^ ((((j) << 2) ^ ((j) >> 1)) & 7)))   /* swz(j << 8) */
+#define LP_CB(j) (((j) ^ ((j) >> 3)))                               /* swz(j)      */
+#define LP_CC(j) ((((j) << 4) ^ ((((j) << 1) ^ ((j) >> 2)) & 7)))   /* swz(j << 4) */
+  const uint32_t sbA = swz((uint32_t)tid), sbB = swz((uint32_t)tid << 4),
+                 sbC = swz((uint32_t)lo | ((uint32_t)hi << 8));
+  const int nsw = A.plan.nsw;
+  int g = 0;
+  for (int s = 0; s < nsw; ++s) {
+    g = A.plan.geom[s];
+    if (s > 0 || A.staged) {
+      if (g == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = lp_sm[sbA ^ LP_CA(j)];
+      } else if (g == 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = lp_sm[sbB ^ LP_CB(j)];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = lp_sm[sbC ^ LP_CC(j)];
+      }
+    }
+    if (g == 0) seq_ops<GEN, 2, 0, 1>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale);
+    else if (g == 1) seq_ops<GEN, 0, 1, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale);
+    else seq_ops<GEN, 1, 0, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale);
+    if (s + 1 == nsw && g != 1 && !A.staged) break;   // the registers go straight to global memory
+    if (s + 1 == nsw && fscale != 1.0) op_scale(a, fscale);
+    // back to shared memory (every thread rewrites exactly the slots it read, except after the
+    // global load of sweep 0, which nobody has touched yet)
+    if (g == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) lp_sm[sbA ^ LP_CA(j)] = a[j];
+    } else if (g == 1) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) lp_sm[sbB ^ LP_CB(j)] = a[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) lp_sm[sbC ^ LP_CC(j)] = a[j];
+    }
+    __syncthreads();
+  }
+  c128* dbase = A.dst + ((sample * A.slots_total + dst_slot) << A.n);
+  if (A.staged) {
+    // the finished tile is in shared memory: gather it in amplitude order
+    const uint32_t q0 = A.st_rs[0], q1 = A.st_rs[1], q2 = A.st_rs[2], q3 = A.st_rs[3];
+    const uint32_t r0 = A.st_ra[0], r1 = A.st_ra[1], r2 = A.st_ra[2], r3 = A.st_ra[3];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = lp_sm[st_sm ^ XSEL4R(j, q0, q1, q2, q3)];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dbase[st_amp | XSEL4R(j, r0, r1, r2, r3)] = a[j];
+  } else if (g == 0) {
+    if (fscale != 1.0) op_scale(a, fscale);
+    const uint32_t ampA = tbase | lo_amp | s_ta[0][hi];
+    const uint32_t g0 = 1u << A.lbit[8], g1 = 1u << A.lbit[9], g2 = 1u << A.lbit[10],
+                   g3 = 1u << A.lbit[11];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dbase[ampA | XSEL4R(j, g0, g1, g2, g3)] = a[j];
+  } else {
+    if (g == 1) {
+      // the last sweep held positions 0-3 (already scaled and written back): one more
+      // transposition so that lanes cover the low index bits
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a[j] = lp_sm[sbC ^ LP_CC(j)];
+    } else if (fscale != 1.0) {
+      op_scale(a, fscale);
+    }
+    const uint32_t ampC = tbase | lo_amp | s_ta[1][hi];
+    const uint32_t g0 = 1u << A.lbit[4], g1 = 1u << A.lbit[5], g2 = 1u << A.lbit[6],
+                   g3 = 1u << A.lbit[7];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dbase[ampC | XSEL4R(j, g0, g1, g2, g3)] = a[j];
+  }
+#undef LP_CA
+#undef LP_CB
+#undef LP_CC
+}
+
+// =====================================================================================
 // tile gather: dst slot <- (sum of Pauli terms) src slot 0, for one or more parameters.
 // One CTA per (sample, 4096-amplitude chunk); the chunk of psi sits in shared memory, terms
 // flipping only low bits read it from there, the others from global / L2.
@@ -2352,6 +2684,11 @@ static bool fast_enabled() {                 // PQC_FAST=0: always use the gener
   return !(e && strcmp(e, "0") == 0);
 }
 
+static bool seq_enabled() {                  // PQC_SEQ=0: XXZ-type passes stay on k_sweep_pass
+  const char* e = getenv("PQC_SEQ");         // (read per launch so tests can compare both paths)
+  return !(e && strcmp(e, "0") == 0);
+}
+
 static int launch_v1(const V1Args& a_in, cudaStream_t st) {
   V1Args a = a_in;
   a.pf_dist = (a.low_run >= 4) ? prefetch_dist() : 0;
@@ -2421,6 +2758,63 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
       else k_layer_pass<2, false><<<(unsigned)grid, 256, fsmem, st>>>(f);
     }
     pqc_prof_launch_end(hh, st);
+    PQC_LAUNCH_CHECK();
+    return 0;
+  }
+  if (a.hpass && a.hpass->seq_ok && a.npartners == 0 && a.nspawn <= FAST_MAX_SPAWN &&
+      fast_enabled() && seq_enabled()) {
+    SeqArgs f;
+    memset(&f, 0, sizeof(f));
+    f.src = a.src;
+    f.dst = a.dst;
+    f.gtrig = a.gtrig;
+    f.tstride = a.tstride;
+    f.toff = a.toff;
+    f.ntrig = a.ntrig;
+    f.nwt = a.nwt;
+    f.n = a.n;
+    memcpy(f.lbit, a.lbit, sizeof(f.lbit));
+    memcpy(f.obit, a.obit, sizeof(f.obit));
+    f.slots_total = a.slots_total;
+    f.active = a.active;
+    f.nspawn = a.nspawn;
+    for (int k = 0; k < a.nspawn; ++k) {
+      f.spawn_slot[k] = a.spawn_slot[k];
+      f.spawn_cr[k] = a.hprog->gens[a.spawn_goff[k]].re;
+      f.spawn_ci[k] = a.hprog->gens[a.spawn_goff[k]].im;
+    }
+    f.plan = a.hpass->seq;
+    f.staged = a.hpass->direct_ok ? 0 : 1;
+    if (f.staged) {
+      // thread bits 0-3 -> the tile positions of amplitude bits 0-3; the other 8 positions in
+      // ascending order -> thread bits 4-7, then register bits 0-3
+      std::vector<int> rest;
+      for (int t = 0; t < 4; ++t) f.st_q[t] = -1;
+      for (int pos = 0; pos < 12; ++pos) {
+        if (a.lbit[pos] < 4) f.st_q[a.lbit[pos]] = pos;
+        else rest.push_back(pos);
+      }
+      bool okq = rest.size() == 8;
+      for (int t = 0; t < 4; ++t) okq = okq && f.st_q[t] >= 0;
+      if (!okq) PQC_FAIL(-5, "internal: tile without the four low amplitude bits");
+      for (int t = 0; t < 4; ++t) {
+        f.st_hi[t] = rest[t];
+        const uint32_t i = 1u << rest[4 + t];
+        f.st_rs[t] = i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u);
+        f.st_ra[t] = 1u << a.lbit[rest[4 + t]];
+      }
+    }
+    static bool qattr = false;
+    if (!qattr) {
+      PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      qattr = true;
+    }
+    const size_t qsmem = 4096 * sizeof(c128) + (size_t)a.ntrig * sizeof(double2);
+    const int hq = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st);
+    if (a.nspawn > 0) k_layer_seq<true><<<(unsigned)grid, 256, qsmem, st>>>(f);
+    else k_layer_seq<false><<<(unsigned)grid, 256, qsmem, st>>>(f);
+    pqc_prof_launch_end(hq, st);
     PQC_LAUNCH_CHECK();
     return 0;
   }

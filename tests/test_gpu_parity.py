@@ -329,6 +329,33 @@ def test_layer_pass_fast_path_matches_generic_sweep_kernel(kind, n, p, monkeypat
     assert rel(F[0].cpu().numpy(), orc.qfi(ref[0], gr[0])) < RTOL
 
 
+@pytest.mark.parametrize("kind,n,p", [("XXZ", 16, 2), ("XXZ", 13, 3), ("XXZ", 12, 4)])
+def test_layer_sequence_path_matches_generic_sweep_kernel(kind, n, p, monkeypatch):
+    """XXZ passes (XY pair rotations, nibble sweeps in any order) run on k_layer_seq (plan lines
+    say fast=2); PQC_SEQ=0 keeps them on the generic k_sweep_pass.  Same arithmetic in the same
+    order: states and QFIMs agree to rounding, and row 0 agrees with the oracle."""
+    qc = pyqc.templates.generate_circuit(kind, n, p, shuffle=False)
+    assert "fast=2" in qc.program.describe()
+    specs, init = orc.generate_circuit(kind, n, p)
+    ang = np.random.default_rng(3 * n + p).random((3, orc.n_params(specs))) * 2 * np.pi
+    st = qc.run_batch(ang)
+    F = qc.qfim_batch(ang)
+    gr = qc.program.gradients(ang, init=qc.initial_state.tensor)
+    monkeypatch.setenv("PQC_SEQ", "0")
+    st0 = qc.run_batch(ang)
+    F0 = qc.qfim_batch(ang)
+    gr0 = qc.program.gradients(ang, init=qc.initial_state.tensor)
+    monkeypatch.delenv("PQC_SEQ")
+    assert np.abs((st - st0).cpu().numpy()).max() < 1e-14
+    assert np.abs((gr - gr0).cpu().numpy()).max() < 1e-13
+    assert rel(F.cpu().numpy(), F0.cpu().numpy()) < 1e-12
+    ref = orc.run(specs, n, ang[:1], init)
+    assert np.abs(st[:1].cpu().numpy() - ref).max() < ATOL
+    g1 = orc.gradients(specs, n, ang[:1], init)
+    assert np.abs(gr[:1, 1:].cpu().numpy() - g1).max() < ATOL
+    assert rel(F[0].cpu().numpy(), orc.qfi(ref[0], g1[0])) < RTOL
+
+
 def test_eigvalsh_vs_lapack():
     rng = np.random.default_rng(11)
     for P in (1, 2, 5, 12, 32, 33, 64):
@@ -449,6 +476,49 @@ def test_config2_full_size_properties():
     # sharded form (dist.py partition, single rank) gives the same integer counts
     from pyramaterised_b200 import dist as pdist
     assert torch.equal(pdist.sharded_fidelity_hist(sub, b), h1)
+
+
+def _sparse_circuit(n, q):
+    """Three layers of every primitive family on the 12 qubits q[0..11] of an n-qubit register."""
+    G = pyqc.gates
+    qc = pyqc.PQC(n)
+    qc.add_layer([G.H(q[0], n), G.fixed_R_y(q[3], n, 0.7)] + [G.R_y(k, n) for k in q] +
+                 [G.CNOT([q[0], q[11]], n), G.CZ([q[5], q[6]], n), G.CNOT([q[7], q[2]], n)])
+    qc.add_layer([G.R_z(k, n) for k in q] +
+                 [G.R_xx([q[2], q[9]], n), G.R_zz([q[4], q[7]], n), G.R_yy([q[1], q[10]], n),
+                  G.CNOT([q[8], q[3]], n)])
+    qc.add_layer([G.R_x(k, n) for k in q] + [G.CZ([q[0], q[6]], n), G.R_zz([q[11], q[5]], n)])
+    return qc
+
+
+def test_config5_size_28_qubit_register_vs_12_qubit_oracle():
+    """Config 5's register size (28 qubits, 4 GiB per complex128 state).  Gates act on 12
+    qubits spread over the whole register (tile-low, middle and top index bits), so the state is
+    the 12-qubit oracle state embedded at the other qubits = 0: amplitudes bit-for-bit
+    comparable at full size, Meyer-Wallach Q_28 = 12/28 * Q_12, pair fidelity = the 12-qubit one."""
+    n = 28
+    q = [0, 1, 2, 9, 10, 13, 14, 20, 24, 25, 26, 27]
+    big, small = _sparse_circuit(n, q), _sparse_circuit(12, list(range(12)))
+    P = small.n_true_params
+    assert big.n_true_params == P
+    ang = np.random.default_rng(28).random((2, P)) * 2 * np.pi
+    ref = orc.run(specs_from_circuit(small), 12, ang, None)
+    st = big.run_batch(ang)                                     # [2, 2^28]
+    assert st.shape == (2, 1 << n)
+    # index of the embedded amplitude: bit (11 - k) of j -> index bit (n - 1 - q[k])
+    j = np.arange(4096)
+    idx = np.zeros(4096, dtype=np.int64)
+    for k in range(12):
+        idx |= ((j >> (11 - k)) & 1) << (n - 1 - q[k])
+    got = st[:, torch.as_tensor(idx, device="cuda")].cpu().numpy()
+    assert np.abs(got - ref).max() < ATOL
+    nrm = engine.overlap(st, st).cpu().numpy()
+    assert np.abs(nrm - 1).max() < 1e-12                        # nothing leaked elsewhere
+    Q = engine.meyer_wallach(st).cpu().numpy()
+    for s in range(2):
+        assert abs(Q[s] - 12.0 / 28.0 * orc.single_Q(ref[s], 12)) < ATOL
+    _, F = engine.fidelity_hist(st, bins=7, want_F=True)
+    assert abs(float(F.reshape(-1)[0]) - abs(np.vdot(ref[0], ref[1])) ** 2) < ATOL
 
 
 def test_config4_full_size_stabilizer_states_have_zero_magic():
