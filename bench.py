@@ -203,6 +203,9 @@ def run_b200(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: NCCL's own log lines (version banner, INFO) go
+        # to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -289,7 +292,8 @@ def run_b200(a):
     e2e = total * a.steps / (ms_e2e / 1e3)
     peak, peak_src = measured_peak_gbs()
     achieved = prof["bytes"] / (prof["ms"] / 1e3) / 1e9 if prof["ms"] > 0 else 0.0
-    kern = "k_layer_pass"     # the pass kernel of this workload (k_sweep_pass = its generic form)
+    # the pass kernel of this workload (k_sweep_pass is the generic form of both)
+    kern = "k_layer_pass" if a.circuit == "TFIM" else "k_layer_seq"
     alg_per_launch = prof["bytes"] / max(1, prof["launches"])
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world,

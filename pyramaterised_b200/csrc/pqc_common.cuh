@@ -166,12 +166,16 @@ struct FastPlan {
 // in ANY order and up to SEQ_MAX_SWEEPS times (the XXZ template's XY bonds alternate between
 // nibbles), and whose ops may also be XY pair rotations (PQC_K_RXY) on two register bits.
 #define SEQ_MAX_SWEEPS 6
-#define SEQ_MAX_OPS 6
+#define SEQ_MAX_OPS 72               // per pass, all sweeps together
+#define SEQ_MAX_SPAWN 8
 struct SeqPlan {
   int nsw;
   int geom[SEQ_MAX_SWEEPS];          // registers hold tile positions 0: 8-11, 1: 0-3, 2: 4-7
-  int nops[SEQ_MAX_SWEEPS];
-  FastOp ops[SEQ_MAX_SWEEPS][SEQ_MAX_OPS];   // RXY: subk = ka * 4 + kb (ka < kb), t[0] = trig slot
+  int off[SEQ_MAX_SWEEPS], nops[SEQ_MAX_SWEEPS];   // the sweep's ops: ops[off .. off + nops)
+  // RXY: subk = ka * 4 + kb (ka < kb), t[0] = trig slot
+  // RZ:  t[0] = trig slot, t[1] = register bit or -1, t[2] = tile position or -1, t[3] = global bit
+  // CZ:  t[0], t[1] = register bits or -1, t[2], t[3] = tile positions or -1, wt, nterms = global bits
+  FastOp ops[SEQ_MAX_OPS];
   uint32_t wn[FAST_MAX_WT][3][16];
   uint32_t wo[FAST_MAX_WT][PQC_MAX_QUBITS - 12];
 };

@@ -582,9 +582,10 @@ struct Builder {
     ps.seq_ok = false;
     memset(&ps.seq, 0, sizeof(ps.seq));
     if (!ps.fast_ok && cap == V1_LOCAL_BITS && V1_LOCAL_BITS == 12 && n >= V1_LOCAL_BITS &&
-        ps.nsweeps >= 2 && ps.nsweeps <= SEQ_MAX_SWEEPS &&
-        (int)spawn_param.size() <= FAST_MAX_SPAWN && ps.nwt <= FAST_MAX_WT) {
+        ps.nsweeps >= 1 && ps.nsweeps <= SEQ_MAX_SWEEPS &&
+        (int)spawn_param.size() <= SEQ_MAX_SPAWN && ps.nwt <= FAST_MAX_WT) {
       bool ok = true;
+      int nflat = 0;
       ps.seq.nsw = ps.nsweeps;
       for (int si = 0; si < ps.nsweeps && ok; ++si) {
         const SweepD& d = sweeps[ps.sweep_off + si];
@@ -592,7 +593,7 @@ struct Builder {
         if (d.rb[0] == 8) g = 0; else if (d.rb[0] == 0) g = 1; else if (d.rb[0] == 4) g = 2;
         ok = ok && g >= 0 && (si > 0 || g == 0);
         for (int k = 0; k < 4 && ok; ++k) ok = d.rb[k] == d.rb[0] + k;
-        ok = ok && d.pad == 0 && d.mop_end - d.mop_begin <= SEQ_MAX_OPS;
+        ok = ok && d.pad == 0 && nflat + d.mop_end - d.mop_begin <= SEQ_MAX_OPS;
         if (!ok) {
           if (getenv("PQC_PLAN_DEBUG"))
             fprintf(stderr, "seq: sweep %d rb %d..%d pad %d nops %d rejected\n", si, d.rb[0], d.rb[3],
@@ -600,6 +601,7 @@ struct Builder {
           break;
         }
         ps.seq.geom[si] = g;
+        ps.seq.off[si] = nflat;
         ps.seq.nops[si] = 0;
         for (int mi = d.mop_begin; mi < d.mop_end && ok; ++mi) {
           const MOp& m = mops[ps.mop_off + mi];
@@ -620,12 +622,27 @@ struct Builder {
           } else if (m.kind == PQC_K_RXY && m.k0 >= 0 && m.k1 >= 0 && m.k0 != m.k1) {
             f.t[0] = m.trig;
             f.subk = std::min(m.k0, m.k1) * 4 + std::max(m.k0, m.k1);
+          } else if (m.kind == PQC_OP_RZ) {
+            f.t[0] = m.trig;
+            f.t[1] = m.k0;
+            f.t[2] = m.l0;
+            f.t[3] = m.b0;
+          } else if (m.kind == PQC_OP_CZ) {
+            f.t[0] = m.k0;
+            f.t[1] = m.k1;
+            f.t[2] = m.l0;
+            f.t[3] = m.l1;
+            f.wt = m.b0;
+            f.nterms = m.b1;
+          } else if (m.kind == PQC_OP_IDENT) {
+            continue;
           } else {
             if (getenv("PQC_PLAN_DEBUG"))
               fprintf(stderr, "seq: sweep %d op kind %d k0 %d k1 %d rejected\n", si, m.kind, m.k0, m.k1);
             ok = false;
           }
-          ps.seq.ops[si][ps.seq.nops[si]++] = f;
+          ps.seq.ops[nflat++] = f;
+          ps.seq.nops[si]++;
         }
       }
       if (ok) {
@@ -1810,8 +1827,8 @@ struct SeqArgs {
   int lbit[12];
   int obit[PQC_MAX_QUBITS];
   int slots_total, active, nspawn;
-  int spawn_slot[FAST_MAX_SPAWN];
-  double spawn_cr[FAST_MAX_SPAWN], spawn_ci[FAST_MAX_SPAWN];
+  int spawn_slot[SEQ_MAX_SPAWN];
+  double spawn_cr[SEQ_MAX_SPAWN], spawn_ci[SEQ_MAX_SPAWN];
   // staged ends (tile positions 0-2 are not the amplitude bits 0-2): global memory is accessed
   // in amplitude order -- lane bits = amplitude bits 0-3 -- and the tile is scattered into /
   // gathered from its swizzled shared-memory slots.  Thread bit t < 4 sits at tile position
@@ -1835,14 +1852,83 @@ __device__ __forceinline__ void op_xy(c128 (&a)[16], double c, double s) {
   }
 }
 
+// Consecutive diagonal ops of a sweep (R_z phases, CZ signs) are accumulated per thread --
+// thread-level phase T, one phase per register bit (bit = 1 takes the conjugate), a 16-bit sign
+// mask -- and applied together: at most 16 complex multiplications per touched register bit
+// whatever the number of gates.  `base` = the thread's tile-local index (register bits zero).
 template <bool GEN, int RN, int NX, int NY>
 __device__ __forceinline__ void seq_ops(c128 (&a)[16], const SeqArgs& A, int slot, int vx, int vy,
                                         const double2* trig, const uint32_t (*s_wn)[3][16],
-                                        const uint32_t* s_wb, int gen, double& fscale) {
-  const int nops = A.plan.nops[slot];
+                                        const uint32_t* s_wb, int gen, double& fscale,
+                                        uint32_t base, uint32_t tbase) {
+  const int nops = A.plan.nops[slot], off = A.plan.off[slot];
   for (int oi = 0; oi < nops; ++oi) {
-    const FastOp& op = A.plan.ops[slot][oi];
-    const int kind = op.kind;
+    const int kind = A.plan.ops[off + oi].kind;
+    if (kind == PQC_OP_RZ || kind == PQC_OP_CZ) {
+      // ---- a run of diagonal ops: accumulate, then apply once
+      double tc = 1.0, ts = 0.0;                  // thread-level phase (tc + i ts)
+      double pc[4] = {1.0, 1.0, 1.0, 1.0}, pn[4] = {0.0, 0.0, 0.0, 0.0};   // bit k = 1: (pc + i pn)
+      uint32_t sg = 0u, touched = 0u;             // sign mask over j; bit 4 of touched: T set
+      for (; oi < nops; ++oi) {
+        const FastOp& op = A.plan.ops[off + oi];
+        if (op.kind == PQC_OP_RZ) {
+          const double2 cs = trig[op.t[0]];
+          const int k0 = op.t[1];
+          if (k0 >= 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k == k0) {                      // (pc + i pn) *= (c + i s)
+                const double c = pc[k], sn = pn[k];
+                pc[k] = c * cs.x - sn * cs.y;
+                pn[k] = sn * cs.x + c * cs.y;
+              }
+            touched |= 1u << k0;
+          } else {
+            const uint32_t bit = op.t[2] >= 0 ? ((base >> op.t[2]) & 1u) : ((tbase >> op.t[3]) & 1u);
+            const double sn = bit ? cs.y : -cs.y, c = tc, s0 = ts;
+            tc = c * cs.x - s0 * sn;
+            ts = s0 * cs.x + c * sn;
+            touched |= 16u;
+          }
+        } else if (op.kind == PQC_OP_CZ) {
+          // 16-bit masks over j of "bit set": a register bit's pattern, else all / none
+          auto mask_of = [&](int k, int l, int b) -> uint32_t {
+            if (k >= 0) return k == 0 ? 0xAAAAu : (k == 1 ? 0xCCCCu : (k == 2 ? 0xF0F0u : 0xFF00u));
+            const uint32_t bit = l >= 0 ? ((base >> l) & 1u) : ((tbase >> b) & 1u);
+            return bit ? 0xFFFFu : 0u;
+          };
+          sg ^= mask_of(op.t[0], op.t[2], op.wt) & mask_of(op.t[1], op.t[3], op.nterms);
+        } else {
+          break;
+        }
+      }
+      --oi;                                       // the outer loop steps past the run's last op
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (touched & (1u << k)) {                // warp-uniform
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const double sn = (j & (1 << k)) ? pn[k] : -pn[k];
+            const c128 v = a[j];
+            a[j] = make_double2(v.x * pc[k] - v.y * sn, v.y * pc[k] + v.x * sn);
+          }
+        }
+      }
+      if (touched & 16u) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const c128 v = a[j];
+          a[j] = make_double2(v.x * tc - v.y * ts, v.y * tc + v.x * ts);
+        }
+      }
+      if (sg) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if ((sg >> j) & 1u) a[j] = make_double2(-a[j].x, -a[j].y);
+      }
+      continue;
+    }
+    const FastOp& op = A.plan.ops[off + oi];
     if (kind == PQC_K_RXY) {
       const double2 cs = trig[op.t[0]];
       switch (op.subk) {
@@ -2003,9 +2089,13 @@ __global__ void __launch_bounds__(256, 2) k_layer_seq(const SeqArgs A) {
         for (int j = 0; j < 16; ++j) a[j] = lp_sm[sbC ^ LP_CC(j)];
       }
     }
-    if (g == 0) seq_ops<GEN, 2, 0, 1>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale);
-    else if (g == 1) seq_ops<GEN, 0, 1, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale);
-    else seq_ops<GEN, 1, 0, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale);
+    if (g == 0)
+      seq_ops<GEN, 2, 0, 1>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale, (uint32_t)tid, tbase);
+    else if (g == 1)
+      seq_ops<GEN, 0, 1, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale, (uint32_t)tid << 4, tbase);
+    else
+      seq_ops<GEN, 1, 0, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale,
+                            (uint32_t)lo | ((uint32_t)hi << 8), tbase);
     if (s + 1 == nsw && g != 1 && !A.staged) break;   // the registers go straight to global memory
     if (s + 1 == nsw && fscale != 1.0) op_scale(a, fscale);
     // back to shared memory (every thread rewrites exactly the slots it read, except after the
@@ -2761,7 +2851,7 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
     PQC_LAUNCH_CHECK();
     return 0;
   }
-  if (a.hpass && a.hpass->seq_ok && a.npartners == 0 && a.nspawn <= FAST_MAX_SPAWN &&
+  if (a.hpass && a.hpass->seq_ok && a.npartners == 0 && a.nspawn <= SEQ_MAX_SPAWN &&
       fast_enabled() && seq_enabled()) {
     SeqArgs f;
     memset(&f, 0, sizeof(f));

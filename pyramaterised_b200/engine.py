@@ -141,6 +141,8 @@ class Program:
         D = self.dim
         if out is None:
             out = torch.empty((S, D), dtype=torch.complex128, device=dev)
+        if S == 0:
+            return out
         stride = 0
         if init is not None:
             init = as_states(init, dev)
@@ -173,6 +175,10 @@ class Program:
         lib = _lib.load()
         a = as_angles(angles, self.P, dev)
         S = a.shape[0]
+        if S == 0:
+            F = torch.empty((0, self.P, self.P), dtype=torch.float64, device=dev)
+            st = torch.empty((0, self.dim), dtype=torch.complex128, device=dev)
+            return (F, st) if want_states else F
         need = C.c_int64()
         _lib.check(lib.pqc_qfim_workspace_bytes(self._h, S, C.byref(need)))
         per = (need.value - 256) // max(1, S)
@@ -242,6 +248,8 @@ def meyer_wallach(states):
     states = states.contiguous()
     S, D = states.shape
     out = torch.empty((S,), dtype=torch.float64, device=states.device)
+    if S == 0:
+        return out
     _lib.check(_lib.load().pqc_meyer_wallach(_p(states), S, D.bit_length() - 1, _p(out), _stream()))
     _count(2)
     return out
@@ -329,6 +337,8 @@ def magic(states, alphas=(2.0,)):
     S, D = states.shape
     al = (C.c_double * len(alphas))(*[float(x) for x in alphas])
     out = torch.empty((len(alphas), S), dtype=torch.float64, device=states.device)
+    if S == 0:
+        return out
     _lib.check(_lib.load().pqc_magic_batch(_p(states), S, D.bit_length() - 1, len(alphas), al,
                                            _p(out), _stream()))
     _count(2)

@@ -329,11 +329,13 @@ def test_layer_pass_fast_path_matches_generic_sweep_kernel(kind, n, p, monkeypat
     assert rel(F[0].cpu().numpy(), orc.qfi(ref[0], gr[0])) < RTOL
 
 
-@pytest.mark.parametrize("kind,n,p", [("XXZ", 16, 2), ("XXZ", 13, 3), ("XXZ", 12, 4)])
+@pytest.mark.parametrize("kind,n,p", [("XXZ", 16, 2), ("XXZ", 13, 3), ("XXZ", 12, 4),
+                                      ("NPQC", 14, 3), ("NPQC", 12, 5), ("NPQC", 17, 2)])
 def test_layer_sequence_path_matches_generic_sweep_kernel(kind, n, p, monkeypatch):
-    """XXZ passes (XY pair rotations, nibble sweeps in any order) run on k_layer_seq (plan lines
-    say fast=2); PQC_SEQ=0 keeps them on the generic k_sweep_pass.  Same arithmetic in the same
-    order: states and QFIMs agree to rounding, and row 0 agrees with the oracle."""
+    """XXZ passes (XY pair rotations, nibble sweeps in any order) and NPQC passes (runs of R_z
+    phases and CZ signs, applied once per run) execute on k_layer_seq (plan lines say fast=2);
+    PQC_SEQ=0 keeps them on the generic k_sweep_pass.  States, derivative states and QFIMs agree
+    to rounding, and row 0 agrees with the oracle."""
     qc = pyqc.templates.generate_circuit(kind, n, p, shuffle=False)
     assert "fast=2" in qc.program.describe()
     specs, init = orc.generate_circuit(kind, n, p)
@@ -354,6 +356,29 @@ def test_layer_sequence_path_matches_generic_sweep_kernel(kind, n, p, monkeypatc
     g1 = orc.gradients(specs, n, ang[:1], init)
     assert np.abs(gr[:1, 1:].cpu().numpy() - g1).max() < ATOL
     assert rel(F[0].cpu().numpy(), orc.qfi(ref[0], g1[0])) < RTOL
+
+
+def test_ragged_and_empty_batches():
+    """Batch edges: a QFIM batch that does not fill its last 256-set chunk, a single row, an
+    empty batch; every row must equal the one-row call bit for bit (fixed summation orders)."""
+    qc = pyqc.templates.generate_circuit("TFIM", 12, 3, shuffle=False)
+    P = qc.n_true_params
+    ang = np.random.default_rng(9).random((300, P)) * 2 * np.pi
+    F = qc.qfim_batch(ang)
+    st = qc.run_batch(ang)
+    assert F.shape == (300, P, P) and st.shape == (300, 4096)
+    for row in (0, 255, 256, 299):
+        F1 = qc.qfim_batch(ang[row:row + 1])
+        assert torch.equal(F1[0], F[row])
+        assert torch.equal(qc.run_batch(ang[row:row + 1])[0], st[row])
+    assert torch.equal(F, F.transpose(1, 2))                       # exactly symmetric
+    e = np.zeros((0, P))
+    assert qc.run_batch(e).shape == (0, 4096)
+    assert qc.qfim_batch(e).shape == (0, P, P)
+    assert engine.meyer_wallach(st[:0]).shape == (0,)
+    assert engine.magic(st[:0], (2.0,)).shape == (1, 0)
+    with pytest.raises(IndexError):
+        qc.run_batch(ang[:, :P - 1])                               # short angle rows, circuit.py:97
 
 
 def test_eigvalsh_vs_lapack():
