@@ -941,6 +941,9 @@ extern "C" PQC_API int pqc_program_describe(const pqc_program* prog, char* out, 
       }
     }
   }
+  // the plain run plan (PQC.run), when it differs from what was printed above
+  if (prog->v1_ok && prog->v1_grad_ok)
+    for (int pi : prog->v1_run) s += "RUN PASS " + pass_line(prog->v1_passes[pi]) + "\n";
   if ((int64_t)s.size() + 1 > cap) s.resize((size_t)cap - 1);
   memcpy(out, s.c_str(), s.size() + 1);
   return 0;
