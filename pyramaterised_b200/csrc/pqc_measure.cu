@@ -568,6 +568,53 @@ __global__ void __launch_bounds__(256, 2) k_fidelity_dmma(
       }
 }
 
+// Split-K form for a few pairs of very long vectors: CTA (slice, pair) takes the partial inner
+// product over its K slice; the slices are then added in a fixed order (reproducible).
+__global__ void __launch_bounds__(256) k_fid_splitk(const c128* __restrict__ A, long long SA,
+                                                    const c128* __restrict__ B, long long SB, int n,
+                                                    int tri, int ksplit, double2* __restrict__ part) {
+  __shared__ double red[32];
+  long long p = blockIdx.y, i, j;
+  if (tri) {                                  // itertools.combinations order
+    i = 0;
+    while (p >= SA - 1 - i) { p -= SA - 1 - i; ++i; }
+    j = i + 1 + p;
+  } else {
+    i = p / SB;
+    j = p - i * SB;
+  }
+  const long long D = 1ll << n, len = D / ksplit, k0 = (long long)blockIdx.x * len;
+  const c128* a = A + i * D + k0;
+  const c128* b = B + j * D + k0;
+  double re = 0.0, im = 0.0;
+  for (long long k = threadIdx.x; k < len; k += 256) {
+    const c128 x = a[k], y = b[k];
+    re += x.x * y.x + x.y * y.y;
+    im += x.x * y.y - x.y * y.x;
+  }
+  re = block_sum<256>(re, red);
+  im = block_sum<256>(im, red);
+  if (threadIdx.x == 0) part[(long long)blockIdx.y * ksplit + blockIdx.x] = make_double2(re, im);
+}
+
+__global__ void k_fid_splitk_fin(const double2* __restrict__ part, long long npairs, int ksplit,
+                                 long long bins, double step, unsigned long long* __restrict__ hist,
+                                 double* __restrict__ F) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  double re = 0.0, im = 0.0;
+  for (int k = 0; k < ksplit; ++k) {
+    re += part[p * ksplit + k].x;
+    im += part[p * ksplit + k].y;
+  }
+  const double f = re * re + im * im;
+  if (F) F[p] = f;
+  if (hist) {
+    const long long b = np_hist_bin(f, bins, step);
+    if (b >= 0) atomicAdd(hist + b, 1ull);
+  }
+}
+
 extern "C" int pqc_fidelity_hist(const pqc_c128* d_A, int64_t n_a, const pqc_c128* d_B,
                                  int64_t n_b, int n, int triangular, int64_t bins,
                                  long long* d_hist, double* d_F, void* stream) {
@@ -579,6 +626,31 @@ extern "C" int pqc_fidelity_hist(const pqc_c128* d_A, int64_t n_a, const pqc_c12
   const long long grid = triangular ? nbi * (nbi + 1) / 2 : nbi * nbj;
   if (grid > 0x7fffffffLL) PQC_FAIL(-1, "fidelity grid too large; split the block");
   const char* force = getenv("PQC_FIDELITY");
+  {
+    // a handful of huge states (config 5: 4 GiB each): the pair-tile kernels would run on a few
+    // CTAs, each walking all 2^n amplitudes -- split the inner products over K instead
+    const long long npairs = triangular ? n_a * (n_a - 1) / 2 : n_a * n_b;
+    const bool splitk = (n >= 20 && grid < 64 && npairs <= 65535 && !force) ||
+                        (force && strcmp(force, "splitk") == 0 && n >= 12 && npairs <= 65535);
+    if (splitk && npairs > 0) {
+      cudaStream_t st = (cudaStream_t)stream;
+      int ksplit = 1;
+      while (ksplit < 1024 && (1ll << n) / (2 * ksplit) >= 4096 && npairs * ksplit < 148 * 16)
+        ksplit *= 2;
+      double2* part = nullptr;
+      PQC_CUDA(cudaMallocAsync(&part, sizeof(double2) * npairs * ksplit, st));
+      k_fid_splitk<<<dim3((unsigned)ksplit, (unsigned)npairs), 256, 0, st>>>(
+          (const c128*)d_A, n_a, (const c128*)d_B, n_b, n, triangular, ksplit, part);
+      k_fid_splitk_fin<<<(unsigned)((npairs + 127) / 128), 128, 0, st>>>(
+          part, npairs, ksplit, bins, bins > 0 ? 1.0 / (double)bins : 0.0,
+          (unsigned long long*)d_hist, d_F);
+      g_pqc_launches += 1;
+      const cudaError_t e = cudaGetLastError();
+      cudaFreeAsync(part, st);
+      if (e != cudaSuccess) PQC_FAIL(-2, std::string("fidelity split-K launch: ") + cudaGetErrorString(e));
+      return 0;
+    }
+  }
   const bool use_dmma = n >= 4 && !(force && strcmp(force, "fma") == 0);
   if (use_dmma) {
     static bool attr_set = false;

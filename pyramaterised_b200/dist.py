@@ -105,6 +105,54 @@ def sharded_expressibility(local_states, n_total, hilbert_dim, pair_hist=_engine
     return kl(hist, hilbert_dim)
 
 
+def streamed_rows(n_blocks, rank, world):
+    """Block rows of the streamed pair sweep owned by `rank`: rows are dealt in a zig-zag
+    (r, 2w-1-r, 2w+r, ...) because row I costs n_blocks - I block generations."""
+    return [i for i in range(n_blocks) if (i % (2 * world)) in (rank, 2 * world - 1 - rank)]
+
+
+def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_engine_pair_hist,
+                            kl=None, per_block=None):
+    """Measurements.expressibility for a sample set whose states cannot be resident together
+    (BASELINE config 5: 4 GiB per 28-qubit state).  `run_block(lo, hi)` returns the states of
+    samples [lo, hi) of the ONE global angle stream; two blocks are resident at a time and
+    blocks are regenerated as needed, so every unordered pair is histogrammed exactly once
+    (measure.py:133-159).  Block rows are dealt over the ranks; the int64 histograms are summed
+    with one all-reduce and KL is evaluated on every rank.  `per_block(lo, hi, states)` is called
+    once per owned diagonal block (e.g. to take Meyer-Wallach Q of the same states)."""
+    from . import engine
+    rank, world = rank_world()
+    n_pairs = n_total * (n_total - 1) // 2
+    if n_pairs == 0:
+        return 0
+    bins = engine.n_bins(n_pairs)
+    if bins <= 0:
+        raise ValueError("`bins` must be positive, when an integer")
+    nb = (n_total + block - 1) // block
+    hist = None
+    for i in streamed_rows(nb, rank, world):
+        lo, hi = i * block, min(n_total, (i + 1) * block)
+        A = run_block(lo, hi)
+        if hist is None:
+            hist = torch.zeros((bins,), dtype=torch.int64, device=A.device)
+        if per_block is not None:
+            per_block(lo, hi, A)
+        hist += pair_hist(A, A, True, bins)
+        for j in range(i + 1, nb):
+            B = run_block(j * block, min(n_total, (j + 1) * block))
+            hist += pair_hist(A, B, False, bins)
+            del B
+        del A
+    if hist is None:                      # a rank without rows still joins the all-reduce
+        hist = torch.zeros((bins,), dtype=torch.int64,
+                           device=engine.device() if torch.cuda.is_available() else "cpu")
+    if world > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    if kl is None:
+        return float(engine.kl_haar(hist, hilbert_dim).item())
+    return kl(hist, hilbert_dim)
+
+
 def sharded_qfim_eqd(circuit, global_angles, cutoff, want_qfim=False):
     """update_state + get_effective_quantum_dimension for every row of `global_angles`;
     each rank simulates its block, EQDs (int32) are gathered on every rank."""

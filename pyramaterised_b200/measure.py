@@ -153,6 +153,30 @@ class Measurements:
             return 0
         return self._expr_of_states(states, N)
 
+    def expressibility_streamed(self, sample_N, block, want_Q=False):
+        """expressibility(sample_N) -- and entanglement(sample_N) with want_Q -- for circuits
+        whose states do not fit in memory together (additive API; BASELINE config 5).  Draws the
+        same angle stream, keeps two blocks of `block` states resident and regenerates blocks as
+        needed; under torch.distributed the block rows are dealt over the ranks."""
+        from . import dist as pdist
+        N = 2 ** self.QC.n_qubits
+        if sample_N <= 0:
+            return (0, []) if want_Q else 0
+        ang = self.QC.draw_random(sample_N)
+        Q = {}
+
+        def run_block(lo, hi):
+            return self.QC.program.run(ang[lo:hi], init=self.QC.initial_state.tensor)
+
+        def per_block(lo, hi, states):
+            Q[lo] = engine.meyer_wallach(states).cpu().numpy().tolist()
+
+        e = pdist.streamed_expressibility(run_block, sample_N, block, N,
+                                          per_block=per_block if want_Q else None)
+        if not want_Q:
+            return e
+        return e, [q for lo in sorted(Q) for q in Q[lo]]     # this rank's rows, in sample order
+
     def find_eff_H(self, circuit_f_samples, n):
         """Effective Hilbert-space dimension by minimising expr over N (measure.py:199-224)."""
         F = torch.as_tensor(np.asarray(circuit_f_samples, dtype=np.float64), device=engine.device())

@@ -47,6 +47,10 @@ def _worker(rank, world, port, S, q):
         e = pdist.sharded_expressibility(local, S, 16, pair_hist=_np_pair_hist, kl=_np_kl)
         bins = int((75 / 10000) * (S * (S - 1) // 2))
         h = pdist.sharded_fidelity_hist(allst, bins, _np_pair_hist)
+        es = pdist.streamed_expressibility(
+            lambda a, b: torch.from_numpy(orc.run(specs, 4, ang[a:b])), S, 7, 16,
+            pair_hist=_np_pair_hist, kl=_np_kl)
+        assert abs(es - e) < 1e-15                               # block-streamed == gathered
         qv = torch.tensor([orc.single_Q(s, 4) for s in local.numpy()])
         mean, std = pdist.gathered_mean_std(qv, S)
         q.put((rank, allst.numpy(), e, h.numpy(), mean, std))
@@ -99,3 +103,6 @@ def test_partitions_cover_everything_once():
             assert np.array_equal(seen, np.triu(np.ones((S, S), dtype=int), 1))
             if S >= 8 * world:                                # balanced within ~25 %
                 assert max(work) <= 1.25 * (sum(work) / world) + S
+            for nb in (1, 5, 16):                             # streamed block rows: a partition
+                rows = sorted(i for r in range(world) for i in pdist.streamed_rows(nb, r, world))
+                assert rows == list(range(nb))

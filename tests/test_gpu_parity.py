@@ -473,6 +473,31 @@ def test_fidelity_dmma_matches_fma_and_numpy(monkeypatch):
         assert np.abs(h1.cpu().numpy() - h0.cpu().numpy()).sum() <= 2
 
 
+def test_fidelity_split_k_path(monkeypatch):
+    """A few pairs of very long vectors (config 5) take the split-K path; forced here at n = 13
+    and compared with numpy and with the tensor-core path (same integer histogram)."""
+    rng = np.random.default_rng(5)
+    D = 1 << 13
+    A = rng.normal(size=(5, D)) + 1j * rng.normal(size=(5, D))
+    A /= np.linalg.norm(A, axis=1, keepdims=True)
+    A[1] = A[0]                                          # fidelity exactly 1: last bin
+    B = rng.normal(size=(3, D)) + 1j * rng.normal(size=(3, D))
+    B /= np.linalg.norm(B, axis=1, keepdims=True)
+    tA, tB = torch.as_tensor(A, device="cuda"), torch.as_tensor(B, device="cuda")
+    h0, F0 = engine.fidelity_hist(tA, tB, bins=11, want_F=True)
+    t0, T0 = engine.fidelity_hist(tA, bins=11, want_F=True)
+    monkeypatch.setenv("PQC_FIDELITY", "splitk")
+    h1, F1 = engine.fidelity_hist(tA, tB, bins=11, want_F=True)
+    t1, T1 = engine.fidelity_hist(tA, bins=11, want_F=True)
+    monkeypatch.delenv("PQC_FIDELITY")
+    assert np.abs(F1.cpu().numpy() - np.abs(A.conj() @ B.T) ** 2).max() < 1e-13
+    tri = np.abs(A.conj() @ A.T)[np.triu_indices(5, 1)] ** 2
+    assert np.abs(T1.cpu().numpy() - tri).max() < 1e-13
+    assert np.abs((F1 - F0).cpu().numpy()).max() < 1e-13
+    assert torch.equal(h1, h0) and int(h1.sum()) == 15
+    assert int(t1.sum()) == 10 and int(t1[-1]) >= 1 and np.abs((t1 - t0).cpu().numpy()).sum() <= 2
+
+
 # ---- size-independent properties at BASELINE.json's full sizes ------------------------------
 def test_config2_full_size_properties():
     """generic_HE 10q x 10 layers, S = 1e5: 4 999 950 000 pairs into 37 499 625 bins."""
@@ -544,6 +569,24 @@ def test_config5_size_28_qubit_register_vs_12_qubit_oracle():
         assert abs(Q[s] - 12.0 / 28.0 * orc.single_Q(ref[s], 12)) < ATOL
     _, F = engine.fidelity_hist(st, bins=7, want_F=True)
     assert abs(float(F.reshape(-1)[0]) - abs(np.vdot(ref[0], ref[1])) ** 2) < ATOL
+
+
+def test_streamed_expressibility_equals_resident_form():
+    """The block-streamed expressibility (two blocks resident, blocks regenerated; the form
+    config 5 needs) bins every pair exactly once: same KL and Q list as the resident form."""
+    qc = pyqc.templates.generate_circuit("generic_HE", 10, 4)
+    m = pyqc.measure.Measurements(qc)
+    reseed()
+    e0 = m.expressibility(333)
+    reseed()
+    q0 = m.entanglement(333)
+    for block in (50, 333, 1000):
+        reseed()
+        e1, q1 = m.expressibility_streamed(333, block, want_Q=True)
+        assert e1 == e0
+        assert q1 == q0
+    reseed()
+    assert m.expressibility_streamed(1, 8) == 0
 
 
 def test_config4_full_size_stabilizer_states_have_zero_magic():

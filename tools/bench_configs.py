@@ -105,6 +105,25 @@ def c5(n=28, p=20, S=2):
             "Q": Q.cpu().numpy().tolist()}
 
 
+def c5x(n=28, p=20, S=17, block=6):
+    """Config 5 shape end to end at a sample count that finishes in seconds: block-streamed
+    expressibility + entanglement (two blocks of `block` 4 GiB states resident)."""
+    qc = pyqc.templates.generate_circuit("NPQC", n, p)
+    m = pyqc.measure.Measurements(qc)
+    reseed()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e, Q = m.expressibility_streamed(S, block, want_Q=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    nb = (S + block - 1) // block
+    gens = sum(min(S, (i + 1) * block) - i * block + sum(min(S, (j + 1) * block) - j * block
+               for j in range(i + 1, nb)) for i in range(nb))
+    return {"config": f"C5 streamed NPQC {n}q x {p} layers, S={S}, block={block}: expressibility + entanglement",
+            "seconds": dt, "state_generations": gens, "pairs": S * (S - 1) // 2,
+            "bins": engine.n_bins(S * (S - 1) // 2), "expr": e, "mean_Q": float(np.mean(Q))}
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c1", "c2", "c4", "c5"]
     out = []
@@ -113,5 +132,6 @@ if __name__ == "__main__":
         elif w.startswith("c2"): r = c2(int(w.split(":")[1]) if ":" in w else 100000)
         elif w == "c4": r = c4()
         elif w.startswith("c3"): r = c3_apply(w.split(":")[1] if ":" in w else "TFIM")
+        elif w.startswith("c5x"): r = c5x(int(w.split(":")[1]) if ":" in w else 28)
         elif w.startswith("c5"): r = c5(int(w.split(":")[1]) if ":" in w else 28)
         print(json.dumps(r), flush=True)
