@@ -594,12 +594,7 @@ struct Builder {
         ok = ok && g >= 0 && (si > 0 || g == 0);
         for (int k = 0; k < 4 && ok; ++k) ok = d.rb[k] == d.rb[0] + k;
         ok = ok && d.pad == 0 && nflat + d.mop_end - d.mop_begin <= SEQ_MAX_OPS;
-        if (!ok) {
-          if (getenv("PQC_PLAN_DEBUG"))
-            fprintf(stderr, "seq: sweep %d rb %d..%d pad %d nops %d rejected\n", si, d.rb[0], d.rb[3],
-                    d.pad, d.mop_end - d.mop_begin);
-          break;
-        }
+        if (!ok) break;
         ps.seq.geom[si] = g;
         ps.seq.off[si] = nflat;
         ps.seq.nops[si] = 0;
@@ -637,8 +632,6 @@ struct Builder {
           } else if (m.kind == PQC_OP_IDENT) {
             continue;
           } else {
-            if (getenv("PQC_PLAN_DEBUG"))
-              fprintf(stderr, "seq: sweep %d op kind %d k0 %d k1 %d rejected\n", si, m.kind, m.k0, m.k1);
             ok = false;
           }
           ps.seq.ops[nflat++] = f;
