@@ -170,6 +170,7 @@ struct FastPlan {
 #define SEQ_MAX_SPAWN 8
 struct SeqPlan {
   int nsw;
+  int has_diag;                      // any R_z / CZ op: the kernel instantiation that folds them
   int geom[SEQ_MAX_SWEEPS];          // registers hold tile positions 0: 8-11, 1: 0-3, 2: 4-7
   int off[SEQ_MAX_SWEEPS], nops[SEQ_MAX_SWEEPS];   // the sweep's ops: ops[off .. off + nops)
   // RXY: subk = ka * 4 + kb (ka < kb), t[0] = trig slot

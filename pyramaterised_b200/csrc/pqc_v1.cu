@@ -618,11 +618,13 @@ struct Builder {
             f.t[0] = m.trig;
             f.subk = std::min(m.k0, m.k1) * 4 + std::max(m.k0, m.k1);
           } else if (m.kind == PQC_OP_RZ) {
+            ps.seq.has_diag = 1;
             f.t[0] = m.trig;
             f.t[1] = m.k0;
             f.t[2] = m.l0;
             f.t[3] = m.b0;
           } else if (m.kind == PQC_OP_CZ) {
+            ps.seq.has_diag = 1;
             f.t[0] = m.k0;
             f.t[1] = m.k1;
             f.t[2] = m.l0;
@@ -1852,7 +1854,7 @@ __device__ __forceinline__ void op_xy(c128 (&a)[16], double c, double s) {
 // thread-level phase T, one phase per register bit (bit = 1 takes the conjugate), a 16-bit sign
 // mask -- and applied together: at most 16 complex multiplications per touched register bit
 // whatever the number of gates.  `base` = the thread's tile-local index (register bits zero).
-template <bool GEN, int RN, int NX, int NY>
+template <bool GEN, bool DIAG, int RN, int NX, int NY>
 __device__ __forceinline__ void seq_ops(c128 (&a)[16], const SeqArgs& A, int slot, int vx, int vy,
                                         const double2* trig, const uint32_t (*s_wn)[3][16],
                                         const uint32_t* s_wb, int gen, double& fscale,
@@ -1860,7 +1862,7 @@ __device__ __forceinline__ void seq_ops(c128 (&a)[16], const SeqArgs& A, int slo
   const int nops = A.plan.nops[slot], off = A.plan.off[slot];
   for (int oi = 0; oi < nops; ++oi) {
     const int kind = A.plan.ops[off + oi].kind;
-    if (kind == PQC_OP_RZ || kind == PQC_OP_CZ) {
+    if (DIAG && (kind == PQC_OP_RZ || kind == PQC_OP_CZ)) {
       // ---- a run of diagonal ops: accumulate, then apply once
       double tc = 1.0, ts = 0.0;                  // thread-level phase (tc + i ts)
       double pc[4] = {1.0, 1.0, 1.0, 1.0}, pn[4] = {0.0, 0.0, 0.0, 0.0};   // bit k = 1: (pc + i pn)
@@ -1987,7 +1989,7 @@ __device__ __forceinline__ void seq_ops(c128 (&a)[16], const SeqArgs& A, int slo
   }
 }
 
-template <bool GEN>
+template <bool GEN, bool DIAG>
 __global__ void __launch_bounds__(256, 2) k_layer_seq(const SeqArgs A) {
   extern __shared__ __align__(16) c128 lp_sm[];
   double2* trig = reinterpret_cast<double2*>(lp_sm + 4096);
@@ -2086,11 +2088,11 @@ __global__ void __launch_bounds__(256, 2) k_layer_seq(const SeqArgs A) {
       }
     }
     if (g == 0)
-      seq_ops<GEN, 2, 0, 1>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale, (uint32_t)tid, tbase);
+      seq_ops<GEN, DIAG, 2, 0, 1>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale, (uint32_t)tid, tbase);
     else if (g == 1)
-      seq_ops<GEN, 0, 1, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale, (uint32_t)tid << 4, tbase);
+      seq_ops<GEN, DIAG, 0, 1, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale, (uint32_t)tid << 4, tbase);
     else
-      seq_ops<GEN, 1, 0, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale,
+      seq_ops<GEN, DIAG, 1, 0, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale,
                             (uint32_t)lo | ((uint32_t)hi << 8), tbase);
     if (s + 1 == nsw && g != 1 && !A.staged) break;   // the registers go straight to global memory
     if (s + 1 == nsw && fscale != 1.0) op_scale(a, fscale);
@@ -2892,14 +2894,19 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
     }
     static bool qattr = false;
     if (!qattr) {
-      PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       qattr = true;
     }
     const size_t qsmem = 4096 * sizeof(c128) + (size_t)a.ntrig * sizeof(double2);
     const int hq = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st);
-    if (a.nspawn > 0) k_layer_seq<true><<<(unsigned)grid, 256, qsmem, st>>>(f);
-    else k_layer_seq<false><<<(unsigned)grid, 256, qsmem, st>>>(f);
+    const bool sp = a.nspawn > 0, dg = f.plan.has_diag != 0;
+    if (sp && dg) k_layer_seq<true, true><<<(unsigned)grid, 256, qsmem, st>>>(f);
+    else if (sp) k_layer_seq<true, false><<<(unsigned)grid, 256, qsmem, st>>>(f);
+    else if (dg) k_layer_seq<false, true><<<(unsigned)grid, 256, qsmem, st>>>(f);
+    else k_layer_seq<false, false><<<(unsigned)grid, 256, qsmem, st>>>(f);
     pqc_prof_launch_end(hq, st);
     PQC_LAUNCH_CHECK();
     return 0;
