@@ -644,7 +644,7 @@ extern "C" int pqc_fidelity_hist(const pqc_c128* d_A, int64_t n_a, const pqc_c12
       k_fid_splitk_fin<<<(unsigned)((npairs + 127) / 128), 128, 0, st>>>(
           part, npairs, ksplit, bins, bins > 0 ? 1.0 / (double)bins : 0.0,
           (unsigned long long*)d_hist, d_F);
-      g_pqc_launches += 1;
+      g_pqc_launches += 2;
       const cudaError_t e = cudaGetLastError();
       cudaFreeAsync(part, st);
       if (e != cudaSuccess) PQC_FAIL(-2, std::string("fidelity split-K launch: ") + cudaGetErrorString(e));
