@@ -72,7 +72,7 @@ def c3_apply(kind="TFIM", n=16, p=16, S=4096):
     engine.profile_begin()
     ms, _ = timed(lambda: qc.program.run(ang, init=qc.initial_state.tensor, out=out))
     prof = engine.profile_end()
-    L = p + 1 if kind == "TFIM" else p
+    L = p + 1 if kind in ("TFIM", "NPQC") else p
     return {"config": f"C3 apply-only {kind} {n}q x {p} layers, S={S}", "ms": ms,
             "states_per_s": S / (ms / 1e3), "passes": qc.program.n_passes,
             "algorithmic_GBps_layers": L * 2 * 16 * 2 ** n * S / (ms / 1e3) / 1e9,
@@ -131,7 +131,10 @@ if __name__ == "__main__":
         if w == "c1": r = c1()
         elif w.startswith("c2"): r = c2(int(w.split(":")[1]) if ":" in w else 100000)
         elif w == "c4": r = c4()
-        elif w.startswith("c3"): r = c3_apply(w.split(":")[1] if ":" in w else "TFIM")
+        elif w.startswith("c3"):                      # c3[:KIND[:n[:p[:S]]]]
+            f = w.split(":")
+            r = c3_apply(f[1] if len(f) > 1 else "TFIM", int(f[2]) if len(f) > 2 else 16,
+                         int(f[3]) if len(f) > 3 else 16, int(f[4]) if len(f) > 4 else 4096)
         elif w.startswith("c5x"): r = c5x(int(w.split(":")[1]) if ":" in w else 28)
         elif w.startswith("c5"): r = c5(int(w.split(":")[1]) if ":" in w else 28)
         print(json.dumps(r), flush=True)
