@@ -165,8 +165,8 @@ struct FastPlan {
 // "Layer sequence" path (k_layer_seq): the same idea for passes that visit the aligned nibbles
 // in ANY order and up to SEQ_MAX_SWEEPS times (the XXZ template's XY bonds alternate between
 // nibbles), and whose ops may also be XY pair rotations (PQC_K_RXY) on two register bits.
-#define SEQ_MAX_SWEEPS 6
-#define SEQ_MAX_OPS 72               // per pass, all sweeps together
+#define SEQ_MAX_SWEEPS 32
+#define SEQ_MAX_OPS 400              // per pass, all sweeps together
 #define SEQ_MAX_SPAWN 8
 struct SeqPlan {
   int nsw;
