@@ -591,7 +591,7 @@ struct Builder {
         const SweepD& d = sweeps[ps.sweep_off + si];
         int g = -1;
         if (d.rb[0] == 8) g = 0; else if (d.rb[0] == 0) g = 1; else if (d.rb[0] == 4) g = 2;
-        ok = ok && g >= 0 && (si > 0 || g == 0);
+        ok = ok && g >= 0;
         for (int k = 0; k < 4 && ok; ++k) ok = d.rb[k] == d.rb[0] + k;
         ok = ok && d.pad == 0 && nflat + d.mop_end - d.mop_begin <= SEQ_MAX_OPS;
         if (!ok) break;
@@ -2872,7 +2872,8 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
       f.spawn_ci[k] = a.hprog->gens[a.spawn_goff[k]].im;
     }
     f.plan = a.hpass->seq;
-    f.staged = a.hpass->direct_ok ? 0 : 1;
+    // direct ends need tile positions 0-2 on amplitude bits 0-2 and a first sweep on positions 8-11
+    f.staged = (a.hpass->direct_ok && f.plan.geom[0] == 0) ? 0 : 1;
     if (f.staged) {
       // thread bits 0-3 -> the tile positions of amplitude bits 0-3; the other 8 positions in
       // ascending order -> thread bits 4-7, then register bits 0-3
