@@ -201,11 +201,14 @@ def run_b200(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    out_fd = 1
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's own log lines (version banner, INFO) go
-        # to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries exactly one JSON line: whatever the libraries print to fd 1 (NCCL's
+        # version banner, INFO lines) is routed to stderr; the line itself goes to the saved fd
+        sys.stdout.flush()
+        out_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -341,7 +344,8 @@ def run_b200(a):
             raise SystemExit(f"bench: GPU QFIM differs from the oracle (rel {err:.3e})")
         line["cpu_baseline"] = cpu
     if rank == 0:
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
