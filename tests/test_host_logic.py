@@ -175,3 +175,30 @@ def test_planner_meet_in_the_middle_qfim_plan():
     assert "BIDIR" not in pyqc.templates.generate_circuit("fsim", 12, 2).program.describe()
     # too few parameters / qubits: forward plan
     assert "BIDIR" not in pyqc.templates.generate_circuit("TFIM", 8, 4).program.describe()
+
+
+def test_planner_layer_sequence_plans():
+    """XXZ (XY pair rotations, nibble sweeps in any order, staged ends) and NPQC (runs of R_z /
+    CZ, many layers per pass) passes are lowered to SeqPlans for k_layer_seq (describe: fast=2);
+    TFIM keeps the layer pass (fast=1); CNOT-chain circuits stay on the generic kernel."""
+    import re
+
+    def tally(kind, n, p, prefix):
+        d = pyqc.templates.generate_circuit(kind, n, p, shuffle=False).program.describe()
+        lines = [l for l in d.splitlines() if l.startswith(prefix)]
+        return {k: sum(("fast=%d" % k) in l for l in lines) for k in (0, 1, 2)}, lines
+
+    xxz, lines = tally("XXZ", 16, 16, "PASS")
+    assert xxz[0] == 0 and xxz[1] == 0 and xxz[2] == len(lines) > 40
+    assert any("direct=0/0" in l for l in lines)               # staged ends are covered
+    run, _ = tally("XXZ", 16, 16, "RUN PASS")
+    assert run[0] == 0 and run[2] >= 40
+    npqc, lines = tally("NPQC", 28, 20, "RUN PASS")
+    assert npqc[0] == 0 and npqc[1] + npqc[2] == len(lines) == 41
+    packed, lines = tally("NPQC", 16, 16, "RUN PASS")           # 16 layers in 5 passes
+    assert packed[0] == 0 and len(lines) <= 6
+    assert max(int(re.search(r"mops=(\d+)", l).group(1)) for l in lines) > 72
+    tfim, lines = tally("TFIM", 16, 16, "PASS")
+    assert tfim[1] == len(lines) and tfim[2] == 0
+    he, _ = tally("generic_HE", 14, 2, "PASS")
+    assert he[2] == 0                                           # CNOT permutations: generic kernel
