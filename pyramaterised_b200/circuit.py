@@ -185,7 +185,7 @@ class PQC():
             angles = self.draw_random(S)
         P = self.n_true_params
         if P == 0:
-            n = S if S is not None else 1
+            n = S if S is not None else (len(angles) if hasattr(angles, "__len__") else 1)
             return self.program.run(None, init=self.initial_state.tensor).expand(n, -1).contiguous()
         out = self.program.run(angles, init=self.initial_state.tensor)
         if not hasattr(angles, "is_cuda") and len(angles):

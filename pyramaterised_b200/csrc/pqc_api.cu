@@ -253,6 +253,7 @@ extern "C" int pqc_program_destroy(pqc_program* prog) {
   if (prog->d_sweeps) cudaFree(prog->d_sweeps);
   if (prog->d_tjobs) cudaFree(prog->d_tjobs);
   if (prog->d_zz) cudaFree(prog->d_zz);
+  if (prog->d_pipe) cudaFree(prog->d_pipe);
   if (prog->d_trig) cudaFree(prog->d_trig);
   delete prog;
   return 0;

@@ -214,7 +214,8 @@ int pqc_program_upload(const pqc_program* cprog) {
   };
   if (up(prog->h_dops, &prog->d_ops) || up(prog->gens, &prog->d_gens) ||
       up(prog->h_mops, &prog->d_mops) || up(prog->h_sweeps, &prog->d_sweeps) ||
-      up(prog->h_tjobs, &prog->d_tjobs) || up(prog->h_zz, &prog->d_zz))
+      up(prog->h_tjobs, &prog->d_tjobs) || up(prog->h_zz, &prog->d_zz) ||
+      up(prog->h_pipe, &prog->d_pipe))
     return -2;
   prog->uploaded = true;
   return 0;

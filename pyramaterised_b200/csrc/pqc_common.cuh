@@ -181,11 +181,71 @@ struct SeqPlan {
   uint32_t wo[FAST_MAX_WT][PQC_MAX_QUBITS - 12];
 };
 
+// "Tile pipe" (k_tile_pipe, pqc_pipe.cu): the persistent, TMA-fed form of the pass kernels.
+// One CTA per SM walks over (vector, tile) work items; tiles arrive in a ring of TP_NBUF
+// shared-memory buffers by bulk async copies (cp.async.bulk + mbarrier) issued ahead of the two
+// consumer groups, so HBM loads never wait for a free register file.  A pass is a list of
+// sweeps with RUNTIME geometry: any 4 of the 12 tile positions in registers, thread bits on the
+// other 8, shared-memory slots an affine function of the logical tile index.  X / CNOT are pure
+// relabelings of that index (they change the planner's slot tables, not the kernel).
+#define TP_MAX_SWEEPS 24
+#define TP_MAX_OPS 320
+#define TP_MAX_TRIG 320
+#define TP_MAX_SPAWN 8
+#define TP_NBUF 3
+struct TPOp {              // 16 bytes
+  uint8_t kind;            // pqc_opcode or PQC_K_*
+  uint8_t sub;             // LAYER_*4: 2 bits per register bit: 0 none, 1 rotation, 2 Hadamard
+  uint8_t a, b;            // RXY: a = ka * 4 + kb;  RZ: a = register bit | 0xff, b = tile position | 0xff
+                           // CZ: a, b = register bits | 0xff
+  uint16_t t[4];           // trig slots (LAYER_*4, RXY, RZ: t[0]; ZZSUM: t[0] = first table slot)
+                           // RZ: t[1] = global bit;  CZ: t[0], t[1] = tile positions | 0xffff, t[2], t[3] = global bits
+  uint8_t wt, nterms, spawn, pad;   // ZZSUM / GEN: linear-form table, term count; GEN: spawn index
+};
+struct TPSweep {
+  uint16_t rd_t[2][16];    // slot of the thread part when loading: rd_t[0][tid & 15] ^ rd_t[1][tid >> 4]
+  uint16_t wr_t[2][16];    // ... when storing back (differs from rd_t only in the re-swizzling sweep 0)
+  uint16_t lidx[2][16];    // logical tile index of the thread part (register bits zero)
+  uint16_t rd_r[4], wr_r[4];   // slot masks of the 4 register bits
+  uint8_t rpos[4];         // tile positions of the register bits
+  uint16_t op_begin, op_end;
+};
+struct PipePlan {
+  int nsw, nops, ntrig, nwt;
+  int low_run;             // tile positions 0 .. low_run-1 are the amplitude bits 0 .. low_run-1
+  int lbit[12];            // amplitude bit of tile position p
+  // tile load (cp.async): thread bits 0-3 sit on the tile positions of amplitude bits 0-3
+  uint32_t ld_amp[2][16];  // amplitude offset of the thread part: ld_amp[0][tid & 15] | ld_amp[1][tid >> 4]
+  uint32_t ld_r[4];        //   and of the 4 bits walked by the copy index j
+  uint16_t ld_slot[2][16]; // shared-memory slot of the thread part
+  uint16_t ld_sr[4];
+  uint32_t st_t[2][16];    // last sweep, direct store: amplitude offset of the thread part
+  uint32_t st_r[4];        //   and of the register bits
+  uint32_t wn[FAST_MAX_WT][3][16];
+  uint32_t wo[FAST_MAX_WT][PQC_MAX_QUBITS - 12];
+  TPSweep sw[TP_MAX_SWEEPS];
+  TPOp ops[TP_MAX_OPS];
+};
+struct PipeArgs {
+  const c128* src;
+  c128* dst;
+  const double2* gtrig;
+  int tstride, toff;
+  int n;
+  int obit[PQC_MAX_QUBITS];
+  int slots_total, active, nspawn;
+  int spawn_slot[TP_MAX_SPAWN];
+  double spawn_cr[TP_MAX_SPAWN], spawn_ci[TP_MAX_SPAWN];
+  long long n_items;       // vectors (samples x (active + nspawn))
+  const PipePlan* plan;    // device copy
+};
+
 struct V1Pass {
   bool fast_ok = false;
   FastPlan fast;
   bool seq_ok = false;
   SeqPlan seq;
+  int pipe_idx = -1;             // index into pqc_program::h_pipe, -1: not convertible
 
   int tb, low_run;
   int lbit[V1_LOCAL_BITS];
@@ -241,6 +301,8 @@ struct pqc_program {
   std::vector<TrigJob> h_tjobs;
   std::vector<uint32_t> h_zz;                 // linear-form tables (V1_WTAB words each)
   std::vector<DOp> h_dops;
+  std::vector<PipePlan> h_pipe;              // tile-pipe form of the passes that have one
+  PipePlan* d_pipe = nullptr;
   bool uploaded = false;
   MOp* d_mops = nullptr;
   SweepD* d_sweeps = nullptr;
@@ -329,6 +391,9 @@ int pqc_v1_gram_qfim(const pqc_program* prog, const c128* buf, long long S, c128
 int pqc_v1_gram_qfim2(const pqc_program* prog, const c128* buf, int slots1, int M1,
                       const c128* buf2, int slots2, const int* d_inv, long long S, c128* d_gpart,
                       double* d_F, cudaStream_t st);
+bool pqc_pipe_build(const V1Pass& ps, int n, PipePlan& out);
+int pqc_pipe_launch(const PipeArgs& a, const PipePlan& hplan, cudaStream_t st);
+bool pqc_pipe_enabled();
 int pqc_prof_launch_begin(double bytes, cudaStream_t st);
 void pqc_prof_launch_end(int h, cudaStream_t st);
 int pqc_pauli_apply_slots(const c128* src, c128* dst, int n, long long S, int slots_total,

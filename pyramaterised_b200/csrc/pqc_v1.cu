@@ -21,6 +21,7 @@
 #include <cstring>
 
 #include "pqc_common.cuh"
+#include "pqc_ops.cuh"
 
 bool pqc_use_v0() {
   static int v = -1;
@@ -851,6 +852,16 @@ int pqc_plan_v1(pqc_program* prog) {
     prog->v1_grad_ok = true;
   }
 
+  // tile-pipe form of every pass that has one (pqc_pipe.cu)
+  prog->h_pipe.clear();
+  for (V1Pass& ps : prog->v1_passes) {
+    PipePlan pp;
+    ps.pipe_idx = -1;
+    if (pqc_pipe_build(ps, n, pp)) {
+      ps.pipe_idx = (int)prog->h_pipe.size();
+      prog->h_pipe.push_back(pp);
+    }
+  }
   prog->h_mops = mops;
   prog->h_sweeps = sweeps;
   prog->h_tjobs = tjobs;
@@ -1037,78 +1048,6 @@ struct V1Args {
   const pqc_program* hprog;
 };
 
-__device__ __forceinline__ uint32_t swz(uint32_t i) {
-  return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u);
-}
-
-// ---- pair-mixing micro-ops on the 16 register amplitudes ---------------------------------
-// Rotations are applied in tangent form: rx = c [[1, -i t], [-i t, 1]], ry = c [[1, -t], [t, 1]]
-// with t = tan(angle/2): two FMAs per amplitude instead of four.  The scalar c factors of a
-// layer op are multiplied in once afterwards (op_scale).  t is finite for every double angle
-// (cos never rounds to exactly 0 at pi/2: |c| >= 6e-17) and the result carries the usual
-// relative rounding error of c x + s y because x + t y is computed with one rounding and the
-// final multiplication by c is exact to one more.
-template <int K>
-__device__ __forceinline__ void op_rx_t(c128 (&a)[16], double t) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    if (j & (1 << K)) continue;
-    const c128 x = a[j], y = a[j | (1 << K)];
-    a[j] = make_double2(fma(t, y.y, x.x), fma(-t, y.x, x.y));
-    a[j | (1 << K)] = make_double2(fma(t, x.y, y.x), fma(-t, x.x, y.y));
-  }
-}
-template <int K>
-__device__ __forceinline__ void op_ry_t(c128 (&a)[16], double t) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    if (j & (1 << K)) continue;
-    const c128 x = a[j], y = a[j | (1 << K)];
-    a[j] = make_double2(fma(-t, y.x, x.x), fma(-t, y.y, x.y));
-    a[j | (1 << K)] = make_double2(fma(t, x.x, y.x), fma(t, x.y, y.y));
-  }
-}
-// Hadamard without its 1/sqrt(2): (x + y, x - y)
-template <int K>
-__device__ __forceinline__ void op_h_u(c128 (&a)[16]) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    if (j & (1 << K)) continue;
-    const c128 x = a[j], y = a[j | (1 << K)];
-    a[j] = make_double2(x.x + y.x, x.y + y.y);
-    a[j | (1 << K)] = make_double2(x.x - y.x, x.y - y.y);
-  }
-}
-__device__ __forceinline__ void op_scale(c128 (&a)[16], double f) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) a[j] = make_double2(a[j].x * f, a[j].y * f);
-}
-
-// generic symmetric two-bit rotation: even-parity pair (00,11) by (ce, se), odd-parity pair
-// (01,10) by (co, so), each as [[c, -i s], [-i s, c]]; optional phase (pc - i ps) on |11>.
-template <int KA, int KB>
-__device__ __forceinline__ void op_pair(c128 (&a)[16], double ce, double se, double co, double so,
-                                        bool even, bool ph, double pc, double psn) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    if (j & ((1 << KA) | (1 << KB))) continue;
-    const int j01 = j | (1 << KA), j10 = j | (1 << KB), j11 = j01 | j10;
-    {
-      const c128 x = a[j01], y = a[j10];
-      a[j01] = make_double2(co * x.x + so * y.y, co * x.y - so * y.x);
-      a[j10] = make_double2(co * y.x + so * x.y, co * y.y - so * x.x);
-    }
-    if (even) {
-      const c128 x = a[j], y = a[j11];
-      a[j] = make_double2(ce * x.x + se * y.y, ce * x.y - se * y.x);
-      a[j11] = make_double2(ce * y.x + se * x.y, ce * y.y - se * x.x);
-    }
-    if (ph) {
-      const c128 z = a[j11];
-      a[j11] = make_double2(z.x * pc + z.y * psn, z.y * pc - z.x * psn);
-    }
-  }
-}
 
 // initial state into slot 0 of every sample (mode 1 |0..0>, 2 broadcast, 3 per sample)
 __global__ void __launch_bounds__(256) k_init_slot0(c128* __restrict__ buf, int mode,
@@ -1127,10 +1066,6 @@ __global__ void __launch_bounds__(256) k_init_slot0(c128* __restrict__ buf, int 
   }
 }
 
-#define SEL4R(j, a0, a1, a2, a3) \
-  ((((j)&1) ? (a0) : 0u) | (((j)&2) ? (a1) : 0u) | (((j)&4) ? (a2) : 0u) | (((j)&8) ? (a3) : 0u))
-#define XSEL4R(j, a0, a1, a2, a3) \
-  ((((j)&1) ? (a0) : 0u) ^ (((j)&2) ? (a1) : 0u) ^ (((j)&4) ? (a2) : 0u) ^ (((j)&8) ? (a3) : 0u))
 #define V1_MAX_MOPS 160
 #define V1_MAX_SWEEPS 32
 
@@ -1837,18 +1772,6 @@ struct SeqArgs {
   SeqPlan plan;
 };
 
-// rotation of the odd-parity pair (01, 10) of register bits KA < KB by [[c, -i s], [-i s, c]]
-template <int KA, int KB>
-__device__ __forceinline__ void op_xy(c128 (&a)[16], double c, double s) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    if (j & ((1 << KA) | (1 << KB))) continue;
-    const int j01 = j | (1 << KA), j10 = j | (1 << KB);
-    const c128 x = a[j01], y = a[j10];
-    a[j01] = make_double2(c * x.x + s * y.y, c * x.y - s * y.x);
-    a[j10] = make_double2(c * y.x + s * x.y, c * y.y - s * x.x);
-  }
-}
 
 // Consecutive diagonal ops of a sweep (R_z phases, CZ signs) are accumulated per thread --
 // thread-level phase T, one phase per register bit (bit = 1 takes the conjugate), a 16-bit sign
@@ -2424,37 +2347,6 @@ static int gram_ksplit(int n) {
 
 // SMALL: P <= 32 (at most 4 row blocks, 10 tiles, one tile group of 8 K-share warps): the 4
 // row-block fragments of a k4-step are loaded once and feed all tiles from registers.
-__device__ __forceinline__ void gr_mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(
-                   (unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void gr_mbar_expect(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
-                   (unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void gr_mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(
-                   (unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void gr_mbar_wait(uint64_t* bar, unsigned parity) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "GR_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra GR_DONE;\n"
-      "bra GR_WAIT;\n"
-      "GR_DONE:\n"
-      "}\n" ::"r"(a), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void gr_bulk_load(void* dst, const void* src, unsigned bytes,
-                                             uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes),
-      "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
 
 // SMALL: P <= 32 (at most 4 row blocks, 10 tiles, one tile group of 8 K-share warps): the 4
 // row-block fragments of a k4-step are loaded once and feed all tiles from registers.
@@ -2797,6 +2689,30 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
   const long long grid = groups << (a.n - a.tb);
   if (grid <= 0) return 0;
   if (grid > 0x7fffffffLL) PQC_FAIL(-1, "pass grid too large; split the batch");
+  if (a.hpass && a.hpass->pipe_idx >= 0 && a.npartners == 0 && a.nspawn <= TP_MAX_SPAWN &&
+      a.items_log2 == 0 && fast_enabled() && pqc_pipe_enabled() &&
+      (a.hpass->fast_ok || seq_enabled())) {
+    PipeArgs f;
+    memset(&f, 0, sizeof(f));
+    f.src = a.src;
+    f.dst = a.dst;
+    f.gtrig = a.gtrig;
+    f.tstride = a.tstride;
+    f.toff = a.toff;
+    f.n = a.n;
+    memcpy(f.obit, a.obit, sizeof(f.obit));
+    f.slots_total = a.slots_total;
+    f.active = a.active;
+    f.nspawn = a.nspawn;
+    for (int k = 0; k < a.nspawn; ++k) {
+      f.spawn_slot[k] = a.spawn_slot[k];
+      f.spawn_cr[k] = a.hprog->gens[a.spawn_goff[k]].re;
+      f.spawn_ci[k] = a.hprog->gens[a.spawn_goff[k]].im;
+    }
+    f.n_items = a.n_items;
+    f.plan = a.hprog->d_pipe + a.hpass->pipe_idx;
+    return pqc_pipe_launch(f, a.hprog->h_pipe[a.hpass->pipe_idx], st);
+  }
   if (a.hpass && a.hpass->fast_ok && a.npartners == 0 && a.nspawn <= FAST_MAX_SPAWN &&
       fast_enabled()) {
     FastArgs f;

@@ -51,11 +51,10 @@ class Measurements:
         """sample_N x QC.run("random") (measure.py:132,247,356,407) as one device batch."""
         if sample_N <= 0:
             return None
-        if hasattr(self.QC, "run_batch"):
-            try:
-                return self.QC.run_batch("random", sample_N)
-            except AttributeError:
-                pass          # stand-in circuits that subclass PQC without calling __init__
+        # stand-in circuits (tests.py:12-60) subclass PQC without calling __init__: they have
+        # run() but no gate list, and must be asked BEFORE any angle is drawn from the module RNG
+        if hasattr(self.QC, "run_batch") and hasattr(self.QC, "gates") and hasattr(self.QC, "_program"):
+            return self.QC.run_batch("random", sample_N)
         return _stack([self.QC.run("random") for _ in range(sample_N)])
 
     # ---- QFIM (measure.py:33-99) -------------------------------------------------------------
@@ -248,6 +247,8 @@ class Measurements:
 
     def entropy_of_magic(self, sample_N):
         states = self._random_states(sample_N)
+        if states is None:                 # np.mean([]) in the reference (measure.py:356-359)
+            return np.mean([])
         magics = engine.magic(states, (2.0,))[0].cpu().numpy()
         return np.mean(magics)
 

@@ -8,6 +8,7 @@ import pytest
 import torch
 
 import cases
+import cases_r2
 import pyramaterised_b200 as pyqc
 from helpers import oracle_case, specs_from_circuit
 from oracle import pqc_oracle as orc
@@ -358,6 +359,37 @@ def test_layer_sequence_path_matches_generic_sweep_kernel(kind, n, p, monkeypatc
     assert rel(F[0].cpu().numpy(), orc.qfi(ref[0], g1[0])) < RTOL
 
 
+@pytest.mark.parametrize("kind,n,p,S", [("TFIM", 16, 3, 37), ("TFIM", 13, 4, 5), ("TFIM_modified", 14, 2, 3),
+                                        ("XXZ", 16, 2, 19), ("XXZ", 13, 3, 3), ("NPQC", 14, 3, 3),
+                                        ("NPQC", 17, 2, 3), ("TFIM", 20, 1, 2)])
+def test_tile_pipe_kernel_matches_per_tile_kernels_bitwise(kind, n, p, S, monkeypatch):
+    """k_tile_pipe (persistent CTAs, TMA-fed ring of tiles, runtime sweep geometry) runs the same
+    plans (PQC_PIPE=1) with the same arithmetic in the same order as k_layer_pass / k_layer_seq:
+    states and derivative states must be BIT-identical, QFIMs too; row 0 agrees with the oracle."""
+    qc = pyqc.templates.generate_circuit(kind, n, p, shuffle=False)
+    specs, init = orc.generate_circuit(kind, n, p)
+    ang = np.random.default_rng(5 * n + p).random((S, orc.n_params(specs))) * 2 * np.pi
+    l0 = engine.launch_count()
+    monkeypatch.setenv("PQC_PIPE", "1")
+    st = qc.run_batch(ang)
+    F = qc.qfim_batch(ang)
+    gr = qc.program.gradients(ang[:3], init=qc.initial_state.tensor)
+    monkeypatch.setenv("PQC_PIPE", "0")
+    st0 = qc.run_batch(ang)
+    F0 = qc.qfim_batch(ang)
+    gr0 = qc.program.gradients(ang[:3], init=qc.initial_state.tensor)
+    monkeypatch.delenv("PQC_PIPE")
+    assert engine.launch_count() > l0
+    assert torch.equal(torch.view_as_real(st), torch.view_as_real(st0))
+    assert torch.equal(torch.view_as_real(gr), torch.view_as_real(gr0))
+    assert torch.equal(F, F0)
+    ref = orc.run(specs, n, ang[:1], init)
+    assert np.abs(st[:1].cpu().numpy() - ref).max() < ATOL
+    if n <= 16:
+        g1 = orc.gradients(specs, n, ang[:1], init)
+        assert rel(F[0].cpu().numpy(), orc.qfi(ref[0], g1[0])) < RTOL
+
+
 def test_ragged_and_empty_batches():
     """Batch edges: a QFIM batch that does not fill its last 256-set chunk, a single row, an
     empty batch; every row must equal the one-row call bit for bit (fixed summation orders)."""
@@ -681,6 +713,55 @@ def test_example_script_flow():
     out_magic = cap.train(method="BFGS", angles=ang)
     assert out_magic[2][-1] >= out[2][-1] - 1e-6           # optimising for magic finds more magic
     assert "4 qubit, 3 layer deep PQC" in repr(ex)
+
+
+def test_find_overparam_point_matches_reference(golden_r2, capsys):
+    """measure.py:101-121: layers are appended until the QFIM rank stops growing; the count, the
+    printed rank sequence and the circuit it leaves behind equal the reference's (module RNG at
+    seed 1, as recorded by tests/golden/make_golden_r2.py)."""
+    qc = cases_r2.build_overparam3(pyqc)
+    m = pyqc.measure.Measurements(qc)
+    reseed()
+    count = m.find_overparam_point([0])
+    assert count == int(golden_r2["overparam/count"])
+    assert qc.n_layers == int(golden_r2["overparam/n_layers_after"])
+    assert capsys.readouterr().out == str(golden_r2["overparam/log"])
+
+
+@pytest.mark.parametrize("method,rate,eps", [("QNG", 0.05, 1e-4), ("gradient", 0.05, 1e-5)])
+def test_train_gradient_and_qng_match_reference(golden_r2, method, rate, eps):
+    """measure.py:473-553, the fixed-step branches (natural gradient: pinv(QFIM) . grad,
+    measure.py:523-529): same number of iterations, same energy / magic / Q / GKP traces."""
+    qc = cases_r2.build_tfim3(pyqc)
+    m = pyqc.measure.Measurements(qc)
+    energy, traj, magics, ents, gkps = m.train(epsilon=eps, rate=rate, method=method,
+                                               angles=list(cases_r2.TFIM3_START))
+    g = golden_r2
+    assert len(traj) == len(g[f"train/{method}/traj"])
+    assert abs(energy - float(g[f"train/{method}/energy"])) < 1e-9
+    assert np.abs(np.array(traj) - g[f"train/{method}/traj"]).max() < 1e-9
+    assert np.abs(np.array(magics) - g[f"train/{method}/magics"]).max() < 1e-8
+    assert np.abs(np.array(ents) - g[f"train/{method}/ents"]).max() < 1e-9
+    assert np.abs(np.array(gkps) - g[f"train/{method}/gkps"]).max() < 1e-8
+    assert np.abs(np.array(qc.get_params()) - g[f"train/{method}/final_angles"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("n", [4, 6])
+def test_effective_hilbert_space_zfsim_matches_reference(golden_r2, n):
+    """The zfsim half of tests.py:311-342: fidelity samples of a half-filled, particle-number
+    conserving circuit and the Hilbert-space dimension find_eff_H fits to them (about
+    C(n, n/2)), against the reference run from the same initial state and RNG position."""
+    qc = pyqc.templates.generate_circuit("zfsim", n, n)
+    qc.initial_state = golden_r2[f"zfsim/{n}/init"]          # State(array)
+    m = pyqc.measure.Measurements(qc)
+    reseed()
+    F = m._gen_f_samples(60)
+    assert np.abs(np.array(F) - golden_r2[f"zfsim/{n}/F"]).max() < ATOL
+    eff = m.find_eff_H(F, n)
+    ref = float(golden_r2[f"zfsim/{n}/effH"])
+    assert abs(eff - ref) < 1e-4 * ref
+    from math import comb, isclose
+    assert isclose(eff, comb(n, n // 2), rel_tol=0.4)           # the reference's own assertion
 
 
 @pytest.mark.gpu

@@ -202,3 +202,18 @@ def test_planner_layer_sequence_plans():
     assert tfim[1] == len(lines) and tfim[2] == 0
     he, _ = tally("generic_HE", 14, 2, "PASS")
     assert he[2] == 0                                           # CNOT permutations: generic kernel
+
+
+@pytest.mark.parametrize("n", [1, 3, 5])
+def test_conversion_matrices_match_reference(golden_r2, n):
+    """measure.py:268-316: the xor / sign lookup tables of the reference's dense magic
+    formulation (host code; kept for API compatibility) against reference-generated fixtures."""
+    m = pyqc.measure.Measurements(pyqc.PQC(n))
+    xor, sign = m.get_conversion_matrices()
+    assert np.array_equal(np.asarray(xor), golden_r2[f"conv/{n}/xor"])
+    assert np.array_equal(np.asarray(sign), golden_r2[f"conv/{n}/sign"])
+    assert np.array_equal(m.numberToBase(3 % (2 ** n), 2, n), golden_r2[f"conv/{n}/base3"])
+    ox, osg = orc.conversion_matrices(n)
+    assert np.array_equal(np.asarray(xor), ox) and np.array_equal(np.asarray(sign), osg)
+    m.set_converstion_matrices((xor, sign))
+    assert m.conversion_matrices[0] is xor
