@@ -266,7 +266,8 @@ extern "C" int pqc_program_stats(const pqc_program* prog, int64_t* out8) {
   out8[2] = (int64_t)prog->ops.size();
   const bool v1r = prog->v1_ok && !pqc_use_v0();
   const bool v1g = prog->v1_grad_ok && !pqc_use_v0();
-  out8[3] = v1r ? (int64_t)prog->v1_run.size() : (int64_t)prog->run_passes.size();
+  out8[3] = v1r ? (int64_t)(pqc_use_front(prog) ? prog->front_run.size() : prog->v1_run.size())
+                : (int64_t)prog->run_passes.size();
   out8[4] = v1r ? V1_LOCAL_BITS : prog->tile_bits;
   out8[5] = prog->grad_supported ? 1 : 0;
   int64_t q = 0;

@@ -190,39 +190,47 @@ struct SeqPlan {
 // relabelings of that index (they change the planner's slot tables, not the kernel).
 #define TP_MAX_SWEEPS 24
 #define TP_MAX_OPS 320
-#define TP_MAX_TRIG 320
+#define TP_MAX_TRIG 256
 #define TP_MAX_SPAWN 8
+#define TP_MAX_WT 24                 // linear-form tables (ZZSUM subsets, GEN) per pass
 #define TP_NBUF 3
+#define PQC_K_LAYER_RZ4 37           // rz on each of the 4 register bits, tangent form
 struct TPOp {              // 16 bytes
   uint8_t kind;            // pqc_opcode or PQC_K_*
   uint8_t sub;             // LAYER_*4: 2 bits per register bit: 0 none, 1 rotation, 2 Hadamard
   uint8_t a, b;            // RXY: a = ka * 4 + kb;  RZ: a = register bit | 0xff, b = tile position | 0xff
                            // CZ: a, b = register bits | 0xff
+                           // CNOT (index permutation): a = control register bit | 0xff, b = target
+                           // register bit;  X: b = target register bit
   uint16_t t[4];           // trig slots (LAYER_*4, RXY, RZ: t[0]; ZZSUM: t[0] = first table slot)
                            // RZ: t[1] = global bit;  CZ: t[0], t[1] = tile positions | 0xffff, t[2], t[3] = global bits
+                           // CNOT: t[0] = control tile position | 0xffff, t[1] = control global bit
   uint8_t wt, nterms, spawn, pad;   // ZZSUM / GEN: linear-form table, term count; GEN: spawn index
 };
 struct TPSweep {
-  uint16_t rd_t[2][16];    // slot of the thread part when loading: rd_t[0][tid & 15] ^ rd_t[1][tid >> 4]
-  uint16_t wr_t[2][16];    // ... when storing back (differs from rd_t only in the re-swizzling sweep 0)
-  uint16_t lidx[2][16];    // logical tile index of the thread part (register bits zero)
-  uint16_t rd_r[4], wr_r[4];   // slot masks of the 4 register bits
+  // thread part, per nibble of the thread index: byte offset of the slot (low 16 bits) and
+  // logical tile index (high 16 bits); word = tt[0][tid & 15] ^ tt[1][tid >> 4]
+  uint32_t tt[2][16];
+  uint16_t rs[4];          // slot byte-offset masks of the 4 register bits
   uint8_t rpos[4];         // tile positions of the register bits
   uint16_t op_begin, op_end;
+  // X / CNOT index permutations folded into the load (the first npre ops) and into the store
+  // (the last npost ops) of the sweep: targets are register bits, so a thread only permutes its
+  // own 16 slots
+  uint8_t npre, npost, pad[2];
 };
 struct PipePlan {
   int nsw, nops, ntrig, nwt;
-  int low_run;             // tile positions 0 .. low_run-1 are the amplitude bits 0 .. low_run-1
   int lbit[12];            // amplitude bit of tile position p
   // tile load (cp.async): thread bits 0-3 sit on the tile positions of amplitude bits 0-3
   uint32_t ld_amp[2][16];  // amplitude offset of the thread part: ld_amp[0][tid & 15] | ld_amp[1][tid >> 4]
   uint32_t ld_r[4];        //   and of the 4 bits walked by the copy index j
-  uint16_t ld_slot[2][16]; // shared-memory slot of the thread part
+  uint16_t ld_slot[2][16]; // slot byte offset of the thread part
   uint16_t ld_sr[4];
   uint32_t st_t[2][16];    // last sweep, direct store: amplitude offset of the thread part
   uint32_t st_r[4];        //   and of the register bits
-  uint32_t wn[FAST_MAX_WT][3][16];
-  uint32_t wo[FAST_MAX_WT][PQC_MAX_QUBITS - 12];
+  uint32_t wn[TP_MAX_WT][3][16];
+  uint32_t wo[TP_MAX_WT][PQC_MAX_QUBITS - 12];
   TPSweep sw[TP_MAX_SWEEPS];
   TPOp ops[TP_MAX_OPS];
 };
@@ -246,6 +254,7 @@ struct V1Pass {
   bool seq_ok = false;
   SeqPlan seq;
   int pipe_idx = -1;             // index into pqc_program::h_pipe, -1: not convertible
+  bool front = false;            // made by the front planner: runs on k_tile_pipe only
 
   int tb, low_run;
   int lbit[V1_LOCAL_BITS];
@@ -302,6 +311,10 @@ struct pqc_program {
   std::vector<uint32_t> h_zz;                 // linear-form tables (V1_WTAB words each)
   std::vector<DOp> h_dops;
   std::vector<PipePlan> h_pipe;              // tile-pipe form of the passes that have one
+  // run plan of the front planner (pqc_front.cu): pass indices, its trig jobs / table slots
+  bool front_ok = false;
+  std::vector<int> front_run;
+  int front_tj0 = 0, front_ntj = 0, front_slots = 0;
   PipePlan* d_pipe = nullptr;
   bool uploaded = false;
   MOp* d_mops = nullptr;
@@ -392,6 +405,9 @@ int pqc_v1_gram_qfim2(const pqc_program* prog, const c128* buf, int slots1, int 
                       const c128* buf2, int slots2, const int* d_inv, long long S, c128* d_gpart,
                       double* d_F, cudaStream_t st);
 bool pqc_pipe_build(const V1Pass& ps, int n, PipePlan& out);
+void pqc_pipe_fill_load_tables(PipePlan& pp);
+bool pqc_plan_front(pqc_program* prog, std::vector<TrigJob>& tjobs);
+bool pqc_use_front(const pqc_program* prog);
 int pqc_pipe_launch(const PipeArgs& a, const PipePlan& hplan, cudaStream_t st);
 bool pqc_pipe_enabled();
 int pqc_prof_launch_begin(double bytes, cudaStream_t st);

@@ -67,14 +67,25 @@ __device__ __forceinline__ void tp_cp_async_arrive(uint64_t* bar) {
                    (unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
+// rz on register bit K in tangent form: a *= (1 - i t) where the bit is 0, (1 + i t) where it is
+// 1; the cos factor goes to the pass' scalar like those of op_rx_t / op_ry_t
+template <int K>
+__device__ __forceinline__ void op_rz_t(c128 (&a)[16], double t) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const double s = (j & (1 << K)) ? t : -t;
+    const c128 v = a[j];
+    a[j] = make_double2(fma(-s, v.y, v.x), fma(s, v.x, v.y));
+  }
+}
+
 // the ops of one sweep on the 16 register amplitudes.  lidx = the thread's logical tile index
-// (register bits zero), tbase = the tile's amplitude offset, wb[] = linear forms of the tile.
+// (register bits zero), tbase = the tile's amplitude offset, tile = its index.
 template <bool GEN>
-__device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const TPSweep& sw,
-                                       const double2* trig, uint32_t lidx, uint32_t tbase,
-                                       const uint32_t (&wb)[FAST_MAX_WT], int gen,
-                                       const PipeArgs& A, double& fscale) {
-  const int ob = sw.op_begin, oe = sw.op_end;
+__device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const TPSweep& sw, int ob,
+                                       int oe, const double2* trig, uint32_t lidx, uint32_t tbase,
+                                       uint32_t tile, int tiles_log2, int gen, const PipeArgs& A,
+                                       double& fscale) {
   for (int oi = ob; oi < oe; ++oi) {
     const TPOp op = P->ops[oi];
     const int kind = op.kind;
@@ -153,6 +164,14 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
       op_rx_t<2>(a, c2.x);
       op_rx_t<3>(a, c3.x);
       fscale *= (c0.y * c1.y) * (c2.y * c3.y);
+    } else if (kind == PQC_K_LAYER_RZ4) {
+      const int sk = op.sub;
+      double f = 1.0;
+      if (sk & 0x03) { const double2 tc = trig[op.t[0]]; op_rz_t<0>(a, tc.x); f *= tc.y; }
+      if (sk & 0x0c) { const double2 tc = trig[op.t[1]]; op_rz_t<1>(a, tc.x); f *= tc.y; }
+      if (sk & 0x30) { const double2 tc = trig[op.t[2]]; op_rz_t<2>(a, tc.x); f *= tc.y; }
+      if (sk & 0xc0) { const double2 tc = trig[op.t[3]]; op_rz_t<3>(a, tc.x); f *= tc.y; }
+      fscale *= f;
     } else if (kind == PQC_K_LAYER_REAL4) {
       const int sk = op.sub;
       double f = 1.0;
@@ -178,8 +197,8 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
     } else if (kind == PQC_K_ZZSUM || kind == PQC_K_GEN) {
       // w(x) = w(tile) ^ w(thread part) ^ w(register value j); wn holds w per tile nibble value
       const uint32_t(*wn)[16] = P->wn[op.wt];
-      const uint32_t wbv = op.wt == 0 ? wb[0] : (op.wt == 1 ? wb[1] : (op.wt == 2 ? wb[2] : wb[3]));
-      const uint32_t w0 = wbv ^ wn[0][lidx & 15u] ^ wn[1][(lidx >> 4) & 15u] ^ wn[2][lidx >> 8];
+      uint32_t w0 = wn[0][lidx & 15u] ^ wn[1][(lidx >> 4) & 15u] ^ wn[2][lidx >> 8];
+      for (int jb = 0; jb < tiles_log2; ++jb) w0 ^= ((tile >> jb) & 1u) ? P->wo[op.wt][jb] : 0u;
       const uint32_t w1 = wn[sw.rpos[0] >> 2][1u << (sw.rpos[0] & 3)];
       const uint32_t w2 = wn[sw.rpos[1] >> 2][1u << (sw.rpos[1] & 3)];
       const uint32_t w3 = wn[sw.rpos[2] >> 2][1u << (sw.rpos[2] & 3)];
@@ -207,10 +226,37 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
   }
 }
 
+#define TP_LIN4(x, a0, a1, a2, a3) \
+  ((((x)&1u) ? (a0) : 0u) ^ (((x)&2u) ? (a1) : 0u) ^ (((x)&4u) ? (a2) : 0u) ^ (((x)&8u) ? (a3) : 0u))
+
+// X / CNOT index permutations ops[begin, end) of a sweep as an affine map of the 4-bit register
+// index: label(j) = XOR_{k in j} col[k] ^ v (k_sweep_pass' `affine`).  reverse: the inverse order,
+// for permutations folded into the load.
+__device__ __forceinline__ void tp_affine(const PipePlan* P, int begin, int end, bool reverse,
+                                          uint32_t lidx, uint32_t tbase, uint32_t (&col)[4],
+                                          uint32_t& v) {
+  col[0] = 1u; col[1] = 2u; col[2] = 4u; col[3] = 8u;
+  v = 0u;
+  for (int q = 0; q < end - begin; ++q) {
+    const TPOp pm = P->ops[reverse ? end - 1 - q : begin + q];
+    const int kt = pm.b;
+    if (pm.kind == PQC_OP_X) {
+      v ^= 1u << kt;
+    } else if (pm.a != 0xff) {               // CNOT, control in registers
+      const int kc = pm.a;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) col[c] ^= ((col[c] >> kc) & 1u) << kt;
+      v ^= ((v >> kc) & 1u) << kt;
+    } else {                                 // CNOT, control fixed for this thread
+      const uint32_t cb = pm.t[0] != 0xffff ? ((lidx >> pm.t[0]) & 1u) : ((tbase >> pm.t[1]) & 1u);
+      v ^= cb << kt;
+    }
+  }
+}
+
 template <bool GEN>
 __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
   extern __shared__ __align__(128) unsigned char tp_sm[];
-  c128* tiles = reinterpret_cast<c128*>(tp_sm);
   double2* trigs = reinterpret_cast<double2*>(tp_sm + TP_SMEM_TILES);
   PipePlan* P = reinterpret_cast<PipePlan*>(tp_sm + TP_SMEM_TILES + TP_SMEM_TRIG);
   __shared__ __align__(8) uint64_t full[TP_NBUF];
@@ -226,15 +272,17 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
   }
   __syncthreads();
   const int tiles_log2 = A.n - 12;
-  const long long total = A.n_items << tiles_log2;
-  const long long nk = (total - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
-  const int ips = A.active + A.nspawn;
+  const uint32_t tmask = (1u << tiles_log2) - 1u;
+  const uint32_t total = (uint32_t)(A.n_items << tiles_log2);   // < 2^31 (checked by the host)
+  const uint32_t stride = gridDim.x;
+  const int nk = (int)((total - blockIdx.x + stride - 1) / stride);
+  const uint32_t ips = (uint32_t)(A.active + A.nspawn);
   const int ntrig = P->ntrig;
 
-  auto item_of = [&](long long k, long long& sample, int& r, uint32_t& tile) {
-    const long long item = (long long)blockIdx.x + k * gridDim.x;
-    const long long vec = item >> tiles_log2;
-    tile = (uint32_t)(item & ((1ll << tiles_log2) - 1));
+  auto item_of = [&](int k, uint32_t& sample, int& r, uint32_t& tile) {
+    const uint32_t item = blockIdx.x + (uint32_t)k * stride;
+    const uint32_t vec = item >> tiles_log2;
+    tile = item & tmask;
     sample = vec / ips;
     r = (int)(vec - sample * ips);
   };
@@ -246,16 +294,15 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
   // the 256 threads of one group: asynchronous copy of the tile of work item k into ring slot
   // k % TP_NBUF (16 x 16 bytes per thread; lanes cover the low amplitude bits, so a warp reads
   // 256-byte runs and writes conflict-free swizzled slots)
-  auto load_tile = [&](long long k) {
-    const int b = (int)(k % TP_NBUF);
-    long long sample;
+  auto load_tile = [&](int k) {
+    const int b = k % TP_NBUF;
+    uint32_t sample, tile;
     int r;
-    uint32_t tile;
     item_of(k, sample, r, tile);
     const int src_slot = (GEN && r >= A.active) ? 0 : r;
-    const c128* src = A.src + ((sample * A.slots_total + src_slot) << A.n) +
+    const c128* src = A.src + (((long long)sample * A.slots_total + src_slot) << A.n) +
                       (tile_base(tile) | P->ld_amp[0][lo] | P->ld_amp[1][hi]);
-    c128* dst = tiles + (size_t)b * 4096;
+    unsigned char* dst = tp_sm + (size_t)b * TP_TILE_BYTES;
     const uint32_t slot0 = (uint32_t)P->ld_slot[0][lo] ^ (uint32_t)P->ld_slot[1][hi];
     const uint32_t g0 = P->ld_r[0], g1 = P->ld_r[1], g2 = P->ld_r[2], g3 = P->ld_r[3];
     const uint32_t s0 = P->ld_sr[0], s1 = P->ld_sr[1], s2 = P->ld_sr[2], s3 = P->ld_sr[3];
@@ -265,13 +312,12 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
     tp_cp_async_arrive(&full[b]);
   };
   // the group's trig entries of work item k -> area [grp][(k >> 1) & 1] (cp.async, 16 B per thread)
-  auto trig_fetch = [&](long long k) {
-    long long sample;
+  auto trig_fetch = [&](int k) {
+    uint32_t sample, tile;
     int r;
-    uint32_t tile;
     item_of(k, sample, r, tile);
-    double2* dst = trigs + (size_t)(grp * 2 + (int)((k >> 1) & 1)) * TP_MAX_TRIG;
-    const double2* srcp = A.gtrig + sample * A.tstride + A.toff;
+    double2* dst = trigs + (size_t)(grp * 2 + ((k >> 1) & 1)) * TP_MAX_TRIG;
+    const double2* srcp = A.gtrig + (long long)sample * A.tstride + A.toff;
     for (int e = t; e < ntrig; e += 256) tp_cp_async16(dst + e, srcp + e);
   };
 
@@ -285,27 +331,18 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
   if (grp == 0 && 2 < nk) load_tile(2);
   tp_cp_async_commit();
 
-  for (long long k = grp; k < nk; k += 2) {
-    const int b = (int)(k % TP_NBUF);
-    c128* buf = tiles + (size_t)b * 4096;
-    const double2* trig = trigs + (size_t)(grp * 2 + (int)((k >> 1) & 1)) * TP_MAX_TRIG;
-    long long sample;
+  for (int k = grp; k < nk; k += 2) {
+    const int b = k % TP_NBUF;
+    unsigned char* buf = tp_sm + (size_t)b * TP_TILE_BYTES;
+    const double2* trig = trigs + (size_t)(grp * 2 + ((k >> 1) & 1)) * TP_MAX_TRIG;
+    uint32_t sample, tile;
     int r;
-    uint32_t tile;
     item_of(k, sample, r, tile);
     const uint32_t tbase = tile_base(tile);
     int dst_slot = r, gen = -1;
-    if (GEN && r >= A.active) {
+    if (GEN && r >= (int)A.active) {
       gen = r - A.active;
       dst_slot = A.spawn_slot[gen];
-    }
-    uint32_t wb[FAST_MAX_WT];
-#pragma unroll
-    for (int w = 0; w < FAST_MAX_WT; ++w) {
-      uint32_t v = 0;
-      if (w < P->nwt)
-        for (int j = 0; j < tiles_log2; ++j) v ^= ((tile >> j) & 1u) ? P->wo[w][j] : 0u;
-      wb[w] = v;
     }
     // this item's trig entries have landed (prefetched one item ahead); fetch the next item's
     tp_cp_async_wait_1();
@@ -319,38 +356,64 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
     const int nsw = P->nsw;
     for (int s = 0; s < nsw; ++s) {
       const TPSweep& sw = P->sw[s];
-      {
-        const uint32_t rd0 = (uint32_t)sw.rd_t[0][lo] ^ (uint32_t)sw.rd_t[1][hi];
-        const uint32_t r0 = sw.rd_r[0], r1 = sw.rd_r[1], r2 = sw.rd_r[2], r3 = sw.rd_r[3];
+      const uint32_t tw = sw.tt[0][lo] ^ sw.tt[1][hi];
+      const uint32_t sb = tw & 0xffffu, lidx = tw >> 16;
+      const uint32_t r0 = sw.rs[0], r1 = sw.rs[1], r2 = sw.rs[2], r3 = sw.rs[3];
+      const int npre = sw.npre, npost = sw.npost, ob = sw.op_begin, oe = sw.op_end;
+      const bool last = s + 1 == nsw;
+      if (npre) {
+        uint32_t col[4], v;
+        tp_affine(P, ob, ob + npre, true, lidx, tbase, col, v);
+        const uint32_t lb = sb ^ TP_LIN4(v, r0, r1, r2, r3);
+        const uint32_t l0 = TP_LIN4(col[0], r0, r1, r2, r3), l1 = TP_LIN4(col[1], r0, r1, r2, r3),
+                       l2 = TP_LIN4(col[2], r0, r1, r2, r3), l3 = TP_LIN4(col[3], r0, r1, r2, r3);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) a[j] = buf[rd0 ^ XSEL4R(j, r0, r1, r2, r3)];
+        for (int j = 0; j < 16; ++j)
+          a[j] = *reinterpret_cast<const c128*>(buf + (lb ^ XSEL4R(j, l0, l1, l2, l3)));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          a[j] = *reinterpret_cast<const c128*>(buf + (sb ^ XSEL4R(j, r0, r1, r2, r3)));
       }
-      const uint32_t lidx = (uint32_t)sw.lidx[0][lo] | (uint32_t)sw.lidx[1][hi];
-      if (s + 1 == nsw) {
+      if (last) {
         // every thread of the group has read its last amplitudes from the ring slot: refill it
         // with the item three steps ahead before doing this sweep's arithmetic
         tp_group_bar(grp);
         if (k + TP_NBUF < nk) load_tile(k + TP_NBUF);
         tp_cp_async_commit();
       }
-      tp_ops<GEN>(a, P, sw, trig, lidx, tbase, wb, gen, A, fscale);
-      if (s + 1 == nsw) break;
-      __syncwarp();
-      {
-        const uint32_t wr0 = (uint32_t)sw.wr_t[0][lo] ^ (uint32_t)sw.wr_t[1][hi];
-        const uint32_t w0 = sw.wr_r[0], w1 = sw.wr_r[1], w2 = sw.wr_r[2], w3 = sw.wr_r[3];
+      tp_ops<GEN>(a, P, sw, ob + npre, oe - npost, trig, lidx, tbase, tile, tiles_log2, gen, A, fscale);
+      uint32_t col[4] = {1u, 2u, 4u, 8u}, v = 0u;
+      if (npost) tp_affine(P, oe - npost, oe, false, lidx, tbase, col, v);
+      if (last) {
+        if (fscale != 1.0) op_scale(a, fscale);
+        const uint32_t amp = tbase | P->st_t[0][lo] | P->st_t[1][hi];
+        uint32_t g0 = P->st_r[0], g1 = P->st_r[1], g2 = P->st_r[2], g3 = P->st_r[3];
+        uint32_t gb = amp;
+        if (npost) {
+          gb = amp ^ TP_LIN4(v, g0, g1, g2, g3);
+          const uint32_t q0 = TP_LIN4(col[0], g0, g1, g2, g3), q1 = TP_LIN4(col[1], g0, g1, g2, g3),
+                         q2 = TP_LIN4(col[2], g0, g1, g2, g3), q3 = TP_LIN4(col[3], g0, g1, g2, g3);
+          g0 = q0; g1 = q1; g2 = q2; g3 = q3;
+        }
+        c128* dp = A.dst + (((long long)sample * A.slots_total + dst_slot) << A.n);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) buf[wr0 ^ XSEL4R(j, w0, w1, w2, w3)] = a[j];
+        for (int j = 0; j < 16; ++j) dp[gb ^ XSEL4R(j, g0, g1, g2, g3)] = a[j];
+        break;
+      }
+      if (npost) {
+        const uint32_t lb = sb ^ TP_LIN4(v, r0, r1, r2, r3);
+        const uint32_t l0 = TP_LIN4(col[0], r0, r1, r2, r3), l1 = TP_LIN4(col[1], r0, r1, r2, r3),
+                       l2 = TP_LIN4(col[2], r0, r1, r2, r3), l3 = TP_LIN4(col[3], r0, r1, r2, r3);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          *reinterpret_cast<c128*>(buf + (lb ^ XSEL4R(j, l0, l1, l2, l3))) = a[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          *reinterpret_cast<c128*>(buf + (sb ^ XSEL4R(j, r0, r1, r2, r3))) = a[j];
       }
       tp_group_bar(grp);
-    }
-    if (fscale != 1.0) op_scale(a, fscale);
-    {
-      const uint32_t amp = tbase | P->st_t[0][lo] | P->st_t[1][hi];
-      const uint32_t g0 = P->st_r[0], g1 = P->st_r[1], g2 = P->st_r[2], g3 = P->st_r[3];
-      c128* dp = A.dst + ((sample * A.slots_total + dst_slot) << A.n) + amp;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) dp[XSEL4R(j, g0, g1, g2, g3)] = a[j];
     }
   }
 }
@@ -406,11 +469,10 @@ bool pqc_pipe_build(const V1Pass& ps, int n, PipePlan& pp) {
   pp.nwt = ps.nwt;
   if (pp.ntrig > TP_MAX_TRIG || pp.nwt > FAST_MAX_WT) return false;
   for (int p = 0; p < 12; ++p) pp.lbit[p] = ps.lbit[p];
-  int low_run = 0;
-  while (low_run < 12 && ps.lbit[low_run] == low_run) ++low_run;
-  pp.low_run = low_run;
-  memcpy(pp.wn, wn, sizeof(pp.wn));
-  memcpy(pp.wo, wo, sizeof(pp.wo));
+  for (int w = 0; w < FAST_MAX_WT; ++w) {
+    memcpy(pp.wn[w], wn[w], sizeof(pp.wn[w]));
+    memcpy(pp.wo[w], wo[w], sizeof(pp.wo[w]));
+  }
   {
     // tile load: thread bits 0-3 on the tile positions of amplitude bits 0-3 (256-byte runs per
     // half warp), thread bits 4-7 and the copy index j on the other positions in ascending order
@@ -429,11 +491,11 @@ bool pqc_pipe_build(const V1Pass& ps, int n, PipePlan& pp) {
             idx |= 1u << tpos[4 * h + i];
             amp |= 1u << ps.lbit[tpos[4 * h + i]];
           }
-        pp.ld_slot[h][v] = (uint16_t)h_swz(idx);
+        pp.ld_slot[h][v] = (uint16_t)(h_swz(idx) << 4);
         pp.ld_amp[h][v] = amp;
       }
     for (int k = 0; k < 4; ++k) {
-      pp.ld_sr[k] = (uint16_t)h_swz(1u << tpos[8 + k]);
+      pp.ld_sr[k] = (uint16_t)(h_swz(1u << tpos[8 + k]) << 4);
       pp.ld_r[k] = 1u << ps.lbit[tpos[8 + k]];
     }
   }
@@ -447,18 +509,14 @@ bool pqc_pipe_build(const V1Pass& ps, int n, PipePlan& pp) {
       if (p < r0 || p >= r0 + 4) tp[nt++] = p;
     for (int k = 0; k < 4; ++k) {
       sw.rpos[k] = (uint8_t)(r0 + k);
-      const uint32_t m = 1u << (r0 + k);
-      sw.rd_r[k] = (uint16_t)h_swz(m);
-      sw.wr_r[k] = (uint16_t)h_swz(m);
+      sw.rs[k] = (uint16_t)(h_swz(1u << (r0 + k)) << 4);
     }
     for (int h = 0; h < 2; ++h)
       for (int v = 0; v < 16; ++v) {
         uint32_t idx = 0;
         for (int i = 0; i < 4; ++i)
           if ((v >> i) & 1) idx |= 1u << tp[4 * h + i];
-        sw.lidx[h][v] = (uint16_t)idx;
-        sw.rd_t[h][v] = (uint16_t)h_swz(idx);
-        sw.wr_t[h][v] = (uint16_t)h_swz(idx);
+        sw.tt[h][v] = (h_swz(idx) << 4) | (idx << 16);
         if (s + 1 == pp.nsw) {
           uint32_t amp = 0;
           for (int p = 0; p < 12; ++p)
@@ -538,6 +596,7 @@ int pqc_pipe_launch(const PipeArgs& a, const PipePlan& hplan, cudaStream_t st) {
   }
   const long long total = a.n_items << (a.n - 12);
   if (total <= 0) return 0;
+  if (total > 0x7fffffffLL) PQC_FAIL(-1, "pass grid too large; split the batch");
   const unsigned grid = (unsigned)std::min<long long>(total, sms[dev]);
   const int h = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st);
   if (a.nspawn > 0) k_tile_pipe<true><<<grid, TP_THREADS, TP_SMEM_TOTAL, st>>>(a);

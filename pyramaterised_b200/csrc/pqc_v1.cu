@@ -23,6 +23,19 @@
 #include "pqc_common.cuh"
 #include "pqc_ops.cuh"
 
+// The front plan (pqc_front.cu) runs PQC.run unless every pass of the block plan is a layer pass
+// (the TFIM template: k_layer_pass' compile-time geometry is the faster kernel there).
+// PQC_FRONT=0 / 1 forces the choice (read per call so tests can compare the plans).
+bool pqc_use_front(const pqc_program* prog) {
+  if (!prog->front_ok || prog->front_run.empty()) return false;
+  const char* e = getenv("PQC_FRONT");
+  if (e && strcmp(e, "0") == 0) return false;
+  if (e && strcmp(e, "1") == 0) return true;
+  bool all_fast = !prog->v1_run.empty();
+  for (int pi : prog->v1_run) all_fast = all_fast && prog->v1_passes[pi].fast_ok;
+  return !all_fast;
+}
+
 bool pqc_use_v0() {
   static int v = -1;
   if (v < 0) {
@@ -862,6 +875,8 @@ int pqc_plan_v1(pqc_program* prog) {
       prog->h_pipe.push_back(pp);
     }
   }
+  // light-cone plan of PQC.run for k_tile_pipe (pqc_front.cu); appends passes and trig jobs
+  pqc_plan_front(prog, tjobs);
   prog->h_mops = mops;
   prog->h_sweeps = sweeps;
   prog->h_tjobs = tjobs;
@@ -879,6 +894,23 @@ extern "C" PQC_API int pqc_program_describe(const pqc_program* prog, char* out, 
     char buf[256];
     int nm = 0;
     std::string kinds;
+    if (ps.front) {
+      const PipePlan& pp = prog->h_pipe[ps.pipe_idx];
+      for (int i = 0; i < pp.nsw; ++i) {
+        const TPSweep& sw = pp.sw[i];
+        snprintf(buf, sizeof(buf), " [rb %d,%d,%d,%d pre%d post%d:", sw.rpos[0], sw.rpos[1], sw.rpos[2],
+                 sw.rpos[3], sw.npre, sw.npost);
+        kinds += buf;
+        for (int m = sw.op_begin; m < sw.op_end; ++m) {
+          snprintf(buf, sizeof(buf), " %d", pp.ops[m].kind);
+          kinds += buf;
+        }
+        kinds += "]";
+      }
+      snprintf(buf, sizeof(buf), "sweeps=%d ops=%d trig=%d tables=%d front=1", pp.nsw, pp.nops, pp.ntrig,
+               pp.nwt);
+      return std::string(buf) + kinds;
+    }
     for (int i = 0; i < ps.nsweeps; ++i) {
       const SweepD& sw = prog->h_sweeps[ps.sweep_off + i];
       snprintf(buf, sizeof(buf), " [rb %d,%d,%d,%d io%d:", sw.rb[0], sw.rb[1], sw.rb[2], sw.rb[3], sw.io);
@@ -950,6 +982,12 @@ extern "C" PQC_API int pqc_program_describe(const pqc_program* prog, char* out, 
   // the plain run plan (PQC.run), when it differs from what was printed above
   if (prog->v1_ok && prog->v1_grad_ok)
     for (int pi : prog->v1_run) s += "RUN PASS " + pass_line(prog->v1_passes[pi]) + "\n";
+  if (prog->front_ok) {
+    snprintf(buf, sizeof(buf), "FRONT plan: %d passes, used for PQC.run: %d\n", (int)prog->front_run.size(),
+             pqc_use_front(prog) ? 1 : 0);
+    s += buf;
+    for (int pi : prog->front_run) s += "FRONT PASS " + pass_line(prog->v1_passes[pi]) + "\n";
+  }
   if ((int64_t)s.size() + 1 > cap) s.resize((size_t)cap - 1);
   memcpy(out, s.c_str(), s.size() + 1);
   return 0;
@@ -2689,9 +2727,12 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
   const long long grid = groups << (a.n - a.tb);
   if (grid <= 0) return 0;
   if (grid > 0x7fffffffLL) PQC_FAIL(-1, "pass grid too large; split the batch");
+  if (a.hpass && a.hpass->front && (a.npartners != 0 || a.items_log2 != 0 || a.hpass->pipe_idx < 0))
+    PQC_FAIL(-5, "internal: front-plan pass outside k_tile_pipe");
   if (a.hpass && a.hpass->pipe_idx >= 0 && a.npartners == 0 && a.nspawn <= TP_MAX_SPAWN &&
-      a.items_log2 == 0 && fast_enabled() && pqc_pipe_enabled() &&
-      (a.hpass->fast_ok || seq_enabled())) {
+      a.items_log2 == 0 &&
+      (a.hpass->front ||
+       (fast_enabled() && pqc_pipe_enabled() && (a.hpass->fast_ok || seq_enabled())))) {
     PipeArgs f;
     memset(&f, 0, sizeof(f));
     f.src = a.src;
@@ -2852,22 +2893,27 @@ int pqc_v1_run(const pqc_program* prog, const double* d_angles, long long ld, lo
   if (pqc_program_upload(prog)) return -2;
   // sample chunks keep the library-owned trig table below 256 MB
   const long long D = 1ll << prog->n;
-  const long long per = (long long)std::max(1, prog->v1_run_slots) * (long long)sizeof(double2);
+  const bool front = pqc_use_front(prog);
+  const std::vector<int>& plan = front ? prog->front_run : prog->v1_run;
+  const int tj0 = front ? prog->front_tj0 : prog->v1_run_tj0;
+  const int ntj = front ? prog->front_ntj : prog->v1_run_ntj;
+  const int slots = front ? prog->front_slots : prog->v1_run_slots;
+  const long long per = (long long)std::max(1, slots) * (long long)sizeof(double2);
   const long long chunk = std::max<long long>(1, (256ll << 20) / per);
   for (long long c0 = 0; c0 < S; c0 += chunk) {
     const long long c = std::min(chunk, S - c0);
     const double* ang = d_angles ? d_angles + c0 * ld : nullptr;
     c128* out = d_out + c0 * D;
-    int rc = trig_prepare(prog, prog->v1_run_tj0, prog->v1_run_ntj, prog->v1_run_slots, ang, ld, c, st);
+    int rc = trig_prepare(prog, tj0, ntj, slots, ang, ld, c, st);
     if (rc) return rc;
     rc = launch_init(out, mode, mode == 3 ? d_init + c0 * init_stride : d_init, init_stride, c, 1,
                      prog->n, st);
     if (rc) return rc;
-    for (int pi : prog->v1_run) {
+    for (int pi : plan) {
       V1Args a;
       memset(&a, 0, sizeof(a));
       fill_pass_args(prog, prog->v1_passes[pi], a);
-      a.tstride = prog->v1_run_slots;
+      a.tstride = slots;
       a.src = out;
       a.dst = out;
       a.n_items = c;

@@ -390,6 +390,52 @@ def test_tile_pipe_kernel_matches_per_tile_kernels_bitwise(kind, n, p, S, monkey
         assert rel(F[0].cpu().numpy(), orc.qfi(ref[0], g1[0])) < RTOL
 
 
+FRONT_CASES = [("XXZ", 16, 3, 5), ("XXZ", 13, 4, 3), ("generic_HE", 16, 3, 5), ("generic_HE", 12, 4, 3),
+               ("NPQC", 16, 5, 5), ("NPQC", 17, 3, 2), ("TFIM", 16, 3, 5), ("TFIM_modified", 14, 2, 3),
+               ("qg_circuit", 13, 2, 3), ("Circuit_2", 12, 2, 3), ("clifford", 12, 2, 3),
+               ("Circuit_9", 12, 2, 3), ("y_CPHASE", 13, 2, 3), ("XXZ", 20, 2, 1)]
+
+
+@pytest.mark.parametrize("kind,n,p,S", FRONT_CASES)
+def test_front_plan_matches_block_plan_and_oracle(kind, n, p, S, monkeypatch):
+    """PQC.run through the front planner (light-cone passes on k_tile_pipe: any 4 tile bits in
+    registers, X / CNOT folded into the sweeps' addresses, R_z in tangent form, per-level
+    table-lookup R_zz phases; PQC_FRONT=1) against the block planner's plan on the per-tile
+    kernels (PQC_FRONT=0) and against the oracle -- the three-way check of every new path."""
+    qc = pyqc.templates.generate_circuit(kind, n, p, shuffle=False)
+    assert "FRONT plan" in qc.program.describe()
+    specs = specs_from_circuit(qc)
+    init = qc.initial_state.tensor.cpu().numpy()
+    ang = np.random.default_rng(7 * n + p).random((S, max(1, orc.n_params(specs)))) * 2 * np.pi
+    l0 = engine.launch_count()
+    monkeypatch.setenv("PQC_FRONT", "1")
+    st = qc.run_batch(ang)
+    monkeypatch.setenv("PQC_FRONT", "0")
+    st0 = qc.run_batch(ang)
+    monkeypatch.delenv("PQC_FRONT")
+    assert engine.launch_count() > l0
+    assert np.abs((st - st0).cpu().numpy()).max() < 1e-12
+    ref = orc.run(specs, n, ang[:1], init)
+    assert np.abs(st[:1].cpu().numpy() - ref).max() < ATOL
+    nrm = engine.overlap(st, st).cpu().numpy()
+    assert np.abs(nrm - 1).max() < 1e-12
+
+
+@pytest.mark.parametrize("kind,n,p", [("XXZ", 16, 16), ("generic_HE", 16, 16), ("NPQC", 16, 16),
+                                      ("NPQC", 20, 20), ("NPQC", 22, 20)])
+def test_full_depth_states_vs_oracle(kind, n, p):
+    """Full-depth circuits of BASELINE configs 3 / 5 on the default plan (front planner) against the
+    oracle: row 0 of a small batch, every amplitude to 1e-10."""
+    qc = pyqc.templates.generate_circuit(kind, n, p, shuffle=False)
+    specs = specs_from_circuit(qc)
+    init = qc.initial_state.tensor.cpu().numpy()
+    ang = np.random.default_rng(n + p).random((2, orc.n_params(specs))) * 2 * np.pi
+    st = qc.run_batch(ang)
+    ref = orc.run(specs, n, ang[:1], init)
+    assert np.abs(st[0].cpu().numpy() - ref[0]).max() < ATOL
+    assert abs(float(engine.meyer_wallach(st[:1])[0].item()) - orc.single_Q(ref[0], n)) < ATOL
+
+
 def test_ragged_and_empty_batches():
     """Batch edges: a QFIM batch that does not fill its last 256-set chunk, a single row, an
     empty batch; every row must equal the one-row call bit for bit (fixed summation orders)."""

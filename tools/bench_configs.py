@@ -72,7 +72,7 @@ def c3_apply(kind="TFIM", n=16, p=16, S=4096):
     engine.profile_begin()
     ms, _ = timed(lambda: qc.program.run(ang, init=qc.initial_state.tensor, out=out))
     prof = engine.profile_end()
-    L = p + 1 if kind in ("TFIM", "NPQC") else p
+    L = p + 1 if kind in ("TFIM", "NPQC", "generic_HE") else p
     return {"config": f"C3 apply-only {kind} {n}q x {p} layers, S={S}", "ms": ms,
             "states_per_s": S / (ms / 1e3), "passes": qc.program.n_passes,
             "algorithmic_GBps_layers": L * 2 * 16 * 2 ** n * S / (ms / 1e3) / 1e9,
