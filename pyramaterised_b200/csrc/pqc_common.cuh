@@ -195,10 +195,22 @@ struct SeqPlan {
 #define TP_MAX_WT 24                 // linear-form tables (ZZSUM subsets, GEN) per pass
 #define TP_NBUF 3
 #define PQC_K_LAYER_RZ4 37           // rz on each of the 4 register bits, tangent form
+#define PQC_K_LAYER_RY4 38           // ry on each register bit; a slot may absorb a fixed ry and a
+                                     // CZ with a bit that is constant for the thread (see below)
+#define PQC_K_CZF 39                 // CZ(register bit, thread-constant bit): a pending Z "frame"
+#define PQC_K_ZFLUSH 40              // apply the pending Z frame now
+// Z frame (k_tile_pipe): CZ between a register bit k and a bit that is constant for the thread is
+// Z^b on bit k.  Z anticommutes with the X / Y rotations and commutes with everything diagonal,
+// so instead of touching 16 amplitudes it flips a per-thread flag; later rx / ry / xy rotations
+// on k take the opposite angle sign and the sign itself is applied once, when the sweep ends.
+// A partner byte: 0xff none, else tile position (bit 7 clear) or 0x80 | amplitude bit.
 struct TPOp {              // 16 bytes
   uint8_t kind;            // pqc_opcode or PQC_K_*
   uint8_t sub;             // LAYER_*4: 2 bits per register bit: 0 none, 1 rotation, 2 Hadamard
-  uint8_t a, b;            // RXY: a = ka * 4 + kb;  RZ: a = register bit | 0xff, b = tile position | 0xff
+  uint8_t a, b;            // LAYER_RY4: partner bytes of slots 0, 1 (slots 2, 3: wt, nterms); a slot with
+                           // a partner holds two trig entries, t[k] + (partner bit): ry(fixed) CZ ry(theta)
+                           // CZF: a = register bit, b = partner byte
+                           // RXY: a = ka * 4 + kb;  RZ: a = register bit | 0xff, b = tile position | 0xff
                            // CZ: a, b = register bits | 0xff
                            // CNOT (index permutation): a = control register bit | 0xff, b = target
                            // register bit;  X: b = target register bit

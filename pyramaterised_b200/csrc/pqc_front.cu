@@ -518,6 +518,24 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
       tslot[key] = ntrig;
       return ntrig++;
     };
+    // ry(alpha) CZ ry(theta) merged into one rotation: entries (tan, cos) of (theta + alpha) / 2
+    // and (theta - alpha) / 2 in two consecutive slots (partner bit 0 / 1)
+    auto trig_pair = [&](const FOp& o, double alpha) -> int {
+      const int base = ntrig;
+      for (int e = 0; e < 2; ++e) {
+        TrigJob j;
+        memset(&j, 0, sizeof(j));
+        j.kind = PQC_OP_RX;
+        j.param = o.param;
+        j.param2 = -1;
+        j.slot = ntrig++;
+        j.pad = 1;
+        j.scale = o.scale;
+        j.offset = o.offset + (e == 0 ? alpha : -alpha);
+        tj.push_back(j);
+      }
+      return base;
+    };
     for (int s = 0; s < pp.nsw; ++s) {
       TPSweep& sw = pp.sw[s];
       const uint32_t R = sweeps[s].R;
@@ -593,6 +611,34 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
       sw.npre = (uint8_t)sim.pre.size();
       // ---- body: levels of mutually commuting ops
       {
+        // peephole: ry(fixed alpha) -> CZ(q, thread-constant bit) -> ry on one register qubit q
+        // with nothing else on q in between becomes ONE rotation whose angle depends on the
+        // partner bit (the CZ itself turns into the pending Z frame, see PQC_K_CZF)
+        std::map<int, std::pair<double, int>> merged;    // ry op -> (alpha, partner amplitude bit)
+        std::vector<char> absorbed(N, 0);
+        static const bool no_merge = getenv("PQC_FRONT_NOMERGE") != nullptr;
+        static const bool no_czf = getenv("PQC_FRONT_NOCZF") != nullptr;
+        for (int q = 0; q < n && !no_merge && !no_czf; ++q) {
+          if (kof[q] < 0) continue;
+          std::vector<int> seq;
+          for (int i : sim.body)
+            if ((F.ops[i].support >> q) & 1u) seq.push_back(i);
+          for (size_t x = 0; x + 2 < seq.size(); ++x) {
+            const FOp& A = F.ops[seq[x]];
+            const FOp& C = F.ops[seq[x + 1]];
+            const FOp& B = F.ops[seq[x + 2]];
+            if (A.kind != PQC_OP_RY || A.param >= 0 || absorbed[seq[x]] || merged.count(seq[x])) continue;
+            if (C.kind != PQC_OP_CZ || B.kind != PQC_OP_RY) continue;
+            const int other = C.b0 == q ? C.b1 : C.b0;
+            if (kof[other] >= 0) continue;
+            merged[seq[x + 2]] = std::make_pair(A.offset, other);
+            absorbed[seq[x]] = absorbed[seq[x + 1]] = 1;
+            x += 2;
+          }
+        }
+        auto partner_byte = [&](int bit) -> uint8_t {
+          return lpos[bit] >= 0 ? (uint8_t)lpos[bit] : (uint8_t)(0x80 | bit);
+        };
         std::map<int, int> level;
         int maxlev = 0;
         for (int i : sim.body) {
@@ -607,8 +653,10 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
         for (int lv = 1; lv <= maxlev; ++lv) {
           std::vector<int> L;
           for (int i : sim.body)
-            if (level[i] == lv) L.push_back(i);
-          // 4-slot layer ops: class 0 rx, 1 real (ry / h), 2 rz on a register bit
+            if (level[i] == lv && !absorbed[i]) L.push_back(i);
+          // 4-slot layer ops: class 0 rx, 1 ry (or the ry / Hadamard mix), 2 rz on a register bit
+          bool level_has_h = false;
+          for (int i : L) level_has_h = level_has_h || F.ops[i].kind == PQC_OP_H;
           for (int cls = 0; cls < 3; ++cls) {
             std::vector<TPOp> packs;
             for (int i : L) {
@@ -620,21 +668,51 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
               if (cls == 2 && o.kind == PQC_OP_RZ && kof[o.b0] >= 0) code = 1;
               if (!code) continue;
               const int k = kof[o.b0];
-              if (k < 0) FRONT_FAIL(11);
+              if (k < 0) return false;
+              const bool is_merged = merged.count(i) != 0;
+              // a merged ry carries its own frame update: it may not share a REAL4 op (which
+              // flushes the frame for its Hadamards) -- the mix only occurs in initial layers
+              if (is_merged && level_has_h) return false;
               size_t q = 0;
               while (q < packs.size() && ((packs[q].sub >> (2 * k)) & 3)) ++q;
               if (q == packs.size()) {
                 TPOp t;
                 memset(&t, 0, sizeof(t));
-                t.kind = (uint8_t)(cls == 0 ? PQC_K_LAYER_RX4 : (cls == 1 ? PQC_K_LAYER_REAL4 : PQC_K_LAYER_RZ4));
+                t.kind = (uint8_t)(cls == 0 ? PQC_K_LAYER_RX4
+                                            : (cls == 2 ? PQC_K_LAYER_RZ4
+                                                        : (level_has_h ? PQC_K_LAYER_REAL4 : PQC_K_LAYER_RY4)));
                 t.a = t.b = 0xff;
+                if (t.kind == PQC_K_LAYER_RY4) t.wt = t.nterms = 0xff;
                 packs.push_back(t);
               }
               packs[q].sub |= (uint8_t)(code << (2 * k));
-              if (code == 1) packs[q].t[k] = (uint16_t)trig_of(0, o);
+              if (is_merged) {
+                const std::pair<double, int>& mg = merged[i];
+                packs[q].t[k] = (uint16_t)trig_pair(o, mg.first);
+                const uint8_t pb = partner_byte(mg.second);
+                if (k == 0) packs[q].a = pb;
+                else if (k == 1) packs[q].b = pb;
+                else if (k == 2) packs[q].wt = pb;
+                else packs[q].nterms = pb;
+              } else if (code == 1) {
+                packs[q].t[k] = (uint16_t)trig_of(0, o);
+              }
             }
             for (const TPOp& t : packs)
-              if (!push(t)) FRONT_FAIL(12);
+              if (!push(t)) return false;
+          }
+          // CZ(register bit, thread-constant bit): the pending Z frame
+          for (int i : L) {
+            const FOp& o = F.ops[i];
+            if (o.kind != PQC_OP_CZ) continue;
+            const int k0 = kof[o.b0], k1 = kof[o.b1];
+            if ((k0 >= 0) == (k1 >= 0) || no_czf) continue;
+            TPOp t;
+            memset(&t, 0, sizeof(t));
+            t.kind = PQC_K_CZF;
+            t.a = (uint8_t)(k0 >= 0 ? k0 : k1);
+            t.b = partner_byte(k0 >= 0 ? o.b1 : o.b0);
+            if (!push(t)) return false;
           }
           // XY pair rotations
           for (int i : L) {
@@ -662,7 +740,7 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
               t.t[0] = (uint16_t)trig_of(1, o);
               t.t[1] = (uint16_t)o.b0;
               if (!push(t)) FRONT_FAIL(15);
-            } else if (o.kind == PQC_OP_CZ) {
+            } else if (o.kind == PQC_OP_CZ && (no_czf || (kof[o.b0] >= 0) == (kof[o.b1] >= 0))) {
               TPOp t;
               memset(&t, 0, sizeof(t));
               t.kind = PQC_OP_CZ;

@@ -93,6 +93,300 @@ __global__ void k_mw_finalize(const double* __restrict__ acc, long long S, int n
   Q[s] = 2.0 * (1.0 - (1.0 / n) * tot);
 }
 
+// ---------------------------------------------------------------------------------
+// Meyer-Wallach for n > 14: every qubit's (r00, Re r01, Im r01) from ONE read of the state per
+// group of tile bits -- all 12 bits of a 4096-amplitude tile in pass 0, 8 more bits per further
+// pass (3 reads at 28 qubits instead of the n / 2 of k_mw_accumulate) -- and bitwise
+// reproducible: a CTA walks a fixed range of tiles of one state, every tile's 16 values per
+// sweep are reduced over the warp by a fixed halving exchange and accumulated per lane, CTA and
+// chunk sums are added in a fixed order (no floating-point atomics).
+// Sweep A holds tile positions 8-11 in registers (loaded straight from global memory, lanes on
+// amplitude bits 0-3), B positions 0-3, C positions 4-7 (through swizzled shared memory).
+// r11 = N - r00 with the norm N taken in pass 0.
+// ---------------------------------------------------------------------------------
+struct MWPass {
+  int tb[12];                // amplitude bit of tile position p
+  int ob[PQC_MAX_QUBITS];    // amplitude bits outside the tile, ascending
+  int doB, doC;              // sweeps B / C carry target bits (A always does)
+};
+
+__device__ __forceinline__ uint32_t mw_swz(uint32_t i) {
+  return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u);
+}
+
+// (r00, Re r01, Im r01) of register bit K over the thread's 16 amplitudes
+template <int K>
+__device__ __forceinline__ void mw_bit(const c128 (&a)[16], double& r00, double& xr, double& xi) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j & (1 << K)) continue;
+    const c128 x = a[j], y = a[j | (1 << K)];
+    s0 = fma(x.x, x.x, fma(x.y, x.y, s0));
+    s1 = fma(x.x, y.x, fma(x.y, y.y, s1));      // a0 * conj(a1)
+    s2 = fma(x.y, y.x, fma(-x.x, y.y, s2));
+  }
+  r00 = s0; xr = s1; xi = s2;
+}
+
+// warp reduce-scatter of 16 values: afterwards lane l holds the warp total of value (l >> 1) & 15
+__device__ __forceinline__ double mw_reduce16(double (&v)[16], int lane) {
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int m = 16 >> step, half = 8 >> step;      // lane-xor distance, values kept
+    const bool hi = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < half) {
+        const double send = hi ? v[i] : v[half + i];
+        const double keep = hi ? v[half + i] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+      }
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <bool DOB, bool DOC>
+__global__ void __launch_bounds__(256, 2) k_mw_tiles(const c128* __restrict__ states, int n,
+                                                     const MWPass P, int tiles_per_cta, int cps,
+                                                     double* __restrict__ part) {
+  extern __shared__ __align__(16) c128 mw_sm[];
+  __shared__ double wred[3][8][16];
+  const int tid = threadIdx.x, lo = tid & 15, hi = tid >> 4, lane = tid & 31, warp = tid >> 5;
+  const long long s = blockIdx.x / cps;
+  const int chunk = blockIdx.x % cps;
+  const int tiles_log2 = n - 12;
+  const c128* psi = states + (s << n);
+  uint32_t ampA = (uint32_t)lo;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ampA |= (((uint32_t)hi >> i) & 1u) << P.tb[4 + i];
+  const uint32_t g0 = 1u << P.tb[8], g1 = 1u << P.tb[9], g2 = 1u << P.tb[10], g3 = 1u << P.tb[11];
+  const uint32_t sbA = mw_swz((uint32_t)tid), sbB = mw_swz((uint32_t)tid << 4),
+                 sbC = mw_swz((uint32_t)lo | ((uint32_t)hi << 8));
+  double accA = 0.0, accB = 0.0, accC = 0.0;
+#define MW_SEL4(j, a0, a1, a2, a3) \
+  ((((j)&1) ? (a0) : 0u) | (((j)&2) ? (a1) : 0u) | (((j)&4) ? (a2) : 0u) | (((j)&8) ? (a3) : 0u))
+#define MW_CA(j) ((((j) << 8) ^ ((((j) << 2) ^ ((j) >> 1)) & 7)))   /* swz(j << 8) */
+#define MW_CB(j) (((j) ^ ((j) >> 3)))                               /* swz(j)      */
+#define MW_CC(j) ((((j) << 4) ^ ((((j) << 1) ^ ((j) >> 2)) & 7)))   /* swz(j << 4) */
+  for (int ti = 0; ti < tiles_per_cta; ++ti) {
+    const uint32_t tile = (uint32_t)chunk * (uint32_t)tiles_per_cta + (uint32_t)ti;
+    uint32_t tbase = 0;
+    for (int j = 0; j < tiles_log2; ++j) tbase |= ((tile >> j) & 1u) << P.ob[j];
+    c128 a[16];
+    {
+      const c128* sp = psi + (tbase | ampA);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a[j] = sp[MW_SEL4(j, g0, g1, g2, g3)];
+    }
+    double v[16];
+    {
+      mw_bit<0>(a, v[0], v[1], v[2]);
+      mw_bit<1>(a, v[3], v[4], v[5]);
+      mw_bit<2>(a, v[6], v[7], v[8]);
+      mw_bit<3>(a, v[9], v[10], v[11]);
+      // the thread's share of the norm: r00 + r11 of register bit 0
+      double nr = v[0];
+#pragma unroll
+      for (int j = 1; j < 16; j += 2) nr = fma(a[j].x, a[j].x, fma(a[j].y, a[j].y, nr));
+      v[12] = nr;
+      v[13] = v[14] = v[15] = 0.0;
+      accA += mw_reduce16(v, lane);
+    }
+    if (DOB || DOC) {
+      if (ti > 0) __syncthreads();                // the previous tile's readers are done
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mw_sm[sbA ^ MW_CA(j)] = a[j];
+      __syncthreads();
+      if (DOB) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = mw_sm[sbB ^ MW_CB(j)];
+        mw_bit<0>(a, v[0], v[1], v[2]);
+        mw_bit<1>(a, v[3], v[4], v[5]);
+        mw_bit<2>(a, v[6], v[7], v[8]);
+        mw_bit<3>(a, v[9], v[10], v[11]);
+        v[12] = v[13] = v[14] = v[15] = 0.0;
+        accB += mw_reduce16(v, lane);
+      }
+      if (DOC) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = mw_sm[sbC ^ MW_CC(j)];
+        mw_bit<0>(a, v[0], v[1], v[2]);
+        mw_bit<1>(a, v[3], v[4], v[5]);
+        mw_bit<2>(a, v[6], v[7], v[8]);
+        mw_bit<3>(a, v[9], v[10], v[11]);
+        v[12] = v[13] = v[14] = v[15] = 0.0;
+        accC += mw_reduce16(v, lane);
+      }
+    }
+  }
+#undef MW_CA
+#undef MW_CB
+#undef MW_CC
+  // warps in a fixed order; lane 2 i of a warp holds value i
+  if ((lane & 1) == 0) {
+    wred[0][warp][lane >> 1] = accA;
+    wred[1][warp][lane >> 1] = accB;
+    wred[2][warp][lane >> 1] = accC;
+  }
+  __syncthreads();
+  if (tid < 48) {
+    const int sw = tid >> 4, i = tid & 15;
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += wred[sw][w][i];
+    part[((long long)blockIdx.x) * 48 + tid] = t;
+  }
+}
+
+struct MWFin {
+  int npass, cps;
+  int src_pass[PQC_MAX_QUBITS];   // per amplitude bit: pass and value slot (sweep * 16 + 3 k)
+  int src_slot[PQC_MAX_QUBITS];
+};
+
+// part: [pass][state][chunk][48]; chunks added in order; Q = 2 (1 - 1/n sum_k Tr rho_k^2)
+__global__ void k_mw_tiles_fin(const double* __restrict__ part, long long S, int n, const MWFin F,
+                               double* __restrict__ Q, double* __restrict__ acc_out) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  auto total = [&](int pass, int slot) {
+    const double* p = part + (((long long)pass * S + s) * F.cps) * 48 + slot;
+    double t = 0.0;
+    for (int c = 0; c < F.cps; ++c) t += p[(long long)c * 48];
+    return t;
+  };
+  const double N = total(0, 12);
+  double tot = 0.0;
+  for (int b = 0; b < n; ++b) {
+    const double r00 = total(F.src_pass[b], F.src_slot[b]);
+    const double xr = total(F.src_pass[b], F.src_slot[b] + 1);
+    const double xi = total(F.src_pass[b], F.src_slot[b] + 2);
+    const double r11 = N - r00;
+    tot += r00 * r00 + r11 * r11 + 2.0 * (xr * xr + xi * xi);
+    if (acc_out) {                               // k_mw_accumulate's layout, by QUBIT index
+      double* o = acc_out + (s * n + (n - 1 - b)) * 4;
+      o[0] = r00; o[1] = r11; o[2] = xr; o[3] = xi;
+    }
+  }
+  if (Q) Q[s] = 2.0 * (1.0 - (1.0 / n) * tot);
+}
+
+static bool mw_tiles_enabled() {                 // PQC_MW=generic keeps k_mw_accumulate
+  const char* e = getenv("PQC_MW");
+  return !(e && strcmp(e, "generic") == 0);
+}
+
+// d_Q and / or d_acc ([S][n][4], the layout of k_mw_accumulate) may be null
+static int mw_tiles(const c128* d_states, long long S, int n, double* d_Q, double* d_acc,
+                    cudaStream_t st) {
+  const int T = 1 << (n - 12);
+  // chunks per state: enough CTAs to fill the GPU twice over, a power of two dividing T
+  int cps = 1;
+  while (cps < T && S * cps < 2 * 148 * 2) cps *= 2;
+  const int tpc = T / cps;
+  if (S * cps > 0x7fffffffLL) PQC_FAIL(-1, "Meyer-Wallach grid too large; split the batch");
+  MWPass passes[4];
+  MWFin fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.cps = cps;
+  int np = 0;
+  {
+    // pass 0: bits 0-11; later passes: bits 0-3 and the next 8 (or 4, padded) bits
+    int next = 0;
+    while (next < n) {
+      if (np >= 4) PQC_FAIL(-5, "internal: too many Meyer-Wallach passes");
+      MWPass& p = passes[np];
+      memset(&p, 0, sizeof(p));
+      bool in[32] = {false};
+      if (np == 0) {
+        for (int i = 0; i < 12; ++i) { p.tb[i] = i; in[i] = true; }
+        p.doB = p.doC = 1;
+        for (int i = 0; i < 12; ++i) {
+          const int sw = i >= 8 ? 0 : (i < 4 ? 1 : 2), k = i & 3;
+          fin.src_pass[i] = 0;
+          fin.src_slot[i] = sw * 16 + 3 * k;
+        }
+        next = 12;
+      } else {
+        const int left = n - next;
+        for (int i = 0; i < 4; ++i) { p.tb[i] = i; in[i] = true; }
+        const int nA = std::min(4, left);          // new bits on positions 8-11 first
+        int filler = 4;                            // bits 4-11 were measured in pass 0
+        auto take_filler = [&]() {
+          while (in[filler]) ++filler;
+          in[filler] = true;
+          return filler;
+        };
+        // positions must ascend with the amplitude bit inside the tile only for readability; any
+        // assignment works because every address is built from per-position masks
+        for (int k = 0; k < 4; ++k) {
+          if (k < nA) {
+            p.tb[8 + k] = next + k; in[next + k] = true;
+            fin.src_pass[next + k] = np;
+            fin.src_slot[next + k] = 0 * 16 + 3 * k;
+          } else {
+            p.tb[8 + k] = -1;
+          }
+        }
+        const int nC = std::min(4, left - nA);
+        for (int k = 0; k < 4; ++k) {
+          if (k < nC) {
+            p.tb[4 + k] = next + nA + k; in[next + nA + k] = true;
+            fin.src_pass[next + nA + k] = np;
+            fin.src_slot[next + nA + k] = 2 * 16 + 3 * k;
+          } else {
+            p.tb[4 + k] = -1;
+          }
+        }
+        for (int i = 4; i < 12; ++i)
+          if (p.tb[i] < 0) p.tb[i] = take_filler();
+        p.doB = 0;
+        p.doC = nC > 0 ? 1 : 0;
+        next += nA + nC;
+      }
+      int o = 0;
+      for (int b = 0; b < n; ++b)
+        if (!in[b]) p.ob[o++] = b;
+      ++np;
+    }
+  }
+  fin.npass = np;
+  double* part = nullptr;
+  PQC_CUDA(cudaMallocAsync(&part, sizeof(double) * 48 * (size_t)np * S * cps, st));
+  static bool attr[64] = {false};
+  int dev = 0;
+  PQC_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr[dev]) {
+    PQC_CUDA(cudaFuncSetAttribute(k_mw_tiles<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    PQC_CUDA(cudaFuncSetAttribute(k_mw_tiles<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    PQC_CUDA(cudaFuncSetAttribute(k_mw_tiles<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    attr[dev] = true;
+  }
+  int rc = 0;
+  for (int q = 0; q < np && rc == 0; ++q) {
+    double* pp = part + (size_t)q * S * cps * 48;
+    const unsigned grid = (unsigned)(S * cps);
+    if (passes[q].doB)
+      k_mw_tiles<true, true><<<grid, 256, 65536, st>>>(d_states, n, passes[q], tpc, cps, pp);
+    else if (passes[q].doC)
+      k_mw_tiles<false, true><<<grid, 256, 65536, st>>>(d_states, n, passes[q], tpc, cps, pp);
+    else
+      k_mw_tiles<false, false><<<grid, 256, 0, st>>>(d_states, n, passes[q], tpc, cps, pp);
+    ++g_pqc_launches;
+    if (cudaGetLastError() != cudaSuccess) rc = -2;
+  }
+  if (rc == 0) {
+    k_mw_tiles_fin<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(part, S, n, fin, d_Q, d_acc);
+    ++g_pqc_launches;
+    if (cudaGetLastError() != cudaSuccess) rc = -2;
+  }
+  cudaFreeAsync(part, st);
+  if (rc) pqc_set_error("Meyer-Wallach tile kernel launch failed");
+  return rc;
+}
+
 static int mw_accumulate(const c128* d_states, long long S, int n, double* d_acc, cudaStream_t st) {
   const int chunk_log2 = std::min(n, 14);
   const long long grid = S << (n - chunk_log2);
@@ -108,6 +402,7 @@ extern "C" int pqc_meyer_wallach(const pqc_c128* d_states, int64_t S, int n, dou
   if (S <= 0) return 0;
   if (n < 1 || n > PQC_MAX_QUBITS) PQC_FAIL(-1, "bad qubit count");
   cudaStream_t st = (cudaStream_t)stream;
+  if (n > 14 && mw_tiles_enabled()) return mw_tiles((const c128*)d_states, S, n, d_Q, nullptr, st);
   double* acc = nullptr;
   PQC_CUDA(cudaMallocAsync(&acc, sizeof(double) * 4 * n * S, st));
   int rc = mw_accumulate((const c128*)d_states, S, n, acc, st);
@@ -135,7 +430,9 @@ extern "C" int pqc_ptrace_1q(const pqc_c128* d_state, int n, int qubit, pqc_c128
   cudaStream_t st = (cudaStream_t)stream;
   double* acc = nullptr;
   PQC_CUDA(cudaMallocAsync(&acc, sizeof(double) * 4 * n, st));
-  int rc = mw_accumulate((const c128*)d_state, 1, n, acc, st);
+  int rc = (n > 14 && mw_tiles_enabled())
+               ? mw_tiles((const c128*)d_state, 1, n, nullptr, acc, st)
+               : mw_accumulate((const c128*)d_state, 1, n, acc, st);
   if (rc == 0) {
     k_rho_from_acc<<<1, 1, 0, st>>>(acc, n, qubit, (c128*)d_rho);
     ++g_pqc_launches;

@@ -79,17 +79,150 @@ __device__ __forceinline__ void op_rz_t(c128 (&a)[16], double t) {
   }
 }
 
+__device__ __forceinline__ uint32_t tp_partner_bit(uint32_t pb, uint32_t lidx, uint32_t tbase) {
+  return (pb & 0x80u) ? ((tbase >> (pb & 0x7fu)) & 1u) : ((lidx >> pb) & 1u);
+}
+__device__ __forceinline__ double tp_flip(double v, uint32_t s31) {
+  return __hiloint2double(__double2hiint(v) ^ (int)s31, __double2loint(v));
+}
+// apply the pending Z frame: amplitudes whose register bit k is 1 change sign where fz bit k is set
+__device__ __forceinline__ void tp_zflush(c128 (&a)[16], uint32_t& fz) {
+  const uint32_t m0 = (fz & 1u) << 31, m1 = ((fz >> 1) & 1u) << 31, m2 = ((fz >> 2) & 1u) << 31,
+                 m3 = ((fz >> 3) & 1u) << 31;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const uint32_t m = ((j & 1) ? m0 : 0u) ^ ((j & 2) ? m1 : 0u) ^ ((j & 4) ? m2 : 0u) ^ ((j & 8) ? m3 : 0u);
+    a[j] = make_double2(tp_flip(a[j].x, m), tp_flip(a[j].y, m));
+  }
+  fz = 0u;
+}
+
 // the ops of one sweep on the 16 register amplitudes.  lidx = the thread's logical tile index
 // (register bits zero), tbase = the tile's amplitude offset, tile = its index.
+// The 4-slot layer ops run all four slots unconditionally (identity parameters for absent gates):
+// straight-line code with an even number of register-set hand-overs, so the compiler needs no
+// register moves at the interpreter's merge point (a lone conditional rotation costs 32 moves).
 template <bool GEN>
 __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const TPSweep& sw, int ob,
                                        int oe, const double2* trig, uint32_t lidx, uint32_t tbase,
                                        uint32_t tile, int tiles_log2, int gen, const PipeArgs& A,
                                        double& fscale) {
+  uint32_t fz = 0u;                               // pending Z frame, one bit per register bit
+  // cos factors that depend on a partner bit differ from thread to thread, and the thread ->
+  // amplitude map changes with the sweep: they are applied before this sweep ends (fscale, which
+  // is the same for every thread of a sample, rides on to the last sweep)
+  double lscale = 1.0;
+  // tangent-form amplitudes grow by 1 / |cos| per rotation (1.6e16 at an angle of exactly pi):
+  // a deep pass at Clifford angles would overflow, so the pending scale is applied early once
+  // it is tiny.  Never taken at generic angles.
+#define TP_RESCALE()                                                         \
+  {                                                                          \
+    if (fabs(fscale) < 1e-100) { op_scale(a, fscale); fscale = 1.0; }        \
+    if (fabs(lscale) < 1e-100) { op_scale(a, lscale); lscale = 1.0; }        \
+  }
+  const double2 ident = make_double2(0.0, 1.0);   // (tan, cos) of angle 0
   for (int oi = ob; oi < oe; ++oi) {
     const TPOp op = P->ops[oi];
     const int kind = op.kind;
-    if (kind == PQC_OP_RZ || kind == PQC_OP_CZ) {
+    if (kind == PQC_K_LAYER_RY4) {
+      const int sk = op.sub;
+      double2 c0 = ident, c1 = ident, c2 = ident, c3 = ident;
+#define TP_RY_SLOT(K, PB, C)                                                       \
+  if (sk & (3 << (2 * K))) {                                                       \
+    uint32_t e = op.t[K];                                                          \
+    if ((PB) != 0xff) {                                                            \
+      const uint32_t bb = tp_partner_bit(PB, lidx, tbase);                         \
+      e += bb;                                                                     \
+      fz ^= bb << K;                                                               \
+      C = trig[e];                                                                 \
+      lscale *= C.y;                                                               \
+      C.y = 1.0;                                                                   \
+    } else {                                                                       \
+      C = trig[e];                                                                 \
+    }                                                                              \
+    if ((fz >> K) & 1u) C.x = -C.x;                                                \
+  }
+      TP_RY_SLOT(0, op.a, c0) TP_RY_SLOT(1, op.b, c1) TP_RY_SLOT(2, op.wt, c2) TP_RY_SLOT(3, op.nterms, c3)
+#undef TP_RY_SLOT
+      op_ry_t<0>(a, c0.x);
+      op_ry_t<1>(a, c1.x);
+      op_ry_t<2>(a, c2.x);
+      op_ry_t<3>(a, c3.x);
+      fscale *= (c0.y * c1.y) * (c2.y * c3.y);
+      TP_RESCALE()
+    } else if (kind == PQC_K_LAYER_RZ4) {
+      const int sk = op.sub;
+      double2 c0 = ident, c1 = ident, c2 = ident, c3 = ident;
+      if (sk & 0x03) c0 = trig[op.t[0]];
+      if (sk & 0x0c) c1 = trig[op.t[1]];
+      if (sk & 0x30) c2 = trig[op.t[2]];
+      if (sk & 0xc0) c3 = trig[op.t[3]];
+      op_rz_t<0>(a, c0.x);
+      op_rz_t<1>(a, c1.x);
+      op_rz_t<2>(a, c2.x);
+      op_rz_t<3>(a, c3.x);
+      fscale *= (c0.y * c1.y) * (c2.y * c3.y);
+      TP_RESCALE()
+    } else if (kind == PQC_K_LAYER_RX4) {
+      const int sk = op.sub;
+      double2 c0 = ident, c1 = ident, c2 = ident, c3 = ident;
+      if (sk & 0x03) c0 = trig[op.t[0]];
+      if (sk & 0x0c) c1 = trig[op.t[1]];
+      if (sk & 0x30) c2 = trig[op.t[2]];
+      if (sk & 0xc0) c3 = trig[op.t[3]];
+      if (fz & 1u) c0.x = -c0.x;
+      if (fz & 2u) c1.x = -c1.x;
+      if (fz & 4u) c2.x = -c2.x;
+      if (fz & 8u) c3.x = -c3.x;
+      op_rx_t<0>(a, c0.x);
+      op_rx_t<1>(a, c1.x);
+      op_rx_t<2>(a, c2.x);
+      op_rx_t<3>(a, c3.x);
+      fscale *= (c0.y * c1.y) * (c2.y * c3.y);
+      TP_RESCALE()
+    } else if (kind == PQC_K_CZF) {
+      fz ^= tp_partner_bit(op.b, lidx, tbase) << op.a;
+    } else if (kind == PQC_K_RXY) {
+      double2 cs = trig[op.t[0]];
+      const int ka = op.a >> 2, kb = op.a & 3;
+      if (((fz >> ka) ^ (fz >> kb)) & 1u) cs.y = -cs.y;
+      switch (op.a) {
+        case 1: op_xy<0, 1>(a, cs.x, cs.y); break;
+        case 2: op_xy<0, 2>(a, cs.x, cs.y); break;
+        case 3: op_xy<0, 3>(a, cs.x, cs.y); break;
+        case 6: op_xy<1, 2>(a, cs.x, cs.y); break;
+        case 7: op_xy<1, 3>(a, cs.x, cs.y); break;
+        default: op_xy<2, 3>(a, cs.x, cs.y); break;
+      }
+    } else if (kind == PQC_K_ZZSUM || kind == PQC_K_GEN) {
+      // w(x) = w(tile) ^ w(thread part) ^ w(register value j); wn holds w per tile nibble value
+      const uint32_t(*wn)[16] = P->wn[op.wt];
+      uint32_t w0 = wn[0][lidx & 15u] ^ wn[1][(lidx >> 4) & 15u] ^ wn[2][lidx >> 8];
+      for (int jb = 0; jb < tiles_log2; ++jb) w0 ^= ((tile >> jb) & 1u) ? P->wo[op.wt][jb] : 0u;
+      const uint32_t w1 = wn[sw.rpos[0] >> 2][1u << (sw.rpos[0] & 3)];
+      const uint32_t w2 = wn[sw.rpos[1] >> 2][1u << (sw.rpos[1] & 3)];
+      const uint32_t w3 = wn[sw.rpos[2] >> 2][1u << (sw.rpos[2] & 3)];
+      const uint32_t w4 = wn[sw.rpos[3] >> 2][1u << (sw.rpos[3] & 3)];
+      if (kind == PQC_K_ZZSUM) {
+        const double2* tz = trig + op.t[0];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const double2 ph = tz[__popc(w0 ^ XSEL4R(j, w1, w2, w3, w4))];
+          const c128 v = a[j];
+          a[j] = make_double2(v.x * ph.x - v.y * ph.y, v.y * ph.x + v.x * ph.y);
+        }
+      } else if (GEN && gen == op.spawn) {
+        const double cr = A.spawn_cr[gen], ci = A.spawn_ci[gen];
+        const int nt = op.nterms;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const double f = (double)(nt - 2 * __popc(w0 ^ XSEL4R(j, w1, w2, w3, w4)));
+          const double fr = f * cr, fi = f * ci;
+          const c128 v = a[j];
+          a[j] = make_double2(v.x * fr - v.y * fi, v.y * fr + v.x * fi);
+        }
+      }
+    } else if (kind == PQC_OP_RZ || kind == PQC_OP_CZ) {
       // ---- a run of diagonal ops: accumulate, then apply once (as k_layer_seq)
       double tc = 1.0, ts = 0.0;                  // thread-level phase (tc + i ts)
       double pc[4] = {1.0, 1.0, 1.0, 1.0}, pn[4] = {0.0, 0.0, 0.0, 0.0};   // bit k = 1: (pc + i pn)
@@ -147,32 +280,14 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
       }
       if (sg) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if ((sg >> j) & 1u) a[j] = make_double2(-a[j].x, -a[j].y);
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t m = ((sg >> j) & 1u) << 31;
+          a[j] = make_double2(tp_flip(a[j].x, m), tp_flip(a[j].y, m));
+        }
       }
-      continue;
-    }
-    if (kind == PQC_K_LAYER_RX4) {
-      const int sk = op.sub;
-      double2 c0 = make_double2(0.0, 1.0), c1 = c0, c2 = c0, c3 = c0;
-      if (sk & 0x03) c0 = trig[op.t[0]];
-      if (sk & 0x0c) c1 = trig[op.t[1]];
-      if (sk & 0x30) c2 = trig[op.t[2]];
-      if (sk & 0xc0) c3 = trig[op.t[3]];
-      op_rx_t<0>(a, c0.x);
-      op_rx_t<1>(a, c1.x);
-      op_rx_t<2>(a, c2.x);
-      op_rx_t<3>(a, c3.x);
-      fscale *= (c0.y * c1.y) * (c2.y * c3.y);
-    } else if (kind == PQC_K_LAYER_RZ4) {
-      const int sk = op.sub;
-      double f = 1.0;
-      if (sk & 0x03) { const double2 tc = trig[op.t[0]]; op_rz_t<0>(a, tc.x); f *= tc.y; }
-      if (sk & 0x0c) { const double2 tc = trig[op.t[1]]; op_rz_t<1>(a, tc.x); f *= tc.y; }
-      if (sk & 0x30) { const double2 tc = trig[op.t[2]]; op_rz_t<2>(a, tc.x); f *= tc.y; }
-      if (sk & 0xc0) { const double2 tc = trig[op.t[3]]; op_rz_t<3>(a, tc.x); f *= tc.y; }
-      fscale *= f;
     } else if (kind == PQC_K_LAYER_REAL4) {
+      // ry / Hadamard mix (initial layers): H does not commute with a pending Z frame
+      if (fz) tp_zflush(a, fz);
       const int sk = op.sub;
       double f = 1.0;
 #define TP_REAL_SLOT(K)                                                    \
@@ -184,46 +299,14 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
       TP_REAL_SLOT(0) TP_REAL_SLOT(1) TP_REAL_SLOT(2) TP_REAL_SLOT(3)
 #undef TP_REAL_SLOT
       fscale *= f;
-    } else if (kind == PQC_K_RXY) {
-      const double2 cs = trig[op.t[0]];
-      switch (op.a) {
-        case 1: op_xy<0, 1>(a, cs.x, cs.y); break;
-        case 2: op_xy<0, 2>(a, cs.x, cs.y); break;
-        case 3: op_xy<0, 3>(a, cs.x, cs.y); break;
-        case 6: op_xy<1, 2>(a, cs.x, cs.y); break;
-        case 7: op_xy<1, 3>(a, cs.x, cs.y); break;
-        default: op_xy<2, 3>(a, cs.x, cs.y); break;
-      }
-    } else if (kind == PQC_K_ZZSUM || kind == PQC_K_GEN) {
-      // w(x) = w(tile) ^ w(thread part) ^ w(register value j); wn holds w per tile nibble value
-      const uint32_t(*wn)[16] = P->wn[op.wt];
-      uint32_t w0 = wn[0][lidx & 15u] ^ wn[1][(lidx >> 4) & 15u] ^ wn[2][lidx >> 8];
-      for (int jb = 0; jb < tiles_log2; ++jb) w0 ^= ((tile >> jb) & 1u) ? P->wo[op.wt][jb] : 0u;
-      const uint32_t w1 = wn[sw.rpos[0] >> 2][1u << (sw.rpos[0] & 3)];
-      const uint32_t w2 = wn[sw.rpos[1] >> 2][1u << (sw.rpos[1] & 3)];
-      const uint32_t w3 = wn[sw.rpos[2] >> 2][1u << (sw.rpos[2] & 3)];
-      const uint32_t w4 = wn[sw.rpos[3] >> 2][1u << (sw.rpos[3] & 3)];
-      if (kind == PQC_K_ZZSUM) {
-        const double2* tz = trig + op.t[0];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const double2 ph = tz[__popc(w0 ^ XSEL4R(j, w1, w2, w3, w4))];
-          const c128 v = a[j];
-          a[j] = make_double2(v.x * ph.x - v.y * ph.y, v.y * ph.x + v.x * ph.y);
-        }
-      } else if (GEN && gen == op.spawn) {
-        const double cr = A.spawn_cr[gen], ci = A.spawn_ci[gen];
-        const int nt = op.nterms;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const double f = (double)(nt - 2 * __popc(w0 ^ XSEL4R(j, w1, w2, w3, w4)));
-          const double fr = f * cr, fi = f * ci;
-          const c128 v = a[j];
-          a[j] = make_double2(v.x * fr - v.y * fi, v.y * fr + v.x * fi);
-        }
-      }
+      TP_RESCALE()
+    } else if (kind == PQC_K_ZFLUSH) {
+      if (fz) tp_zflush(a, fz);
     }
   }
+  if (fz) tp_zflush(a, fz);
+  if (lscale != 1.0) op_scale(a, lscale);
+#undef TP_RESCALE
 }
 
 #define TP_LIN4(x, a0, a1, a2, a3) \
@@ -534,6 +617,8 @@ bool pqc_pipe_build(const V1Pass& ps, int n, PipePlan& pp) {
       o.kind = (uint8_t)f.kind;
       o.a = o.b = 0xff;
       if (f.kind == PQC_K_LAYER_RX4 || f.kind == PQC_K_LAYER_REAL4) {
+        // REAL4 stays REAL4 (not LAYER_RY4): its cos factors multiply in slot order, which is
+        // what keeps these plans bit-identical to k_layer_pass / k_layer_seq
         for (int k = 0; k < 4; ++k) {
           const int kd = ((f.subk >> (8 * k)) & 0xff) - 1;
           int code = 0;

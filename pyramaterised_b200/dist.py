@@ -36,24 +36,41 @@ def shard_rows(array, rank=None, world=None):
     return array[lo:hi]
 
 
-def all_gather_rows(local, n_rows):
-    """Concatenate the per-rank row blocks (shard_bounds order) on every rank."""
+def _as_real(t):
+    """NCCL has no complex dtype: complex tensors travel as their float64 (re, im) view."""
+    return torch.view_as_real(t) if t.is_complex() else t
+
+
+def all_gather_rows(local, n_rows, async_op=False):
+    """Concatenate the per-rank row blocks (shard_bounds order) on every rank with ONE
+    all_gather_into_tensor on a preallocated buffer (no per-rank list, no torch.cat when the
+    blocks are equal).  async_op: returns (tensor, finish) -- call finish() before reading rows
+    of other ranks; the caller may work on its own rows meanwhile."""
     rank, world = rank_world()
     if world == 1:
-        return local
+        return (local, lambda: local) if async_op else local
     sizes = [shard_bounds(n_rows, r, world)[1] - shard_bounds(n_rows, r, world)[0]
              for r in range(world)]
     pad = max(sizes)
-    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    buf[:local.shape[0]] = local
-    if local.is_complex():           # NCCL has no complex dtype: ship as float64 pairs
-        parts = [torch.empty_like(torch.view_as_real(buf)) for _ in range(world)]
-        dist.all_gather(parts, torch.view_as_real(buf).contiguous())
-        parts = [torch.view_as_complex(p) for p in parts]
+    tail = tuple(local.shape[1:])
+    even = min(sizes) == pad
+    out = torch.empty((world * pad,) + tail, dtype=local.dtype, device=local.device)
+    if even:
+        src = local.contiguous()
     else:
-        parts = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(parts, buf)
-    return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+        src = torch.zeros((pad,) + tail, dtype=local.dtype, device=local.device)
+        src[:local.shape[0]] = local
+    work = dist.all_gather_into_tensor(_as_real(out), _as_real(src), async_op=True)
+
+    def finish():
+        work.wait()
+        if even:
+            return out
+        return torch.cat([out[r * pad:r * pad + sizes[r]] for r in range(world)], dim=0)
+
+    if async_op:
+        return out, finish
+    return finish()
 
 
 def triangle_blocks(n_rows, rank, world):
@@ -88,18 +105,74 @@ def sharded_fidelity_hist(all_states, bins, pair_hist=_engine_pair_hist):
     return hist
 
 
+def shard_pair_plan(n_rows, rank, world):
+    """Pairs this rank histograms when every rank holds its own row block first and the gathered
+    set later: its diagonal block (needs no communication) and, per other shard q, either the
+    whole cross block (shard `rank` x shard q) or, for the shard at distance world / 2 (even
+    world), half of the rows of the lower shard.  Returns (own, cross) with own = (lo, hi) and
+    cross = [(row_lo, row_hi, col_lo, col_hi)]; over all ranks every unordered pair is covered
+    exactly once."""
+    own = shard_bounds(n_rows, rank, world)
+    cross = []
+    for d in range(1, world):
+        q = (rank + d) % world
+        if 2 * d < world:
+            cross.append(own + shard_bounds(n_rows, q, world))
+        elif 2 * d == world:
+            a, b = min(rank, q), max(rank, q)
+            alo, ahi = shard_bounds(n_rows, a, world)
+            mid = (alo + ahi) // 2
+            rows = (alo, mid) if rank == a else (mid, ahi)
+            cross.append(rows + shard_bounds(n_rows, b, world))
+    return own, [c for c in cross if c[1] > c[0] and c[3] > c[2]]
+
+
 def sharded_expressibility(local_states, n_total, hilbert_dim, pair_hist=_engine_pair_hist,
-                           kl=None):
-    """Measurements.expressibility over a sample set whose rows are sharded across ranks."""
+                           kl=None, timings=None):
+    """Measurements.expressibility over a sample set whose rows are sharded across ranks: the
+    all-gather of the states runs while every rank histograms the pairs inside its own block;
+    cross blocks follow, then ONE int64 all-reduce.  `timings` (dict) receives the seconds spent
+    waiting for the gather, in the pair kernels and in the all-reduce (host clock around
+    synchronised regions; for bench.py)."""
     from . import engine
-    allst = all_gather_rows(local_states, n_total)
+    import time
+    rank, world = rank_world()
     n_pairs = n_total * (n_total - 1) // 2
     if n_pairs == 0:
         return 0
     bins = engine.n_bins(n_pairs)
     if bins <= 0:
         raise ValueError("`bins` must be positive, when an integer")
-    hist = sharded_fidelity_hist(allst, bins, pair_hist)
+    cuda = local_states.is_cuda
+
+    def sync():
+        if cuda:
+            torch.cuda.synchronize()
+
+    sync()
+    t0 = time.perf_counter()
+    allst, finish = all_gather_rows(local_states, n_total, async_op=True)
+    hist = torch.zeros((bins,), dtype=torch.int64, device=local_states.device)
+    if local_states.shape[0] > 1:
+        hist += pair_hist(local_states, local_states, True, bins)
+    sync()
+    t1 = time.perf_counter()
+    allst = finish()
+    sync()
+    t2 = time.perf_counter()
+    _, cross = shard_pair_plan(n_total, rank, world)
+    for rlo, rhi, clo, chi in cross:
+        hist += pair_hist(allst[rlo:rhi], allst[clo:chi], False, bins)
+    sync()
+    t3 = time.perf_counter()
+    if world > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    sync()
+    t4 = time.perf_counter()
+    if timings is not None:
+        timings.update({"diag_block_s": t1 - t0, "gather_wait_s": t2 - t1, "cross_blocks_s": t3 - t2,
+                        "all_reduce_s": t4 - t3, "hist_bytes": int(bins) * 8,
+                        "gather_bytes_per_rank": int(allst.numel() * allst.element_size())})
     if kl is None:
         return float(engine.kl_haar(hist, hilbert_dim).item())
     return kl(hist, hilbert_dim)
@@ -111,16 +184,35 @@ def streamed_rows(n_blocks, rank, world):
     return [i for i in range(n_blocks) if (i % (2 * world)) in (rank, 2 * world - 1 - rank)]
 
 
+def _bcast_states(t, src):
+    dist.broadcast(_as_real(t), src=src)
+
+
 def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_engine_pair_hist,
-                            kl=None, per_block=None):
+                            kl=None, per_block=None, resident_blocks=None, checkpoint=None,
+                            stats=None, progress=None):
     """Measurements.expressibility for a sample set whose states cannot be resident together
-    (BASELINE config 5: 4 GiB per 28-qubit state).  `run_block(lo, hi)` returns the states of
-    samples [lo, hi) of the ONE global angle stream; two blocks are resident at a time and
-    blocks are regenerated as needed, so every unordered pair is histogrammed exactly once
-    (measure.py:133-159).  Block rows are dealt over the ranks; the int64 histograms are summed
-    with one all-reduce and KL is evaluated on every rank.  `per_block(lo, hi, states)` is called
-    once per owned diagonal block (e.g. to take Meyer-Wallach Q of the same states)."""
+    (BASELINE config 5: 4 GiB per 28-qubit state; measure.py:123-159).
+
+    `run_block(lo, hi)` returns the states of samples [lo, hi) of the ONE global angle stream.
+    The sample set is cut into blocks of `block` states.  Work proceeds in ROUNDS: in a round the
+    ranks together keep `resident_blocks` row blocks per rank resident (block i lives on rank
+    i % world, generated there once), then every column block j at or after the round's first
+    row travels ONCE to every rank -- from its owner's resident copy if it is a row of this
+    round, else generated by rank j % world -- as an NVLink broadcast, and every rank histograms
+    it against its resident rows i < j (the owner of row j also takes the pairs inside block j).
+    With resident_blocks * world >= n_blocks every state is generated exactly once; the
+    regenerate-per-rank form of round 1 needed n_blocks^2 / 2 generations.
+    One int64 all-reduce at the end; KL on every rank.
+
+    `per_block(lo, hi, states)` is called once per block on its owner in round order (e.g.
+    Meyer-Wallach of the same states).  `checkpoint`: path prefix; each rank saves (histogram,
+    next round, next column) after every column and resumes from its file when it exists --
+    the int64 counts make a resumed run bit-identical to an uninterrupted one.  `stats` (dict)
+    receives generations, broadcasts and their bytes for this rank.  `progress(round, column,
+    n_rounds, n_blocks)` is called on every rank after each column (and its checkpoint)."""
     from . import engine
+    import os
     rank, world = rank_world()
     n_pairs = n_total * (n_total - 1) // 2
     if n_pairs == 0:
@@ -129,25 +221,87 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
     if bins <= 0:
         raise ValueError("`bins` must be positive, when an integer")
     nb = (n_total + block - 1) // block
+    if resident_blocks is None:
+        resident_blocks = max(1, (nb + world - 1) // world)
+    per_round = resident_blocks * world            # row blocks resident across the ranks
+
+    def bounds(i):
+        return i * block, min(n_total, (i + 1) * block)
+
+    st = {"generations": 0, "broadcasts": 0, "broadcast_bytes": 0, "rounds": 0, "resumed": 0}
     hist = None
-    for i in streamed_rows(nb, rank, world):
-        lo, hi = i * block, min(n_total, (i + 1) * block)
-        A = run_block(lo, hi)
+    start_round, start_col = 0, -1
+    ck = f"{checkpoint}.rank{rank}" if checkpoint else None
+    if ck and os.path.exists(ck):
+        saved = torch.load(ck)
+        if saved["n_total"] == n_total and saved["block"] == block and saved["world"] == world \
+                and saved["per_round"] == per_round and saved["bins"] == bins:
+            hist = saved["hist"]
+            start_round, start_col = saved["round"], saved["col"]
+            st["resumed"] = 1
+    dev = None
+    n_rounds = (nb + per_round - 1) // per_round
+    for rnd in range(start_round, n_rounds):
+        r0, r1 = rnd * per_round, min(nb, (rnd + 1) * per_round)
+        rows = {}
+        for i in range(r0, r1):
+            if i % world != rank:
+                continue
+            lo, hi = bounds(i)
+            rows[i] = run_block(lo, hi)
+            st["generations"] += hi - lo
+            dev = rows[i].device
+            if per_block is not None and not (rnd == start_round and i <= start_col):
+                per_block(lo, hi, rows[i])
+        if dev is None:
+            dev = engine.device() if torch.cuda.is_available() else torch.device("cpu")
         if hist is None:
-            hist = torch.zeros((bins,), dtype=torch.int64, device=A.device)
-        if per_block is not None:
-            per_block(lo, hi, A)
-        hist += pair_hist(A, A, True, bins)
-        for j in range(i + 1, nb):
-            B = run_block(j * block, min(n_total, (j + 1) * block))
-            hist += pair_hist(A, B, False, bins)
-            del B
-        del A
-    if hist is None:                      # a rank without rows still joins the all-reduce
+            hist = torch.zeros((bins,), dtype=torch.int64, device=dev)
+        hist = hist.to(dev)
+        for j in range(r0, nb):
+            if rnd == start_round and j <= start_col:
+                continue                           # finished before the checkpoint was written
+            lo, hi = bounds(j)
+            owner = j % world
+            if j in rows:
+                B = rows[j]
+            elif owner == rank:
+                B = run_block(lo, hi)
+                st["generations"] += hi - lo
+            else:
+                ref = next(iter(rows.values())) if rows else None
+                D = ref.shape[1] if ref is not None else None
+                if D is None:
+                    D = run_block(0, 0).shape[1]
+                B = torch.empty((hi - lo, D), dtype=torch.complex128, device=dev)
+            if world > 1:
+                _bcast_states(B, owner)
+                st["broadcasts"] += 1
+                st["broadcast_bytes"] += int(B.numel() * B.element_size())
+            for i, A in rows.items():
+                if i < j:
+                    hist += pair_hist(A, B, False, bins)
+                elif i == j and A.shape[0] > 1:
+                    hist += pair_hist(A, A, True, bins)
+            if j not in rows:
+                del B
+            if ck:
+                torch.save({"hist": hist.cpu(), "round": rnd, "col": j, "n_total": n_total,
+                            "block": block, "world": world, "per_round": per_round, "bins": bins},
+                           ck + ".tmp")
+                os.replace(ck + ".tmp", ck)
+            if progress is not None:
+                progress(rnd, j, n_rounds, nb)
+        rows.clear()
+        start_col = -1
+        st["rounds"] += 1
+    if hist is None:                      # nothing to do on this rank: still joins the all-reduce
         hist = torch.zeros((bins,), dtype=torch.int64,
                            device=engine.device() if torch.cuda.is_available() else "cpu")
     if world > 1:
         dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    if stats is not None:
+        stats.update(st)
     if kl is None:
         return float(engine.kl_haar(hist, hilbert_dim).item())
     return kl(hist, hilbert_dim)

@@ -152,26 +152,51 @@ class Measurements:
             return 0
         return self._expr_of_states(states, N)
 
-    def expressibility_streamed(self, sample_N, block, want_Q=False):
+    def expressibility_streamed(self, sample_N, block, want_Q=False, resident_blocks=None,
+                                checkpoint=None, stats=None):
         """expressibility(sample_N) -- and entanglement(sample_N) with want_Q -- for circuits
         whose states do not fit in memory together (additive API; BASELINE config 5).  Draws the
-        same angle stream, keeps two blocks of `block` states resident and regenerates blocks as
-        needed; under torch.distributed the block rows are dealt over the ranks."""
+        same angle stream and hands blocks of `block` states to dist.streamed_expressibility:
+        every rank keeps `resident_blocks` row blocks resident (default: what fits in 70 % of the
+        free device memory, at most its share of all blocks), every column block is generated
+        ONCE per round by its owner and broadcast to the other ranks over NVLink.
+        `checkpoint` (path prefix) persists the int64 histogram and the position after every
+        column block, so a multi-hour run resumes where it stopped with identical counts; the
+        Meyer-Wallach values of a resumed run cover only the blocks generated after the restart
+        (their owner keeps them in `<checkpoint>.rank<r>.Q.json`, merged on resume)."""
         from . import dist as pdist
+        import json
+        import os
         N = 2 ** self.QC.n_qubits
         if sample_N <= 0:
             return (0, []) if want_Q else 0
         ang = self.QC.draw_random(sample_N)
+        rank, world = pdist.rank_world()
+        if resident_blocks is None:
+            nb = (sample_N + block - 1) // block
+            share = (nb + world - 1) // world
+            free = torch.cuda.mem_get_info()[0] if torch.cuda.is_available() else 1 << 62
+            fit = int(0.7 * free // (block * 16 * N)) - 1        # one more block travels
+            resident_blocks = max(1, min(share, fit))
         Q = {}
+        qfile = f"{checkpoint}.rank{rank}.Q.json" if checkpoint and want_Q else None
+        if qfile and os.path.exists(qfile):
+            Q = {int(k): v for k, v in json.load(open(qfile)).items()}
 
         def run_block(lo, hi):
             return self.QC.program.run(ang[lo:hi], init=self.QC.initial_state.tensor)
 
         def per_block(lo, hi, states):
             Q[lo] = engine.meyer_wallach(states).cpu().numpy().tolist()
+            if qfile:
+                with open(qfile + ".tmp", "w") as f:
+                    json.dump(Q, f)
+                os.replace(qfile + ".tmp", qfile)
 
         e = pdist.streamed_expressibility(run_block, sample_N, block, N,
-                                          per_block=per_block if want_Q else None)
+                                          per_block=per_block if want_Q else None,
+                                          resident_blocks=resident_blocks, checkpoint=checkpoint,
+                                          stats=stats)
         if not want_Q:
             return e
         return e, [q for lo in sorted(Q) for q in Q[lo]]     # this rank's rows, in sample order

@@ -32,7 +32,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, S, q):
+def _worker(rank, world, port, S, q, tmp):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -51,6 +51,37 @@ def _worker(rank, world, port, S, q):
             lambda a, b: torch.from_numpy(orc.run(specs, 4, ang[a:b])), S, 7, 16,
             pair_hist=_np_pair_hist, kl=_np_kl)
         assert abs(es - e) < 1e-15                               # block-streamed == gathered
+        # several rounds (one resident block per rank), interrupted and resumed from the checkpoint
+        run_block = lambda a, b: torch.from_numpy(orc.run(specs, 4, ang[a:b]))   # noqa: E731
+        ck = os.path.join(tmp, "ck")
+
+        class Stop(Exception):
+            pass
+
+        def stop_at(rnd, j, n_rounds, nb):
+            if (rnd, j) == (1, 5):
+                raise Stop()
+
+        try:
+            pdist.streamed_expressibility(run_block, S, 7, 16, pair_hist=_np_pair_hist, kl=_np_kl,
+                                          resident_blocks=1, checkpoint=ck, progress=stop_at)
+            raise AssertionError("the interruption hook did not fire")
+        except Stop:
+            pass
+        assert os.path.exists(f"{ck}.rank{rank}")
+        st = {}
+        er = pdist.streamed_expressibility(run_block, S, 7, 16, pair_hist=_np_pair_hist, kl=_np_kl,
+                                           resident_blocks=1, checkpoint=ck, stats=st)
+        assert st["resumed"] == 1 and st["rounds"] < 5           # 9 blocks, 2 per round
+        assert abs(er - e) < 1e-15                               # resumed == uninterrupted
+        st1 = {}
+        e1 = pdist.streamed_expressibility(run_block, S, 7, 16, pair_hist=_np_pair_hist, kl=_np_kl,
+                                           stats=st1)
+        assert abs(e1 - e) < 1e-15 and st1["rounds"] == 1
+        # every state generated exactly once over the ranks when all row blocks are resident
+        gen = torch.tensor([st1["generations"]])
+        dist.all_reduce(gen)
+        assert int(gen) == S
         qv = torch.tensor([orc.single_Q(s, 4) for s in local.numpy()])
         mean, std = pdist.gathered_mean_std(qv, S)
         q.put((rank, allst.numpy(), e, h.numpy(), mean, std))
@@ -58,12 +89,13 @@ def _worker(rank, world, port, S, q):
         dist.destroy_process_group()
 
 
-def test_world2_matches_single_process():
+def test_world2_matches_single_process(tmp_path):
     S, world = 61, 2
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, S, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, S, q, str(tmp_path)))
+             for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
@@ -103,6 +135,16 @@ def test_partitions_cover_everything_once():
             assert np.array_equal(seen, np.triu(np.ones((S, S), dtype=int), 1))
             if S >= 8 * world:                                # balanced within ~25 %
                 assert max(work) <= 1.25 * (sum(work) / world) + S
+            seen = np.zeros((S, S), dtype=int)                # own block first, cross blocks later
+            for r in range(world):
+                (lo, hi), cross = pdist.shard_pair_plan(S, r, world)
+                for i in range(lo, hi):
+                    seen[i, i + 1:hi] += 1
+                for rlo, rhi, clo, chi in cross:
+                    assert (rlo, rhi) != (clo, chi)
+                    a, b = np.meshgrid(np.arange(rlo, rhi), np.arange(clo, chi), indexing="ij")
+                    np.add.at(seen, (np.minimum(a, b), np.maximum(a, b)), 1)
+            assert np.array_equal(seen, np.triu(np.ones((S, S), dtype=int), 1))
             for nb in (1, 5, 16):                             # streamed block rows: a partition
                 rows = sorted(i for r in range(world) for i in pdist.streamed_rows(nb, r, world))
                 assert rows == list(range(nb))

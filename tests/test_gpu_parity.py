@@ -436,6 +436,28 @@ def test_full_depth_states_vs_oracle(kind, n, p):
     assert abs(float(engine.meyer_wallach(st[:1])[0].item()) - orc.single_Q(ref[0], n)) < ATOL
 
 
+@pytest.mark.parametrize("n,S", [(15, 3), (16, 5), (19, 2), (20, 1), (23, 1), (24, 1)])
+def test_meyer_wallach_tile_kernel_matches_generic_and_oracle(n, S, monkeypatch):
+    """n > 14: k_mw_tiles (all 12 tile bits per read, 8 more per further pass, fixed-order
+    reductions) against k_mw_accumulate (PQC_MW=generic), the oracle, ptrace and itself run twice
+    (bitwise reproducible: no floating-point atomics)."""
+    qc = pyqc.templates.generate_circuit("generic_HE", n, 2)
+    ang = np.random.default_rng(n).random((S, qc.n_true_params)) * 2 * np.pi
+    st = qc.run_batch(ang)
+    Q1 = engine.meyer_wallach(st)
+    Q2 = engine.meyer_wallach(st)
+    assert torch.equal(Q1, Q2)
+    monkeypatch.setenv("PQC_MW", "generic")
+    Q0 = engine.meyer_wallach(st)
+    rho0 = engine.ptrace_1q(st[0], n - 3).cpu().numpy()
+    monkeypatch.delenv("PQC_MW")
+    rho1 = engine.ptrace_1q(st[0], n - 3).cpu().numpy()
+    assert np.abs((Q1 - Q0).cpu().numpy()).max() < 1e-12
+    assert np.abs(rho1 - rho0).max() < 1e-12
+    if n <= 20:
+        assert abs(float(Q1[0].item()) - orc.single_Q(st[0].cpu().numpy(), n)) < ATOL
+
+
 def test_ragged_and_empty_batches():
     """Batch edges: a QFIM batch that does not fill its last 256-set chunk, a single row, an
     empty batch; every row must equal the one-row call bit for bit (fixed summation orders)."""
