@@ -99,6 +99,10 @@ PQC_API long long pqc_launch_count(void);
  * (vectors x 2 x 16 x 2^n per launch), out[3] = reserved. */
 PQC_API int pqc_profile_begin(void);
 PQC_API int pqc_profile_end(double* out4);
+/* Per-kernel split of the region closed by the last pqc_profile_end: out[3 k + {0, 1, 2}] =
+ * summed ms, launches, algorithmic bytes of pass-kernel kind k = 0 k_apply_pass,
+ * 1 k_sweep_pass, 2 k_layer_pass, 3 k_layer_seq, 4 k_tile_pipe. */
+PQC_API int pqc_profile_kinds(double* out, int n_kinds);
 /* Fails (<0) unless the current CUDA device is compute capability 10.x. */
 PQC_API int pqc_device_check(int* cc_major, int* cc_minor, int* n_sms);
 
@@ -126,7 +130,8 @@ PQC_API int pqc_run_batch(const pqc_program* prog, const double* d_angles, int64
 /* ---- PQC.get_gradients (circuit.py:149-192): d_out [S, P+1, D]; slot 0 = the final
  * state, slot 1+p = derivative state for parameter slot p, i.e. U_G..(D_p U_p)..U_1|init>
  * with D_p the sum of the Pauli generators of the gate's members (gates.py:133-138,
- * 454-457,519-522).  init_stride must be 0 (one shared initial state). */
+ * 454-457,519-522).  init_stride: 0 (one shared initial state) or 2^n (one per sample; used
+ * when a circuit is run in segments around a dense ARBGATE). */
 PQC_API int pqc_gradients_batch(const pqc_program* prog, const double* d_angles, int64_t ld_angles,
                         int64_t n_samples, const pqc_c128* d_init, int64_t init_stride,
                         pqc_c128* d_out, void* stream);
@@ -195,6 +200,17 @@ PQC_API int pqc_pauli_expect_batch(const pqc_c128* d_states, int64_t n_samples, 
 PQC_API int pqc_pauli_apply_batch(const pqc_c128* d_states, int64_t n_samples, int n_qubits,
                           int n_terms, const pqc_pauli_term* h_terms, pqc_c128* d_out,
                           void* stream);
+
+/* ---- ARBGATE (gates.py:407-435): exp(-i theta H) of a dense Hermitian H = V diag(lambda) V^dagger,
+ * as products with the eigenvector matrix instead of a matrix exponential per angle:
+ *   out[s][r] = sum_c M[r][c] * w(s, c) * in[s][c],   M row-major [2^n][2^n],
+ *   w = 1 when d_lambda is NULL; else exp(-i theta_s lambda_c), times (-i lambda_c / 2) when
+ *   `deriv` != 0 (the reference's derivative -i H / 2, gates.py:426-428); theta_s =
+ *   d_theta[s * theta_stride].  The gate is the call with M = V^dagger followed by the call with
+ *   M = V and the eigenvalues.  Out of place; n <= 13. */
+PQC_API int pqc_dense_apply_batch(const pqc_c128* d_in, int64_t n_samples, int n_qubits,
+                          const pqc_c128* d_M, const double* d_lambda, const double* d_theta,
+                          int64_t theta_stride, int deriv, pqc_c128* d_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ SIGNATURES = {
     "pqc_abi_version": [],
     "pqc_profile_begin": [],
     "pqc_profile_end": [C.POINTER(_DBL)],
+    "pqc_profile_kinds": [C.POINTER(_DBL), _INT],
     "pqc_device_check": [C.POINTER(_INT), C.POINTER(_INT), C.POINTER(_INT)],
     "pqc_program_create": [_INT, _INT, _INT, C.POINTER(PqcOp), C.POINTER(_P)],
     "pqc_program_destroy": [_P],
@@ -60,6 +61,7 @@ SIGNATURES = {
     "pqc_magic_batch": [_P, _I64, _INT, _INT, C.POINTER(_DBL), _P, _P],
     "pqc_pauli_expect_batch": [_P, _I64, _INT, _INT, C.POINTER(PqcPauliTerm), _P, _P],
     "pqc_pauli_apply_batch": [_P, _I64, _INT, _INT, C.POINTER(PqcPauliTerm), _P, _P],
+    "pqc_dense_apply_batch": [_P, _I64, _INT, _P, _P, _P, _I64, _INT, _P, _P],
 }
 
 _lib = None

@@ -121,7 +121,10 @@ class PQC():
     @property
     def program(self):
         if self._program is None:
-            self._program = engine.Program(self.n_qubits, self.n_true_params, self.lower())
+            if any(hasattr(g, "_lam") for g in self.gates):        # dense gates (ARBGATE)
+                self._program = engine.SegmentedProgram(self.n_qubits, self.gates)
+            else:
+                self._program = engine.Program(self.n_qubits, self.n_true_params, self.lower())
         return self._program
 
     def _derivatives_exact(self):

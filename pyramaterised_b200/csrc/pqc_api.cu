@@ -324,7 +324,8 @@ extern "C" int pqc_gradients_batch(const pqc_program* prog, const double* d_angl
   if (S <= 0) return 0;
   if (!prog->grad_supported) PQC_FAIL(-4, "derivative states unsupported: " + prog->grad_reason);
   if (prog->P > 0 && (!d_angles || ld < prog->P)) PQC_FAIL(-1, "No parameters supplied!");
-  if (init_stride != 0) PQC_FAIL(-1, "derivative states take one shared initial state");
+  if (init_stride != 0 && init_stride != ((int64_t)1 << prog->n))
+    PQC_FAIL(-1, "initial states: one shared state (stride 0) or one per sample (stride 2^n)");
   cudaStream_t st = (cudaStream_t)stream;
   if (pqc_program_upload(prog)) return -2;
   if (prog->v1_grad_ok && !pqc_use_v0()) {
@@ -334,7 +335,7 @@ extern "C" int pqc_gradients_batch(const pqc_program* prog, const double* d_angl
     PQC_CUDA(cudaMallocAsync(&scratch, bytes, st));
     const bool even = (pqc_v1_n_passes(prog, true) % 2) == 0;
     c128* fin = nullptr;
-    int rc = pqc_v1_derivatives(prog, d_angles, ld, S, (const c128*)d_init, 0,
+    int rc = pqc_v1_derivatives(prog, d_angles, ld, S, (const c128*)d_init, init_stride,
                                 even ? (c128*)d_out : scratch, even ? scratch : (c128*)d_out,
                                 nullptr, false, true, &fin, st);
     if (rc == 0 && fin != (c128*)d_out)

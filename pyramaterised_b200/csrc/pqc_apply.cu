@@ -205,7 +205,15 @@ int pqc_plan_program(pqc_program* prog) {
 // exercised by the CPU test-suite).
 int pqc_program_upload(const pqc_program* cprog) {
   pqc_program* prog = const_cast<pqc_program*>(cprog);
-  if (prog->uploaded) return 0;
+  int dev = 0;
+  PQC_CUDA(cudaGetDevice(&dev));
+  if (prog->uploaded) {
+    // the plan's device arrays live on the GPU that was current at the first use
+    if (dev != prog->device)
+      PQC_FAIL(-1, "this program was uploaded on another CUDA device; create one program per device");
+    return 0;
+  }
+  prog->device = dev;
   auto up = [&](auto& vec, auto** dptr) -> int {
     if (vec.empty()) return 0;
     PQC_CUDA(cudaMalloc(dptr, vec.size() * sizeof(vec[0])));
@@ -437,7 +445,8 @@ __global__ void __launch_bounds__(NT) k_apply_pass(const PassArgs a) {
 }
 
 // ---- optional per-launch timing of the gate-apply kernel (bench.py roofline) ------------
-struct ProfRec { cudaEvent_t e0, e1; double bytes; };
+struct ProfRec { cudaEvent_t e0, e1; double bytes; int kind; };
+static double g_prof_kinds[PQC_PROF_KINDS][3];   // of the last pqc_profile_end: ms, launches, bytes
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_prof_pool;
@@ -463,12 +472,17 @@ extern "C" int pqc_profile_begin(void) {
 extern "C" int pqc_profile_end(double* out4) {
   g_prof_on = false;
   double ms = 0.0, bytes = 0.0;
+  memset(g_prof_kinds, 0, sizeof(g_prof_kinds));
   for (auto& r : g_prof) {
     PQC_CUDA(cudaEventSynchronize(r.e1));
     float t = 0.f;
     PQC_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
     ms += t;
     bytes += r.bytes;
+    const int k = r.kind >= 0 && r.kind < PQC_PROF_KINDS ? r.kind : 0;
+    g_prof_kinds[k][0] += t;
+    g_prof_kinds[k][1] += 1.0;
+    g_prof_kinds[k][2] += r.bytes;
   }
   if (out4) {
     out4[0] = ms;
@@ -481,9 +495,19 @@ extern "C" int pqc_profile_end(double* out4) {
   return 0;
 }
 
-int pqc_prof_launch_begin(double bytes, cudaStream_t st) {
+// the per-kernel split of the region closed by the last pqc_profile_end:
+// out[3 * kind + {0, 1, 2}] = ms, launches, algorithmic bytes
+extern "C" int pqc_profile_kinds(double* out, int n_kinds) {
+  if (!out) return -1;
+  for (int k = 0; k < n_kinds; ++k)
+    for (int c = 0; c < 3; ++c) out[3 * k + c] = k < PQC_PROF_KINDS ? g_prof_kinds[k][c] : 0.0;
+  return 0;
+}
+
+int pqc_prof_launch_begin(double bytes, cudaStream_t st, int kind) {
   if (!g_prof_on) return -1;
   ProfRec rec;
+  rec.kind = kind;
   rec.e0 = prof_event();
   rec.e1 = prof_event();
   rec.bytes = bytes;
@@ -498,15 +522,14 @@ void pqc_prof_launch_end(int h, cudaStream_t st) {
 
 template <int NT>
 static int launch_nt(const PassArgs& a, long long grid, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PqcDeviceOnce attr_once;
+  if (attr_once.first()) {
     PQC_CUDA(cudaFuncSetAttribute(k_apply_pass<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   200 * 1024));
-    attr_set = true;
   }
   // algorithmic traffic of one pass: every vector read once and written once
   const int h = pqc_prof_launch_begin(
-      (double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st);
+      (double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st, PQC_PROF_APPLY_PASS);
   k_apply_pass<NT><<<(unsigned)grid, NT, smem, st>>>(a);
   pqc_prof_launch_end(h, st);
   PQC_LAUNCH_CHECK();

@@ -329,6 +329,7 @@ struct pqc_program {
   int front_tj0 = 0, front_ntj = 0, front_slots = 0;
   PipePlan* d_pipe = nullptr;
   bool uploaded = false;
+  int device = -1;               // CUDA device holding the uploaded plan (and the trig scratch)
   MOp* d_mops = nullptr;
   SweepD* d_sweeps = nullptr;
   TrigJob* d_tjobs = nullptr;
@@ -422,7 +423,22 @@ bool pqc_plan_front(pqc_program* prog, std::vector<TrigJob>& tjobs);
 bool pqc_use_front(const pqc_program* prog);
 int pqc_pipe_launch(const PipeArgs& a, const PipePlan& hplan, cudaStream_t st);
 bool pqc_pipe_enabled();
-int pqc_prof_launch_begin(double bytes, cudaStream_t st);
+// Per-device one-time setup (the shared-memory opt-in of a kernel is a per-device attribute):
+// first() is true the first time it is asked on the current device.
+struct PqcDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+// pass-kernel kinds reported separately by pqc_profile_end_kinds
+enum { PQC_PROF_APPLY_PASS = 0, PQC_PROF_SWEEP_PASS = 1, PQC_PROF_LAYER_PASS = 2,
+       PQC_PROF_LAYER_SEQ = 3, PQC_PROF_TILE_PIPE = 4, PQC_PROF_KINDS = 5 };
+int pqc_prof_launch_begin(double bytes, cudaStream_t st, int kind);
 void pqc_prof_launch_end(int h, cudaStream_t st);
 int pqc_pauli_apply_slots(const c128* src, c128* dst, int n, long long S, int slots_total,
                           int src_slot, int dst_slot, const GenTerm* d_terms, int nterms,

@@ -950,12 +950,11 @@ extern "C" int pqc_fidelity_hist(const pqc_c128* d_A, int64_t n_a, const pqc_c12
   }
   const bool use_dmma = n >= 4 && !(force && strcmp(force, "fma") == 0);
   if (use_dmma) {
-    static bool attr_set = false;
+    static PqcDeviceOnce attr_once;
     const size_t smem = 4 * DT * DROW * sizeof(c128);
-    if (!attr_set) {
+    if (attr_once.first()) {
       PQC_CUDA(cudaFuncSetAttribute(k_fidelity_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
-      attr_set = true;
     }
     k_fidelity_dmma<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(
         (const c128*)d_A, n_a, (const c128*)d_B, n_b, n, triangular, bins,
@@ -983,7 +982,7 @@ __device__ __forceinline__ double bin_mid(long long i, long long B, double step)
 }
 
 __global__ void __launch_bounds__(256) k_kl_sums(const long long* __restrict__ hist, long long B,
-                                                 double step, double N, double* __restrict__ scratch) {
+                                                 double step, double N, double* __restrict__ part) {
   __shared__ double red[32];
   double sc = 0.0, sh = 0.0;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < B; i += (long long)gridDim.x * 256) {
@@ -992,14 +991,29 @@ __global__ void __launch_bounds__(256) k_kl_sums(const long long* __restrict__ h
   }
   sc = block_sum<256>(sc, red);
   sh = block_sum<256>(sh, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(scratch + 0, sc);
-    atomicAdd(scratch + 1, sh);
+  if (threadIdx.x == 0) {                     // per-CTA partials, added in CTA order by k_kl_fold
+    part[2 * blockIdx.x + 0] = sc;
+    part[2 * blockIdx.x + 1] = sh;
+  }
+}
+
+// out[c] = sum over CTAs of part[cta * ncomp + c], in a fixed order (one CTA)
+__global__ void __launch_bounds__(256) k_kl_fold(const double* __restrict__ part, int nparts,
+                                                 int ncomp, double* __restrict__ out) {
+  __shared__ double red[32];
+  for (int c = 0; c < ncomp; ++c) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 256) t += part[i * ncomp + c];
+    t = block_sum<256>(t, red);
+    if (threadIdx.x == 0) out[c] = t;
+    __syncthreads();
   }
 }
 
 __global__ void __launch_bounds__(256) k_kl_terms(const long long* __restrict__ hist, long long B,
-                                                  double step, double N, double* __restrict__ scratch) {
+                                                  double step, double N,
+                                                  const double* __restrict__ scratch,
+                                                  double* __restrict__ part) {
   __shared__ double red[32];
   const double tc = scratch[0], th = scratch[1];
   double kl = 0.0;
@@ -1013,7 +1027,7 @@ __global__ void __launch_bounds__(256) k_kl_terms(const long long* __restrict__ 
     kl += t;
   }
   kl = block_sum<256>(kl, red);
-  if (threadIdx.x == 0) atomicAdd(scratch + 2, kl);
+  if (threadIdx.x == 0) part[blockIdx.x] = kl;
 }
 
 __global__ void k_copy1(const double* src, double* dst) { *dst = *src; }
@@ -1025,11 +1039,19 @@ extern "C" int pqc_kl_haar(const long long* d_hist, int64_t bins, double N, doub
   PQC_CUDA(cudaMemsetAsync(d_scratch, 0, 4 * sizeof(double), st));
   const long long grid = std::min<long long>((bins + 255) / 256, 148 * 8);
   const double step = 1.0 / (double)bins;
-  k_kl_sums<<<(unsigned)grid, 256, 0, st>>>(d_hist, bins, step, N, d_scratch);
-  k_kl_terms<<<(unsigned)grid, 256, 0, st>>>(d_hist, bins, step, N, d_scratch);
-  g_pqc_launches += 2;
+  // fixed-order reductions (no floating-point atomics): the result is bitwise reproducible
+  double* part = nullptr;
+  PQC_CUDA(cudaMallocAsync(&part, sizeof(double) * 2 * (size_t)grid, st));
+  k_kl_sums<<<(unsigned)grid, 256, 0, st>>>(d_hist, bins, step, N, part);
+  k_kl_fold<<<1, 256, 0, st>>>(part, (int)grid, 2, d_scratch);
+  k_kl_terms<<<(unsigned)grid, 256, 0, st>>>(d_hist, bins, step, N, d_scratch, part);
+  k_kl_fold<<<1, 256, 0, st>>>(part, (int)grid, 1, d_scratch + 2);
+  g_pqc_launches += 4;
   k_copy1<<<1, 1, 0, st>>>(d_scratch + 2, d_out);
-  PQC_LAUNCH_CHECK();
+  const cudaError_t le = cudaGetLastError();
+  cudaFreeAsync(part, st);
+  if (le != cudaSuccess) PQC_FAIL(-2, cudaGetErrorString(le));
+  ++g_pqc_launches;
   return 0;
 }
 
@@ -1049,8 +1071,9 @@ struct MagicArgs {
   int masks_per_cta;
   int n_alpha;
   double alpha[MAGIC_MAX_ALPHA];
-  double* sums;      // [n_alpha][S]
+  double* sums;      // [n_alpha][S][slices] per-CTA partial sums (folded by k_magic_finalize)
   long long S;
+  int slices;
 };
 
 __global__ void __launch_bounds__(256) k_magic(const MagicArgs a) {
@@ -1111,7 +1134,7 @@ __global__ void __launch_bounds__(256) k_magic(const MagicArgs a) {
   }
   for (int q = 0; q < a.n_alpha; ++q) {
     const double t = block_sum<256>(acc[q], red);
-    if (threadIdx.x == 0) atomicAdd(a.sums + (long long)q * a.S + s, t);
+    if (threadIdx.x == 0) a.sums[((long long)q * a.S + s) * a.slices + slice] = t;
   }
 }
 
@@ -1209,7 +1232,7 @@ __global__ void __launch_bounds__(256, 2) k_magic12(const MagicArgs a) {
   }
   for (int q = 0; q < a.n_alpha; ++q) {
     const double t = block_sum<256>(acc[q], red);
-    if (threadIdx.x == 0) atomicAdd(a.sums + (long long)q * a.S + s, t);
+    if (threadIdx.x == 0) a.sums[((long long)q * a.S + s) * a.slices + slice] = t;
   }
 }
 
@@ -1219,8 +1242,10 @@ __global__ void k_magic_finalize(double* __restrict__ out, long long S, int n, i
   if (e >= S * n_alpha) return;
   const int q = (int)(e / S);
   const double al = a.alpha[q];
-  // sum |2^{-n/2} W|^{2 alpha} = 2^{-n alpha} sum |W|^{2 alpha}
-  const double tot = out[e] * exp2(-(double)n * al);
+  // slices in a fixed order; sum |2^{-n/2} W|^{2 alpha} = 2^{-n alpha} sum |W|^{2 alpha}
+  double acc = 0.0;
+  for (int c = 0; c < a.slices; ++c) acc += a.sums[e * a.slices + c];
+  const double tot = acc * exp2(-(double)n * al);
   out[e] = 1.0 / (1.0 - al) * log(tot) - (double)n * 0.69314718055994530942;
 }
 
@@ -1238,18 +1263,18 @@ extern "C" int pqc_magic_batch(const pqc_c128* d_states, int64_t S, int n, int n
     if (h_alphas[q] == 1.0) PQC_FAIL(-1, "alpha = 1 is singular (1/(1-alpha))");
     a.alpha[q] = h_alphas[q];
   }
-  a.sums = d_out;
+  a.sums = nullptr;
   a.S = S;
+  a.slices = 1;
   const long long D = 1ll << n;
   // enough CTAs to fill the machine: >= 4 * 148 CTAs when the batch is small
   long long slices = std::max<long long>(1, std::min<long long>(D, (148 * 4 + S - 1) / S));
   a.masks_per_cta = (int)((D + slices - 1) / slices);
   slices = (D + a.masks_per_cta - 1) / a.masks_per_cta;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PqcDeviceOnce attr_once;
+  if (attr_once.first()) {
     PQC_CUDA(cudaFuncSetAttribute(k_magic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     PQC_CUDA(cudaFuncSetAttribute(k_magic12, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
   }
   const char* mg = getenv("PQC_MAGIC");       // PQC_MAGIC=generic: in-memory FWHT for every n
   const bool generic_only = mg && strcmp(mg, "generic") == 0;   // (read per call: tests compare)
@@ -1260,20 +1285,26 @@ extern "C" int pqc_magic_batch(const pqc_c128* d_states, int64_t S, int n, int n
     a.masks_per_cta = (int)((D + slices - 1) / slices);
     slices = (D + a.masks_per_cta - 1) / a.masks_per_cta;
     if (S * slices > 0x7fffffffLL) PQC_FAIL(-1, "magic grid too large; split the batch");
-    PQC_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * S * n_alpha, st));
+    a.slices = (int)slices;
+    PQC_CUDA(cudaMallocAsync(&a.sums, sizeof(double) * S * n_alpha * slices, st));
     k_magic12<<<(unsigned)(S * slices), 256, D * (sizeof(c128) + sizeof(double)), st>>>(a);
-    PQC_LAUNCH_CHECK();
     k_magic_finalize<<<(unsigned)((S * n_alpha + 127) / 128), 128, 0, st>>>(d_out, S, n, n_alpha, a);
-    PQC_LAUNCH_CHECK();
+    g_pqc_launches += 2;
+    const cudaError_t le = cudaGetLastError();
+    cudaFreeAsync(a.sums, st);
+    if (le != cudaSuccess) PQC_FAIL(-2, cudaGetErrorString(le));
     return 0;
   }
   const size_t smem = 3 * D * sizeof(double);
   if (S * slices > 0x7fffffffLL) PQC_FAIL(-1, "magic grid too large; split the batch");
-  PQC_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * S * n_alpha, st));
+  a.slices = (int)slices;
+  PQC_CUDA(cudaMallocAsync(&a.sums, sizeof(double) * S * n_alpha * slices, st));
   k_magic<<<(unsigned)(S * slices), 256, smem, st>>>(a);
-  PQC_LAUNCH_CHECK();
   k_magic_finalize<<<(unsigned)((S * n_alpha + 127) / 128), 128, 0, st>>>(d_out, S, n, n_alpha, a);
-  PQC_LAUNCH_CHECK();
+  g_pqc_launches += 2;
+  const cudaError_t le = cudaGetLastError();
+  cudaFreeAsync(a.sums, st);
+  if (le != cudaSuccess) PQC_FAIL(-2, cudaGetErrorString(le));
   return 0;
 }
 
@@ -1477,13 +1508,12 @@ static int eigh_launch(const double* d_mats, int64_t n_mats, int dim, double* d_
   if (smem > 200 * 1024)
     PQC_FAIL(-1, "eigh: matrix too large for the shared-memory Jacobi (dim <= 158, or 110 with vectors)");
   if (n_mats > 0x7fffffffLL) PQC_FAIL(-1, "too many matrices");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PqcDeviceOnce attr_once;
+  if (attr_once.first()) {
     PQC_CUDA(cudaFuncSetAttribute(k_jacobi_eigvals<false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     PQC_CUDA(cudaFuncSetAttribute(k_jacobi_eigvals<true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   if (d_vecs)
     k_jacobi_eigvals<true><<<(unsigned)n_mats, 128, smem, st>>>(d_mats, dim, Pp, d_eig, d_vecs);

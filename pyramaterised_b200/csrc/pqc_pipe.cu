@@ -683,7 +683,7 @@ int pqc_pipe_launch(const PipeArgs& a, const PipePlan& hplan, cudaStream_t st) {
   if (total <= 0) return 0;
   if (total > 0x7fffffffLL) PQC_FAIL(-1, "pass grid too large; split the batch");
   const unsigned grid = (unsigned)std::min<long long>(total, sms[dev]);
-  const int h = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st);
+  const int h = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st, PQC_PROF_TILE_PIPE);
   if (a.nspawn > 0) k_tile_pipe<true><<<grid, TP_THREADS, TP_SMEM_TOTAL, st>>>(a);
   else k_tile_pipe<false><<<grid, TP_THREADS, TP_SMEM_TOTAL, st>>>(a);
   pqc_prof_launch_end(h, st);

@@ -2629,13 +2629,12 @@ int pqc_v1_gram_qfim2(const pqc_program* prog, const c128* buf, int slots1, int 
   // ring depth: P <= 32 runs 2 CTAs per SM with 3 slots each, larger P one CTA with 2-4 slots
   const int ns = T <= 4 ? 3 : (int)std::max<size_t>(2, std::min<size_t>(GR_NS_MAX, (200 * 1024) / stage));
   const size_t smem = std::max((size_t)ns * stage, (size_t)ngrp * GR_TPW * 2 * 32 * sizeof(double));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PqcDeviceOnce attr_once;
+  if (attr_once.first()) {
     PQC_CUDA(cudaFuncSetAttribute(k_gram_real<256, 2, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     PQC_CUDA(cudaFuncSetAttribute(k_gram_real<384, 1, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   if (S * ksplit > 0x7fffffffLL) PQC_FAIL(-1, "gram grid too large");
   double* gp = reinterpret_cast<double*>(d_gpart);
@@ -2710,8 +2709,8 @@ static bool seq_enabled() {                  // PQC_SEQ=0: XXZ-type passes stay 
 static int launch_v1(const V1Args& a_in, cudaStream_t st) {
   V1Args a = a_in;
   a.pf_dist = (a.low_run >= 4) ? prefetch_dist() : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PqcDeviceOnce attr_once;
+  if (attr_once.first()) {
     PQC_CUDA(cudaFuncSetAttribute(k_sweep_pass<false, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     PQC_CUDA(cudaFuncSetAttribute(k_sweep_pass<true, false>,
@@ -2720,7 +2719,6 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     PQC_CUDA(cudaFuncSetAttribute(k_sweep_pass<true, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
   }
   const int ipc = 1 << a.items_log2;
   const long long groups = (a.n_items + ipc - 1) / ipc;
@@ -2779,18 +2777,17 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
     }
     f.plan = a.hpass->fast;
     f.pf_dist = a.pf_dist;
-    static bool fattr = false;
-    if (!fattr) {
+    static PqcDeviceOnce fattr_once;
+    if (fattr_once.first()) {
       PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       PQC_CUDA(cudaFuncSetAttribute(k_layer_pass<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      fattr = true;
     }
     const size_t fsmem = 4096 * sizeof(c128) + (size_t)a.ntrig * sizeof(double2);
-    const int hh = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st);
+    const int hh = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st, PQC_PROF_LAYER_PASS);
     const bool g = a.nspawn > 0;
     if (f.plan.ns == 3) {
       if (g) k_layer_pass<3, true><<<(unsigned)grid, 256, fsmem, st>>>(f);
@@ -2850,16 +2847,15 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
         f.st_ra[t] = 1u << a.lbit[rest[4 + t]];
       }
     }
-    static bool qattr = false;
-    if (!qattr) {
+    static PqcDeviceOnce qattr_once;
+    if (qattr_once.first()) {
       PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      qattr = true;
     }
     const size_t qsmem = 4096 * sizeof(c128) + (size_t)a.ntrig * sizeof(double2);
-    const int hq = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st);
+    const int hq = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st, PQC_PROF_LAYER_SEQ);
     const bool sp = a.nspawn > 0, dg = f.plan.has_diag != 0;
     if (sp && dg) k_layer_seq<true, true><<<(unsigned)grid, 256, qsmem, st>>>(f);
     else if (sp) k_layer_seq<true, false><<<(unsigned)grid, 256, qsmem, st>>>(f);
@@ -2876,7 +2872,7 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
   }
   const size_t smem = ((size_t)1 << V1_LOCAL_BITS) * sizeof(c128) +
                       (size_t)ipc * a.ntrig * sizeof(double2) + (size_t)smem_pad;
-  const int h = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st);
+  const int h = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st, PQC_PROF_SWEEP_PASS);
   const bool dots = a.npartners > 0, gen = a.nspawn > 0;
   if (dots && gen) k_sweep_pass<true, true><<<(unsigned)grid, V1_NT, smem, st>>>(a);
   else if (dots) k_sweep_pass<true, false><<<(unsigned)grid, V1_NT, smem, st>>>(a);

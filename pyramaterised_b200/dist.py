@@ -190,7 +190,7 @@ def _bcast_states(t, src):
 
 def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_engine_pair_hist,
                             kl=None, per_block=None, resident_blocks=None, checkpoint=None,
-                            stats=None, progress=None):
+                            stats=None, progress=None, state_dim=None):
     """Measurements.expressibility for a sample set whose states cannot be resident together
     (BASELINE config 5: 4 GiB per 28-qubit state; measure.py:123-159).
 
@@ -210,7 +210,9 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
     next round, next column) after every column and resumes from its file when it exists --
     the int64 counts make a resumed run bit-identical to an uninterrupted one.  `stats` (dict)
     receives generations, broadcasts and their bytes for this rank.  `progress(round, column,
-    n_rounds, n_blocks)` is called on every rank after each column (and its checkpoint)."""
+    n_rounds, n_blocks)` is called on every rank after each column (and its checkpoint).
+    `state_dim`: amplitudes per state when it differs from `hilbert_dim` (a rank that owns no
+    row of a round allocates its receive buffer from it)."""
     from . import engine
     import os
     rank, world = rank_world()
@@ -270,9 +272,7 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
                 st["generations"] += hi - lo
             else:
                 ref = next(iter(rows.values())) if rows else None
-                D = ref.shape[1] if ref is not None else None
-                if D is None:
-                    D = run_block(0, 0).shape[1]
+                D = ref.shape[1] if ref is not None else (state_dim or int(hilbert_dim))
                 B = torch.empty((hi - lo, D), dtype=torch.complex128, device=dev)
             if world > 1:
                 _bcast_states(B, owner)

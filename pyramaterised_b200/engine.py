@@ -38,6 +38,9 @@ def launch_count():
     return int(_lib.load().pqc_launch_count())
 
 
+PASS_KERNELS = ("k_apply_pass", "k_sweep_pass", "k_layer_pass", "k_layer_seq", "k_tile_pipe")
+
+
 def profile_begin():
     _lib.check(_lib.load().pqc_profile_begin())
 
@@ -46,7 +49,11 @@ def profile_end():
     """-> dict(ms, launches, bytes) for the gate-apply kernel since profile_begin()."""
     out = (C.c_double * 4)()
     _lib.check(_lib.load().pqc_profile_end(out))
-    return {"ms": out[0], "launches": int(out[1]), "bytes": out[2]}
+    kinds = (C.c_double * (3 * len(PASS_KERNELS)))()
+    _lib.check(_lib.load().pqc_profile_kinds(kinds, len(PASS_KERNELS)))
+    by = {name: {"ms": kinds[3 * k], "launches": int(kinds[3 * k + 1]), "bytes": kinds[3 * k + 2]}
+          for k, name in enumerate(PASS_KERNELS) if kinds[3 * k + 1] > 0}
+    return {"ms": out[0], "launches": int(out[1]), "bytes": out[2], "by_kernel": by}
 
 
 def _stream():
@@ -162,10 +169,15 @@ class Program:
         a = as_angles(angles, self.P, dev) if self.P > 0 else None
         S = a.shape[0] if a is not None else 1
         buf = torch.empty((S, self.P + 1, self.dim), dtype=torch.complex128, device=dev)
+        stride = 0
         if init is not None:
             init = as_states(init, dev)
+            if init.dim() == 2:
+                if init.shape[0] != S:
+                    raise ValueError("per-sample initial states must match the angle batch")
+                stride = self.dim
         _lib.check(_lib.load().pqc_gradients_batch(self._h, _p(a), a.shape[1] if a is not None else 0,
-                                                   S, _p(init), 0, _p(buf), _stream()))
+                                                   S, _p(init), stride, _p(buf), _stream()))
         _count(self.n_qfim_passes + self.P)
         return buf
 
@@ -198,6 +210,167 @@ class Program:
                                       _p(F), _p(states), _stream()))
         _count(self.n_qfim_passes + 3 * self.P + 1)
         return (F, states) if want_states else F
+
+
+def dense_apply(states, M, lam=None, theta=None, deriv=False, out=None):
+    """out[s] = M (w_s * states[s]) with w_s = 1, or exp(-i theta_s lam) (times -i lam / 2 with
+    `deriv`): the two halves of an ARBGATE (gates.py:407-435) in its eigenbasis."""
+    states = states.contiguous()
+    S, D = states.shape
+    if out is None:
+        out = torch.empty_like(states)
+    if S == 0:
+        return out
+    if theta is not None:
+        theta = theta.contiguous()
+    _lib.check(_lib.load().pqc_dense_apply_batch(_p(states), S, D.bit_length() - 1, _p(M), _p(lam),
+                                                 _p(theta), 1 if theta is not None else 0,
+                                                 1 if deriv else 0, _p(out), _stream()))
+    _count()
+    return out
+
+
+class SegmentedProgram:
+    """A circuit that contains dense gates (ARBGATE): gate-program segments (Program) joined by
+    dense eigenbasis products.  Same surface as Program (run / gradients / qfim / describe), so
+    PQC and Measurements do not care.  Derivative states follow circuit.py:149-192: the vector of
+    parameter p is created inside its segment (or as (-i H / 2) exp(-i theta H) psi for a dense
+    gate) and carried through every later segment."""
+
+    def __init__(self, n_qubits, gates):
+        self.n = int(n_qubits)
+        self.segs = []                  # ("ops", Program, lo, hi) | ("dense", gate, slot)
+        ops, lo, slot = [], 0, 0
+        for gi, g in enumerate(gates):
+            if hasattr(g, "_lam"):
+                if g.q_N != self.n:
+                    raise ValueError("ARBGATE Hamiltonian does not match the register size")
+                if ops:
+                    self.segs.append(("ops", Program(self.n, slot - lo, ops), lo, slot))
+                self.segs.append(("dense", g, slot))
+                ops, slot = [], slot + 1
+                lo = slot
+                continue
+            for o in g._lower(slot - lo if g.param_count > 0 else -1):
+                ops.append(o[:5] + (gi,) + o[6:])
+            slot += g.param_count
+        if ops:
+            self.segs.append(("ops", Program(self.n, slot - lo, ops), lo, slot))
+        self.P = slot
+        self.grad_supported = all(s[1].grad_supported for s in self.segs if s[0] == "ops")
+        self.n_passes = sum(s[1].n_passes if s[0] == "ops" else 2 for s in self.segs)
+        self.n_qfim_passes = sum(s[1].n_qfim_passes if s[0] == "ops" else 2 for s in self.segs)
+        self._dev = {}
+
+    @property
+    def dim(self):
+        return 1 << self.n
+
+    def describe(self):
+        lines = []
+        for s in self.segs:
+            if s[0] == "ops":
+                lines.append(f"SEGMENT gate program, parameters [{s[2]}, {s[3]})")
+                lines.append(s[1].describe())
+            else:
+                lines.append(f"SEGMENT dense gate {s[1]!r}, parameter {s[2]}: V^dagger, phase, V")
+        return "\n".join(lines)
+
+    def _eig(self, gate):
+        key = id(gate)
+        if key not in self._dev:
+            dev = device()
+            V = torch.from_numpy(np.ascontiguousarray(gate._V)).to(dev)
+            Vh = torch.from_numpy(np.ascontiguousarray(gate._V.conj().T)).to(dev)
+            lam = torch.from_numpy(np.ascontiguousarray(gate._lam)).to(dev)
+            self._dev[key] = (V, Vh, lam)
+        return self._dev[key]
+
+    def _dense(self, gate, vecs, theta, deriv=False):
+        V, Vh, lam = self._eig(gate)
+        y = dense_apply(vecs, Vh)
+        return dense_apply(y, V, lam, theta, deriv)
+
+    def _seg_run(self, seg, a, vecs, rep=1):
+        """One segment applied to vecs [S * rep, D] (sample-major: row s * rep + r)."""
+        if seg[0] == "ops":
+            prog, lo, hi = seg[1], seg[2], seg[3]
+            ang = a[:, lo:hi].repeat_interleave(rep, dim=0) if hi > lo and rep > 1 else a[:, lo:hi]
+            return prog.run(ang.contiguous() if hi > lo else None, init=vecs)
+        th = a[:, seg[2]]
+        return self._dense(seg[1], vecs, th.repeat_interleave(rep) if rep > 1 else th)
+
+    def _start(self, a, init, S):
+        dev = device()
+        if init is None:
+            v = torch.zeros((S, self.dim), dtype=torch.complex128, device=dev)
+            v[:, 0] = 1.0
+            return v
+        init = as_states(init, dev)
+        return init.reshape(1, -1).expand(S, -1).contiguous() if init.dim() == 1 else init
+
+    def run(self, angles, init=None, out=None):
+        dev = device()
+        if self.P > 0:
+            a = as_angles(angles, self.P, dev)
+            S = a.shape[0]
+        else:
+            a = torch.empty((1, 0), dtype=torch.float64, device=dev)
+            S = init.shape[0] if init is not None and hasattr(init, "dim") and init.dim() == 2 else 1
+        v = self._start(a, init, S)
+        for seg in self.segs:
+            v = self._seg_run(seg, a, v)
+        if out is not None:
+            out.copy_(v)
+            return out
+        return v
+
+    def gradients(self, angles, init=None):
+        """-> [S, P+1, D]: [:, 0] the final state, [:, 1 + p] derivative state p."""
+        dev = device()
+        a = as_angles(angles, self.P, dev)
+        S, D = a.shape[0], self.dim
+        buf = torch.empty((S, self.P + 1, D), dtype=torch.complex128, device=dev)
+        psi = self._start(a, init, S)
+        for k, seg in enumerate(self.segs):
+            if seg[0] == "ops":
+                prog, lo, hi = seg[1], seg[2], seg[3]
+                if hi > lo:
+                    g = prog.gradients(a[:, lo:hi].contiguous(), init=psi)     # [S, Pk + 1, D]
+                    new, psi = g[:, 1:], g[:, 0].contiguous()
+                else:
+                    new, psi = None, prog.run(None, init=psi)
+            else:
+                lo, hi = seg[2], seg[2] + 1
+                th = a[:, lo].contiguous()
+                new = self._dense(seg[1], psi, th, deriv=True).unsqueeze(1)
+                psi = self._dense(seg[1], psi, th)
+            if new is None:
+                continue
+            m = hi - lo
+            vecs = new.reshape(S * m, D).contiguous()
+            for later in self.segs[k + 1:]:
+                vecs = self._seg_run(later, a, vecs, rep=m)
+            buf[:, 1 + lo:1 + hi] = vecs.reshape(S, m, D)
+        buf[:, 0] = psi
+        return buf
+
+    def qfim(self, angles, init=None, want_states=False, max_work_bytes=None):
+        dev = device()
+        a = as_angles(angles, self.P, dev)
+        S = a.shape[0]
+        F = torch.empty((S, self.P, self.P), dtype=torch.float64, device=dev)
+        st = torch.empty((S, self.dim), dtype=torch.complex128, device=dev) if want_states else None
+        per = (self.P + 1) * self.dim * 16 * 3
+        chunk = max(1, int((max_work_bytes or QFIM_WORK_BYTES) // per))
+        for c0 in range(0, S, chunk):
+            sl = slice(c0, min(S, c0 + chunk))
+            ini = init[sl] if init is not None and hasattr(init, "dim") and init.dim() == 2 else init
+            g = self.gradients(a[sl], init=ini)
+            F[sl] = qfim_from_grads(g[:, 0].contiguous(), g[:, 1:].contiguous())
+            if want_states:
+                st[sl] = g[:, 0]
+        return (F, st) if want_states else F
 
 
 # ---------------------------------------------------------------------------------------

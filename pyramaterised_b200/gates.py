@@ -359,9 +359,59 @@ class ALLTOALL(_Block):
 
 
 class ARBGATE(Gate):
+    """exp(-i theta H) for an arbitrary Hermitian `Ham` on the whole register (gates.py:407-435);
+    derivative() = -i H / 2 as in the reference (note: exp(-i theta H), not theta / 2).
+
+    The reference calls a dense Qobj.expm() on every set_theta.  Here H is diagonalised once
+    (host LAPACK, H = V diag(lambda) V^dagger) and circuits that contain the gate run as
+    segments: gate-program kernels before and after, two dense products with V^dagger / V and a
+    diagonal phase for the gate itself (engine.SegmentedProgram, csrc/pqc_dense.cu)."""
+
+    is_param = True
+    param_count = 1
+    MAX_QUBITS = 13
+
     def __init__(self, Ham):
-        raise NotImplementedError("ARBGATE (dense expm of an arbitrary Hamiltonian, "
-                                  "gates.py:407-435) is outside the GPU hot path (SURVEY 8f)")
+        self._Ham = Ham
+        mat = np.asarray(Ham.full() if hasattr(Ham, "full") else Ham, dtype=np.complex128)
+        D = mat.shape[0]
+        n = D.bit_length() - 1
+        if mat.ndim != 2 or mat.shape != (D, D) or D != 1 << n:
+            raise ValueError("ARBGATE needs a 2^n x 2^n Hamiltonian")
+        if n > self.MAX_QUBITS:
+            raise NotImplementedError(f"ARBGATE keeps a dense 2^n x 2^n eigenbasis: n <= {self.MAX_QUBITS}")
+        if not np.allclose(mat, mat.conj().T, atol=1e-12):
+            raise ValueError("ARBGATE needs a Hermitian Hamiltonian")
+        super().__init__(n)
+        self.theta = 0
+        self.pauli = 1
+        self._lam, self._V = np.linalg.eigh(mat)
+
+    def _matrix(self, theta):
+        return (self._V * np.exp(-1j * theta * self._lam)[None, :]) @ self._V.conj().T
+
+    @property
+    def operation(self):
+        return qt.DenseOp(self._matrix(self.theta), [[2] * self.q_N, [2] * self.q_N])
+
+    def get_op(self):
+        return self.operation
+
+    def set_theta(self, theta):
+        self.theta = theta
+
+    def flip_pauli(self):
+        self.pauli = -1 * self.pauli            # as in the reference: recorded, never used
+
+    def derivative(self):
+        return -1j * self._Ham / 2
+
+    def _lower(self, slot):
+        raise NotImplementedError("ARBGATE is not a primitive op: circuits that contain it run "
+                                  "through engine.SegmentedProgram")
+
+    def __repr__(self):
+        return f"{type(self).__name__}({self.theta:.2f})"
 
 
 # %% shared parameters ------------------------------------------------------------------------------

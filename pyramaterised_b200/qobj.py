@@ -72,6 +72,9 @@ class DenseOp:
 
     __rmul__ = lambda self, o: DenseOp(self._m * o, self.dims) if _is_scalar(o) else NotImplemented
 
+    def __truediv__(self, o):
+        return DenseOp(self._m / o, self.dims) if _is_scalar(o) else NotImplemented
+
     def __add__(self, o):
         if isinstance(o, DenseOp):
             return DenseOp(self._m + o._m, self.dims)

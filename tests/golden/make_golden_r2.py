@@ -10,6 +10,8 @@ on oracle/qutip_lite.py registered as ``qutip``; authoring container only):
                         fixed start angles: energies, trajectories, magic / Q / GKP traces
   * measure.py:199-224  find_eff_H on fidelity samples of a half-filled zfsim circuit and the
                         fidelity samples themselves (the zfsim half of tests.py:311-342)
+  * gates.py:407-435    ARBGATE circuits (dense expm on the shim): states, derivative states,
+                        QFIM, EQD, cost
   * full-depth rows used by the GPU tests at sizes the oracle cannot reach with QuTiP's dense
     operators are NOT generated here (the numpy oracle covers those).
 
@@ -85,6 +87,18 @@ def main():
         out[f"zfsim/{n}/F"] = np.array(F, dtype=np.float64)
         out[f"zfsim/{n}/effH"] = np.float64(m.find_eff_H(F, n))
         print(f"  zfsim {n}: eff_H = {out[f'zfsim/{n}/effH']:.4f}")
+    # ---- ARBGATE: states, derivative states, QFIM, cost through the reference's own classes
+    for k, ang in enumerate(cases_r2.ARB4_ANGLES):
+        qc = cases_r2.build_arb4(ref)
+        m = ref.measure.Measurements(qc)
+        st = qc.run(list(ang))
+        out[f"arb4/{k}/state"] = np.asarray(st.full())[:, 0]
+        out[f"arb4/{k}/cost"] = np.float64(qc.cost(list(ang)))
+        grads = qc.get_gradients()
+        out[f"arb4/{k}/grads"] = np.stack([np.asarray(g.full())[:, 0] for g in grads])
+        out[f"arb4/{k}/qfi"] = np.asarray(m.get_QFI(), dtype=np.float64)
+        out[f"arb4/{k}/eqd"] = np.int64(m.get_effective_quantum_dimension(1e-12))
+        print(f"  arb4 {k}: cost {out[f'arb4/{k}/cost']:.9f} eqd {out[f'arb4/{k}/eqd']}")
     path = os.path.join(HERE, "ref_golden_r2.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, f"{os.path.getsize(path) / 1e3:.1f} kB, {len(out)} arrays")

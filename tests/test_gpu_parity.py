@@ -2,6 +2,7 @@
 the reference-generated goldens and the numpy oracle.  Tolerances are BASELINE.json's:
 amplitudes / fidelities 1e-10 absolute, QFIM / magic 1e-8 relative, KL 1e-6."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -15,6 +16,7 @@ from oracle import pqc_oracle as orc
 from pyramaterised_b200 import engine
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 ALL = sorted(cases.CASES)
 ATOL = 1e-10
@@ -848,3 +850,72 @@ def test_nccl_sample_sharding_matches_single_gpu():
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["ok"]
+
+
+def test_reference_side_binding_runs_through_the_c_abi():
+    """integration/pqc_b200_binding.py (the stub of INTEGRATION.md B; its `lower` is checked
+    against the unmodified reference in tests/test_reference_binding.py) drives libpqc_b200.so
+    with nothing but ctypes: same states as the package's own path, Q from pqc_meyer_wallach."""
+    import importlib
+    sys.path.insert(0, os.path.join(ROOT, "integration"))
+    try:
+        b = importlib.import_module("pqc_b200_binding")
+    finally:
+        sys.path.pop(0)
+    for kind, n, p in (("generic_HE", 6, 3), ("XXZ", 8, 2), ("fermionic", 4, 1), ("NPQC", 13, 3)):
+        qc = pyqc.templates.generate_circuit(kind, n, p, shuffle=False)
+        ang = np.random.default_rng(n).random((5, qc.n_true_params)) * 2 * np.pi
+        st = b.run_batch(qc, ang)
+        assert torch.equal(torch.view_as_real(st), torch.view_as_real(qc.run_batch(ang)))
+        assert torch.equal(b.meyer_wallach(st, n), engine.meyer_wallach(st))
+
+
+def test_arbgate_circuit_matches_reference(golden_r2):
+    """ARBGATE = exp(-i theta H) of a dense Hamiltonian (gates.py:407-435) inside a circuit:
+    states, cost, every derivative state, QFIM and EQD against the unmodified reference (dense
+    expm on the shim); the batched path equals the one-sample path."""
+    qc = cases_r2.build_arb4(pyqc)
+    assert qc.n_true_params == 13 and "dense gate" in qc.program.describe()
+    m = pyqc.measure.Measurements(qc)
+    for k, ang in enumerate(cases_r2.ARB4_ANGLES):
+        st = qc.run(list(ang))
+        assert np.abs(st.numpy() - golden_r2[f"arb4/{k}/state"]).max() < ATOL
+        assert abs(qc.cost(list(ang)) - float(golden_r2[f"arb4/{k}/cost"])) < ATOL
+        gr = np.stack([g.numpy() for g in qc.get_gradients()])
+        assert np.abs(gr - golden_r2[f"arb4/{k}/grads"]).max() < ATOL
+        assert rel(m.get_QFI(), golden_r2[f"arb4/{k}/qfi"]) < RTOL
+        assert m.get_effective_quantum_dimension(1e-12) == int(golden_r2[f"arb4/{k}/eqd"])
+    A = np.array(cases_r2.ARB4_ANGLES)
+    stb = qc.run_batch(A).cpu().numpy()
+    for k in range(2):
+        assert np.abs(stb[k] - golden_r2[f"arb4/{k}/state"]).max() < ATOL
+    Fb = qc.qfim_batch(A).cpu().numpy()
+    for k in range(2):
+        assert rel(Fb[k], golden_r2[f"arb4/{k}/qfi"]) < RTOL
+    # the gate's own operator surface
+    g = pyqc.ARBGATE(pyqc.templates.TFIM_hamiltonian(3, 0.5))
+    g.set_theta(0.37)
+    U = g.operation.full()
+    assert np.abs(U @ U.conj().T - np.eye(8)).max() < 1e-13
+
+
+def test_dense_apply_large_register_is_unitary():
+    """The dense eigenbasis products at a size where the tiles repeat (10 qubits, 70 states):
+    exp(-i theta H) keeps norms, theta = 0 is the identity, and exp(-i a H) exp(-i b H) =
+    exp(-i (a + b) H)."""
+    n = 10
+    H = pyqc.templates.TFIM_hamiltonian(n, 0.9, 0.2)
+    qa = pyqc.PQC(n)
+    qa.add_layer([pyqc.R_y(i, n) for i in range(n)] + [pyqc.ARBGATE(H), pyqc.ARBGATE(H)])
+    qb = pyqc.PQC(n)
+    qb.add_layer([pyqc.R_y(i, n) for i in range(n)] + [pyqc.ARBGATE(H)])
+    rng = np.random.default_rng(3)
+    A = rng.random((70, n + 2)) * 2 * np.pi
+    B = np.concatenate([A[:, :n], (A[:, n] + A[:, n + 1])[:, None]], axis=1)
+    sa, sb = qa.run_batch(A), qb.run_batch(B)
+    assert np.abs((sa - sb).cpu().numpy()).max() < 1e-10
+    assert np.abs(engine.overlap(sa, sa).cpu().numpy() - 1).max() < 1e-12
+    Z = np.concatenate([A[:, :n], np.zeros((70, 1))], axis=1)
+    q0 = pyqc.PQC(n)
+    q0.add_layer([pyqc.R_y(i, n) for i in range(n)])
+    assert np.abs((qb.run_batch(Z) - q0.run_batch(A[:, :n])).cpu().numpy()).max() < 1e-12

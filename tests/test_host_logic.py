@@ -217,3 +217,24 @@ def test_conversion_matrices_match_reference(golden_r2, n):
     assert np.array_equal(np.asarray(xor), ox) and np.array_equal(np.asarray(sign), osg)
     m.set_converstion_matrices((xor, sign))
     assert m.conversion_matrices[0] is xor
+
+
+def test_arbgate_host_surface():
+    """ARBGATE bookkeeping without a GPU (gates.py:407-435): one parameter, Hermitian check,
+    operation = exp(-i theta H) (NOT theta / 2), derivative = -i H / 2, circuits that contain it
+    plan as segments."""
+    import scipy.linalg
+    import pyramaterised_b200 as pyqc
+    H = pyqc.templates.TFIM_hamiltonian(3, 0.8, 0.1)
+    g = pyqc.ARBGATE(H)
+    assert g.is_param and g.param_count == 1 and g.q_N == 3
+    g.set_theta(0.6)
+    assert np.abs(g.operation.full() - scipy.linalg.expm(-0.6j * H.full())).max() < 1e-13
+    assert np.abs(g.derivative().full() - (-0.5j * H.full())).max() < 1e-15
+    with pytest.raises(ValueError):
+        pyqc.ARBGATE(np.array([[0, 1], [0, 0]], dtype=complex))
+    qc = pyqc.PQC(3)
+    qc.add_layer([pyqc.R_x(0, 3), pyqc.ARBGATE(H), pyqc.R_z(2, 3)])
+    assert qc.n_true_params == 3 and qc.n_params == 6          # quirk Q1 bookkeeping unchanged
+    prog = qc.program
+    assert [s[0] for s in prog.segs] == ["ops", "dense", "ops"] and prog.P == 3
