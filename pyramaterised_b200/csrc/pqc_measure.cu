@@ -912,6 +912,142 @@ __global__ void k_fid_splitk_fin(const double2* __restrict__ part, long long npa
   }
 }
 
+// Blocked split-K form (config 5: a block of resident 4 GiB states against a few travelling
+// ones): CTA (K slice, pair tile) streams its slice of FB_TA = 32 A-rows and FB_TB = 4 B-rows
+// through a double-buffered shared-memory ring (cp.async, FB_KC amplitudes per row and stage) and
+// every warp keeps a 4 x 4 tile of pair accumulators in registers, so each state is read ONCE per
+// pair tile instead of once per pair: 16 * 2^n * (rows_A + rows_B) bytes per tile instead of
+// 32 * 2^n per pair.  Lane partials are folded by a fixed shuffle tree and the K slices are added
+// in order by k_fid_block_fin (reproducible; no floating-point atomics).
+#define FB_TA 32
+#define FB_TB 4
+#define FB_KC 128
+#define FB_ROWS (FB_TA + FB_TB)
+#define FB_STAGE_BYTES (FB_ROWS * FB_KC * 16)
+
+__global__ void __launch_bounds__(256, 1) k_fid_block(const c128* __restrict__ A, long long SA,
+                                                      const c128* __restrict__ B, long long SB, int n,
+                                                      int ksplit, long long tiles_b,
+                                                      double2* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char fb_sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long ta = blockIdx.y / tiles_b, tb = blockIdx.y % tiles_b;
+  const long long a0 = ta * FB_TA, b0 = tb * FB_TB;
+  const long long D = 1ll << n, len = D / ksplit, k0 = (long long)blockIdx.x * len;
+  const int nchunk = (int)(len / FB_KC);
+  // stage loader: row r of the tile (A rows first), FB_KC amplitudes = 2 KB = 128 x 16 B
+  auto load_stage = [&](int c, int buf) {
+    unsigned char* dst = fb_sm + (size_t)buf * FB_STAGE_BYTES;
+    const long long kk = k0 + (long long)c * FB_KC;
+    for (int e = tid; e < FB_ROWS * FB_KC; e += 256) {
+      const int r = e / FB_KC, k = e % FB_KC;
+      const c128* src;
+      if (r < FB_TA) src = A + min(a0 + r, SA - 1) * D;
+      else src = B + min(b0 + (r - FB_TA), SB - 1) * D;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                       (unsigned)__cvta_generic_to_shared(dst + (size_t)e * 16)), "l"(src + kk + k) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  double re[4][4], im[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) re[i][j] = im[i][j] = 0.0;
+  if (nchunk > 0) load_stage(0, 0);
+  for (int c = 0; c < nchunk; ++c) {
+    if (c + 1 < nchunk) {
+      load_stage(c + 1, (c + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const c128* st = reinterpret_cast<const c128*>(fb_sm + (size_t)(c & 1) * FB_STAGE_BYTES);
+#pragma unroll
+    for (int q = 0; q < FB_KC / 32; ++q) {
+      const int k = lane + 32 * q;
+      c128 av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = st[(warp * 4 + i) * FB_KC + k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = st[(FB_TA + j) * FB_KC + k];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {             // conj(a) * b
+          re[i][j] = fma(av[i].x, bv[j].x, fma(av[i].y, bv[j].y, re[i][j]));
+          im[i][j] = fma(av[i].x, bv[j].y, fma(-av[i].y, bv[j].x, im[i][j]));
+        }
+    }
+    __syncthreads();                              // the stage may be overwritten two loads later
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double r = re[i][j], m = im[i][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        r += __shfl_xor_sync(0xffffffffu, r, o);
+        m += __shfl_xor_sync(0xffffffffu, m, o);
+      }
+      const long long ia = a0 + warp * 4 + i, jb = b0 + j;
+      if (lane == 0 && ia < SA && jb < SB)
+        part[(ia * SB + jb) * ksplit + blockIdx.x] = make_double2(r, m);
+    }
+}
+
+// K slices in order, |.|^2, binning; tri: only the pairs i < j of the full SA x SA matrix, emitted
+// in itertools.combinations order
+__global__ void k_fid_block_fin(const double2* __restrict__ part, long long SA, long long SB, int tri,
+                                int ksplit, long long bins, double step,
+                                unsigned long long* __restrict__ hist, double* __restrict__ F) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= SA * SB) return;
+  const long long i = e / SB, j = e % SB;
+  if (tri && j <= i) return;
+  double re = 0.0, im = 0.0;
+  for (int k = 0; k < ksplit; ++k) {
+    re += part[e * ksplit + k].x;
+    im += part[e * ksplit + k].y;
+  }
+  const double f = re * re + im * im;
+  if (F) {
+    const long long idx = tri ? (i * (2 * SA - i - 1) / 2 + (j - i - 1)) : e;
+    F[idx] = f;
+  }
+  if (hist) {
+    const long long b = np_hist_bin(f, bins, step);
+    if (b >= 0) atomicAdd(hist + b, 1ull);
+  }
+}
+
+static int fid_block(const c128* A, long long SA, const c128* B, long long SB, int n, int tri,
+                     long long bins, unsigned long long* hist, double* F, cudaStream_t st) {
+  const long long tiles_a = (SA + FB_TA - 1) / FB_TA, tiles_b = (SB + FB_TB - 1) / FB_TB;
+  const long long tiles = tiles_a * tiles_b;
+  if (tiles > 65535) PQC_FAIL(-1, "fidelity block kernel: too many pair tiles; split the block");
+  const long long D = 1ll << n;
+  int ksplit = 1;                                  // >= 2 CTAs per SM in total, slices >= 4 chunks
+  while (ksplit < 4096 && D / (2 * ksplit) >= 4 * FB_KC && tiles * ksplit < 148 * 2) ksplit *= 2;
+  double2* part = nullptr;
+  PQC_CUDA(cudaMallocAsync(&part, sizeof(double2) * SA * SB * ksplit, st));
+  static PqcDeviceOnce once;
+  if (once.first())
+    PQC_CUDA(cudaFuncSetAttribute(k_fid_block, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  2 * FB_STAGE_BYTES));
+  k_fid_block<<<dim3((unsigned)ksplit, (unsigned)tiles), 256, 2 * FB_STAGE_BYTES, st>>>(
+      A, SA, B, SB, n, ksplit, tiles_b, part);
+  k_fid_block_fin<<<(unsigned)((SA * SB + 127) / 128), 128, 0, st>>>(
+      part, SA, SB, tri, ksplit, bins, bins > 0 ? 1.0 / (double)bins : 0.0, hist, F);
+  g_pqc_launches += 2;
+  const cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(part, st);
+  if (e != cudaSuccess) PQC_FAIL(-2, std::string("fidelity block kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 extern "C" int pqc_fidelity_hist(const pqc_c128* d_A, int64_t n_a, const pqc_c128* d_B,
                                  int64_t n_b, int n, int triangular, int64_t bins,
                                  long long* d_hist, double* d_F, void* stream) {
@@ -927,8 +1063,13 @@ extern "C" int pqc_fidelity_hist(const pqc_c128* d_A, int64_t n_a, const pqc_c12
     // a handful of huge states (config 5: 4 GiB each): the pair-tile kernels would run on a few
     // CTAs, each walking all 2^n amplitudes -- split the inner products over K instead
     const long long npairs = triangular ? n_a * (n_a - 1) / 2 : n_a * n_b;
-    const bool splitk = (n >= 20 && grid < 64 && npairs <= 65535 && !force) ||
-                        (force && strcmp(force, "splitk") == 0 && n >= 12 && npairs <= 65535);
+    // PQC_FIDELITY=splitk keeps the one-pair-per-CTA form (tests compare the two)
+    const bool blocked = (n >= 20 && grid < 64 && !force) ||
+                         (force && strcmp(force, "block") == 0 && n >= 12);
+    if (blocked && npairs > 0)
+      return fid_block((const c128*)d_A, n_a, (const c128*)d_B, n_b, n, triangular, bins,
+                       (unsigned long long*)d_hist, d_F, (cudaStream_t)stream);
+    const bool splitk = force && strcmp(force, "splitk") == 0 && n >= 12 && npairs <= 65535;
     if (splitk && npairs > 0) {
       cudaStream_t st = (cudaStream_t)stream;
       int ksplit = 1;

@@ -23,17 +23,24 @@
 #include "pqc_common.cuh"
 #include "pqc_ops.cuh"
 
-// The front plan (pqc_front.cu) runs PQC.run unless every pass of the block plan is a layer pass
-// (the TFIM template: k_layer_pass' compile-time geometry is the faster kernel there).
+// Which plan runs PQC.run.  The front plan (pqc_front.cu, few deep passes on k_tile_pipe) wins
+// wherever the block plan would run passes on the generic interpreter (CNOT-chain circuits:
+// 2.2x) or k_layer_seq passes with runs of R_z / CZ (NPQC: 1.6x).  The block plan stays when
+// every one of its passes is a layer pass (TFIM: k_layer_pass' compile-time geometry, 1.9x) or a
+// layer-sequence pass without diagonal runs (XXZ: 43 light passes at 4.3 TB/s beat 10 passes of
+// 9 sweeps each by 9 - 20 %); measured in profiles/r2_front_vs_block.jsonl.
 // PQC_FRONT=0 / 1 forces the choice (read per call so tests can compare the plans).
 bool pqc_use_front(const pqc_program* prog) {
   if (!prog->front_ok || prog->front_run.empty()) return false;
   const char* e = getenv("PQC_FRONT");
   if (e && strcmp(e, "0") == 0) return false;
   if (e && strcmp(e, "1") == 0) return true;
-  bool all_fast = !prog->v1_run.empty();
-  for (int pi : prog->v1_run) all_fast = all_fast && prog->v1_passes[pi].fast_ok;
-  return !all_fast;
+  bool all_light = !prog->v1_run.empty();
+  for (int pi : prog->v1_run) {
+    const V1Pass& ps = prog->v1_passes[pi];
+    all_light = all_light && (ps.fast_ok || (ps.seq_ok && !ps.seq.has_diag));
+  }
+  return !all_light;
 }
 
 bool pqc_use_v0() {

@@ -190,7 +190,7 @@ def _bcast_states(t, src):
 
 def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_engine_pair_hist,
                             kl=None, per_block=None, resident_blocks=None, checkpoint=None,
-                            stats=None, progress=None, state_dim=None):
+                            stats=None, progress=None, state_dim=None, prefetch_columns=True):
     """Measurements.expressibility for a sample set whose states cannot be resident together
     (BASELINE config 5: 4 GiB per 28-qubit state; measure.py:123-159).
 
@@ -212,7 +212,9 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
     receives generations, broadcasts and their bytes for this rank.  `progress(round, column,
     n_rounds, n_blocks)` is called on every rank after each column (and its checkpoint).
     `state_dim`: amplitudes per state when it differs from `hilbert_dim` (a rank that owns no
-    row of a round allocates its receive buffer from it)."""
+    row of a round allocates its receive buffer from it).  `prefetch_columns`: a rank generates
+    the next column block it owns on a side stream while it receives and histograms the columns
+    of the other ranks (one more block of states resident)."""
     from . import engine
     import os
     rank, world = rank_world()
@@ -230,7 +232,9 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
     def bounds(i):
         return i * block, min(n_total, (i + 1) * block)
 
-    st = {"generations": 0, "broadcasts": 0, "broadcast_bytes": 0, "rounds": 0, "resumed": 0}
+    st = {"generations": 0, "broadcasts": 0, "broadcast_bytes": 0, "rounds": 0, "resumed": 0,
+          "prefetched": 0}
+    side = None
     hist = None
     start_round, start_col = 0, -1
     ck = f"{checkpoint}.rank{rank}" if checkpoint else None
@@ -260,6 +264,35 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
         if hist is None:
             hist = torch.zeros((bins,), dtype=torch.int64, device=dev)
         hist = hist.to(dev)
+        # columns this rank will have to generate in this round, in order; the NEXT one is generated
+        # ahead on a side stream while columns owned by other ranks are received and histogrammed,
+        # so the ranks generate concurrently instead of one after the other
+        todo = [j for j in range(r0, nb) if j % world == rank and j not in rows
+                and not (rnd == start_round and j <= start_col)]
+        cuda = dev.type == "cuda"
+        if cuda and side is None:
+            side = torch.cuda.Stream(device=dev)
+        pending = {}
+
+        def prefetch():
+            if not prefetch_columns or not todo or pending:
+                return
+            jn = todo.pop(0)
+            a, b = bounds(jn)
+            if cuda:
+                main = torch.cuda.current_stream()
+                side.wait_stream(main)             # the row blocks' generation shares the program
+                with torch.cuda.stream(side):
+                    Bn = run_block(a, b)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                Bn.record_stream(main)
+            else:
+                Bn, ev = run_block(a, b), None
+            pending[jn] = (Bn, ev)
+            st["generations"] += b - a
+            st["prefetched"] += 1
+
         for j in range(r0, nb):
             if rnd == start_round and j <= start_col:
                 continue                           # finished before the checkpoint was written
@@ -268,12 +301,20 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
             if j in rows:
                 B = rows[j]
             elif owner == rank:
-                B = run_block(lo, hi)
-                st["generations"] += hi - lo
+                if j in pending:
+                    B, ev = pending.pop(j)
+                    if ev is not None:
+                        torch.cuda.current_stream().wait_event(ev)
+                else:
+                    if j in todo:
+                        todo.remove(j)
+                    B = run_block(lo, hi)
+                    st["generations"] += hi - lo
             else:
                 ref = next(iter(rows.values())) if rows else None
                 D = ref.shape[1] if ref is not None else (state_dim or int(hilbert_dim))
                 B = torch.empty((hi - lo, D), dtype=torch.complex128, device=dev)
+            prefetch()
             if world > 1:
                 _bcast_states(B, owner)
                 st["broadcasts"] += 1

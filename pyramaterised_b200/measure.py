@@ -176,7 +176,7 @@ class Measurements:
             nb = (sample_N + block - 1) // block
             share = (nb + world - 1) // world
             free = torch.cuda.mem_get_info()[0] if torch.cuda.is_available() else 1 << 62
-            fit = int(0.7 * free // (block * 16 * N)) - 1        # one more block travels
+            fit = int(0.7 * free // (block * 16 * N)) - 2        # a travelling and a prefetched block
             resident_blocks = max(1, min(share, fit))
         Q = {}
         qfile = f"{checkpoint}.rank{rank}.Q.json" if checkpoint and want_Q else None

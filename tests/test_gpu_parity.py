@@ -600,6 +600,35 @@ def test_fidelity_split_k_path(monkeypatch):
     assert int(t1.sum()) == 10 and int(t1[-1]) >= 1 and np.abs((t1 - t0).cpu().numpy()).sum() <= 2
 
 
+def test_fidelity_blocked_split_k_kernel(monkeypatch):
+    """The blocked split-K kernel (each state read once per 32 x 4 pair tile; the form config 5's
+    resident-block x travelling-block products take): ragged tiles on both sides, the triangular
+    form, fidelity 1 in the last bin; same values as numpy and the same integer histogram as the
+    tensor-core path; two runs are bitwise equal (fixed-order reductions)."""
+    rng = np.random.default_rng(6)
+    D = 1 << 13
+    A = rng.normal(size=(37, D)) + 1j * rng.normal(size=(37, D))
+    A /= np.linalg.norm(A, axis=1, keepdims=True)
+    A[9] = A[3]
+    B = rng.normal(size=(6, D)) + 1j * rng.normal(size=(6, D))
+    B /= np.linalg.norm(B, axis=1, keepdims=True)
+    tA, tB = torch.as_tensor(A, device="cuda"), torch.as_tensor(B, device="cuda")
+    h0, F0 = engine.fidelity_hist(tA, tB, bins=13, want_F=True)
+    t0, T0 = engine.fidelity_hist(tA, bins=13, want_F=True)
+    monkeypatch.setenv("PQC_FIDELITY", "block")
+    h1, F1 = engine.fidelity_hist(tA, tB, bins=13, want_F=True)
+    h2, F2 = engine.fidelity_hist(tA, tB, bins=13, want_F=True)
+    t1, T1 = engine.fidelity_hist(tA, bins=13, want_F=True)
+    monkeypatch.delenv("PQC_FIDELITY")
+    assert torch.equal(F1, F2) and torch.equal(h1, h2)
+    assert np.abs(F1.cpu().numpy() - np.abs(A.conj() @ B.T) ** 2).max() < 1e-13
+    tri = np.abs(A.conj() @ A.T)[np.triu_indices(37, 1)] ** 2
+    assert np.abs(T1.cpu().numpy() - tri).max() < 1e-13
+    assert torch.equal(h1, h0) and int(h1.sum()) == 37 * 6
+    assert int(t1.sum()) == 37 * 36 // 2 and int(t1[-1]) >= 1
+    assert np.abs((t1 - t0).cpu().numpy()).sum() <= 2
+
+
 # ---- size-independent properties at BASELINE.json's full sizes ------------------------------
 def test_config2_full_size_properties():
     """generic_HE 10q x 10 layers, S = 1e5: 4 999 950 000 pairs into 37 499 625 bins."""
