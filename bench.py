@@ -204,7 +204,7 @@ def exchange_leg(a, dev, rank, world):
     import pyramaterised_b200 as pyqc
     from pyramaterised_b200 import dist as pdist, engine
 
-    S = 4096 * world
+    S = 16384 * world
     qc = pyqc.templates.generate_circuit("generic_HE", 10, 10)
     ang = np.random.default_rng(2).random((S, qc.n_true_params)) * 2 * np.pi
     lo, hi = pdist.shard_bounds(S, rank, world)

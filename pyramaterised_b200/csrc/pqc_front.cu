@@ -109,6 +109,9 @@ struct Front {
   std::vector<char> done;
   std::vector<int> stamp;
   std::vector<int> lvl;          // level of an op inside the sweep being simulated (valid with stamp)
+  std::vector<double> wgt;       // what executing a mixing op / permutation is worth (see below)
+  std::vector<uint64_t> desc;    // transitive successors of every op, N x dw bits
+  int dw = 0;
   int cur_stamp = 0;
 
   bool ready(int i) const {
@@ -118,9 +121,9 @@ struct Front {
   }
 
   // mixing ops + permutations the closure of `tile` can execute (any number of sweeps)
-  int closure_weight(uint32_t tile, const std::vector<int>& pending, std::vector<int>* out) {
+  double closure_weight(uint32_t tile, const std::vector<int>& pending, std::vector<int>* out) {
     ++cur_stamp;
-    int w = 0;
+    double w = 0;
     bool changed = true;
     std::vector<int> rest = pending, next;
     while (changed) {
@@ -131,7 +134,7 @@ struct Front {
         const bool fits = !((o.mix | o.tgt) & ~tile);
         if (fits && ready(i)) {
           stamp[i] = cur_stamp;
-          if (o.mix || o.tgt) ++w;
+          if (o.mix || o.tgt) w += wgt[i];
           if (out) out->push_back(i);
           changed = true;
         } else {
@@ -145,7 +148,7 @@ struct Front {
 
   struct SweepSim {
     std::vector<int> pre, body, post;
-    int weight = 0;
+    double weight = 0;
     int ntrig = 0, ntables = 0;    // trig entries / linear-form tables the emission will need
   };
 
@@ -194,7 +197,7 @@ struct Front {
         const std::pair<int, int> key(o.param, lvl[i]);
         if (std::find(zzkeys.begin(), zzkeys.end(), key) == zzkeys.end()) zzkeys.push_back(key);
       }
-      if (o.mix || o.tgt) ++S.weight;
+      if (o.mix || o.tgt) S.weight += wgt[i];
     };
     std::vector<int> rest = cand, next;
     for (int phase = 0; phase < 3; ++phase) {
@@ -345,6 +348,32 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
   F.done.assign(N, 0);
   F.stamp.assign(N, 0);
   F.lvl.assign(N, 0);
+  // ---- what an op is worth to a pass: itself plus a share of everything that waits for it.  A
+  // rotation that many later ops depend on (the first-layer rotations of NPQC's odd qubits, which
+  // every CZ partner's chain waits for) should run early even if its own sweep is light: the passes
+  // behind it can then run whole chains with full slots.  Descendants by bitsets, reverse order.
+  {
+    static const double alpha = getenv("PQC_FRONT_ALPHA") ? atof(getenv("PQC_FRONT_ALPHA")) : 0.0;
+    const int W = (N + 63) / 64;
+    F.dw = W;
+    F.desc.assign((size_t)N * W, 0);
+    std::vector<uint64_t>& desc = F.desc;
+    std::vector<std::vector<int>> succ(N);
+    for (int j = 0; j < N; ++j)
+      for (int i : F.preds[j]) succ[i].push_back(j);
+    F.wgt.assign(N, 1.0);
+    for (int i = N - 1; i >= 0; --i) {
+      uint64_t* di = &desc[(size_t)i * W];
+      for (int sidx : succ[i]) {
+        const uint64_t* ds = &desc[(size_t)sidx * W];
+        for (int w = 0; w < W; ++w) di[w] |= ds[w];
+        di[sidx >> 6] |= 1ull << (sidx & 63);
+      }
+      long cnt = 0;
+      for (int w = 0; w < W; ++w) cnt += __builtin_popcountll(di[w]);
+      F.wgt[i] = 1.0 + alpha * (double)cnt;
+    }
+  }
 
   const size_t tj0 = tjobs.size();
   const uint32_t low = 0xfu;
@@ -357,8 +386,42 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
     if (++guard > 4096) FRONT_FAIL(5);
     // ---- tile: grow by closure gain per added bit (candidates: the missing bits of pending ops)
     uint32_t tile = low;
+    // cheap unblockers first: a bit with at most two pending rotations that many ops on OTHER bits
+    // wait for (NPQC's odd qubits: one first-layer rotation each, then only CZ partners).  With
+    // them in the tile early the later passes run whole chains with every register slot busy and
+    // every CZ partner a thread-constant bit.
+    uint32_t cheap = 0;                         // every cheap unblocker, in the tile or not
+    {
+      static const bool seed_on = !getenv("PQC_FRONT_NOSEED");
+      std::vector<int> own(n, 0);
+      for (int i : pending) {
+        const uint32_t m = F.ops[i].mix | F.ops[i].tgt;
+        for (int b = 0; b < n; ++b) own[b] += (m >> b) & 1u;
+      }
+      std::vector<std::pair<double, int>> seeds;
+      std::vector<uint64_t> acc(F.dw);
+      for (int b = 0; b < n && seed_on; ++b) {
+        if (own[b] == 0 || own[b] > 2) continue;
+        std::fill(acc.begin(), acc.end(), 0);
+        for (int i : pending)
+          if (((F.ops[i].mix | F.ops[i].tgt) >> b) & 1u)
+            for (int w = 0; w < F.dw; ++w) acc[w] |= F.desc[(size_t)i * F.dw + w];
+        long blocked = 0;
+        for (int j : pending) {
+          const uint32_t m = F.ops[j].mix | F.ops[j].tgt;
+          if (m && !((m >> b) & 1u) && ((acc[j >> 6] >> (j & 63)) & 1ull)) ++blocked;
+        }
+        if (blocked >= 8 * own[b]) {
+          cheap |= 1u << b;
+          if (!((tile >> b) & 1u)) seeds.push_back(std::make_pair(-(double)blocked / own[b], b));
+        }
+      }
+      std::sort(seeds.begin(), seeds.end());
+      for (const auto& sd : seeds)
+        if (__builtin_popcount(tile) < 12) tile |= 1u << sd.second;
+    }
     while (__builtin_popcount(tile) < 12) {
-      const int base = F.closure_weight(tile, pending, nullptr);
+      const double base = F.closure_weight(tile, pending, nullptr);
       std::vector<uint32_t> cands;
       for (int i : pending) {
         const uint32_t need = (F.ops[i].mix | F.ops[i].tgt) & ~tile;
@@ -370,8 +433,8 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
       double best = -1.0;
       uint32_t bm = 0;
       for (uint32_t m : cands) {
-        const int g = F.closure_weight(tile | m, pending, nullptr) - base;
-        const double score = (double)g / __builtin_popcount(m);
+        const double g = F.closure_weight(tile | m, pending, nullptr) - base;
+        const double score = g / __builtin_popcount(m);
         if (score > best) { best = score; bm = m; }
       }
       tile |= bm;
@@ -400,7 +463,33 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
       std::vector<int> ub, other;
       for (int p = 0; p < 12; ++p) ((useful >> tb[p]) & 1u ? ub : other).push_back(tb[p]);
       std::vector<uint32_t> Rs;
-      if ((int)ub.size() <= 4) {
+      {
+        // cheap unblockers of the tile that still have a ready rotation: a light sweep of their own
+        // (padded with bits that have nothing to do), so that the chains they unblock meet their CZ
+        // partners as thread-constant bits later instead of sharing the registers with them
+        uint32_t cu = 0;
+        for (int i : cand) {
+          const FOp& o = F.ops[i];
+          if (F.done[i] || !(o.mix | o.tgt) || ((o.mix | o.tgt) & ~cheap)) continue;
+          bool rdy = true;
+          for (int pr : F.preds[i]) rdy = rdy && F.done[pr];
+          if (rdy) cu |= o.mix | o.tgt;
+        }
+        cu &= tile;
+        if (cu) {
+          uint32_t R = 0;
+          for (int b = 0; b < n && __builtin_popcount(R) < 4; ++b)
+            if ((cu >> b) & 1u) R |= 1u << b;
+          for (int i = (int)other.size() - 1; i >= 0 && __builtin_popcount(R) < 4; --i) R |= 1u << other[i];
+          for (int b : ub)
+            if (__builtin_popcount(R) < 4 && !((R >> b) & 1u) && ((cheap >> b) & 1u)) R |= 1u << b;
+          for (int b : ub)
+            if (__builtin_popcount(R) < 4 && !((R >> b) & 1u)) R |= 1u << b;
+          if (__builtin_popcount(R) == 4) Rs.push_back(R);
+        }
+      }
+      if (!Rs.empty()) {
+      } else if ((int)ub.size() <= 4) {
         uint32_t R = 0;
         for (int b : ub) R |= 1u << b;
         for (int i = (int)other.size() - 1; i >= 0 && __builtin_popcount(R) < 4; --i) R |= 1u << other[i];

@@ -235,6 +235,21 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
     st = {"generations": 0, "broadcasts": 0, "broadcast_bytes": 0, "rounds": 0, "resumed": 0,
           "prefetched": 0}
     side = None
+    import time
+    prof = bool(stats is not None and stats.get("profile"))
+    for k in ("t_rows", "t_colgen", "t_bcast", "t_hist"):
+        st[k] = 0.0
+
+    def tick(key, t0):
+        """Phase timer (only with stats={"profile": True}: it synchronises the device)."""
+        if not prof:
+            return 0.0
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if key:
+            st[key] += t1 - t0
+        return t1
     hist = None
     start_round, start_col = 0, -1
     ck = f"{checkpoint}.rank{rank}" if checkpoint else None
@@ -250,6 +265,7 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
     for rnd in range(start_round, n_rounds):
         r0, r1 = rnd * per_round, min(nb, (rnd + 1) * per_round)
         rows = {}
+        tq = tick(None, 0.0)
         for i in range(r0, r1):
             if i % world != rank:
                 continue
@@ -259,6 +275,7 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
             dev = rows[i].device
             if per_block is not None and not (rnd == start_round and i <= start_col):
                 per_block(lo, hi, rows[i])
+        tick("t_rows", tq)
         if dev is None:
             dev = engine.device() if torch.cuda.is_available() else torch.device("cpu")
         if hist is None:
@@ -298,6 +315,7 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
                 continue                           # finished before the checkpoint was written
             lo, hi = bounds(j)
             owner = j % world
+            tq = tick(None, 0.0)
             if j in rows:
                 B = rows[j]
             elif owner == rank:
@@ -314,16 +332,19 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
                 ref = next(iter(rows.values())) if rows else None
                 D = ref.shape[1] if ref is not None else (state_dim or int(hilbert_dim))
                 B = torch.empty((hi - lo, D), dtype=torch.complex128, device=dev)
-            prefetch()
+            tq = tick("t_colgen", tq)
+            prefetch()        # before the broadcast: the side stream runs while this rank waits for it
             if world > 1:
                 _bcast_states(B, owner)
                 st["broadcasts"] += 1
                 st["broadcast_bytes"] += int(B.numel() * B.element_size())
+            tq = tick("t_bcast", tq)
             for i, A in rows.items():
                 if i < j:
                     hist += pair_hist(A, B, False, bins)
                 elif i == j and A.shape[0] > 1:
                     hist += pair_hist(A, A, True, bins)
+            tick("t_hist", tq)
             if j not in rows:
                 del B
             if ck:

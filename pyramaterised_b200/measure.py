@@ -175,7 +175,11 @@ class Measurements:
         if resident_blocks is None:
             nb = (sample_N + block - 1) // block
             share = (nb + world - 1) // world
-            free = torch.cuda.mem_get_info()[0] if torch.cuda.is_available() else 1 << 62
+            if torch.cuda.is_available():                          # free + what torch holds cached
+                free = torch.cuda.mem_get_info()[0] + torch.cuda.memory_reserved() - \
+                    torch.cuda.memory_allocated()
+            else:
+                free = 1 << 62
             fit = int(0.7 * free // (block * 16 * N)) - 2        # a travelling and a prefetched block
             resident_blocks = max(1, min(share, fit))
         Q = {}

@@ -33,12 +33,12 @@ def main():
     m = pyqc.measure.Measurements(qc)
     # warm-up: plan upload, NCCL communicator, allocator pools
     pyqc.gates.rng.bit_generator.state = np.random.default_rng(7).bit_generator.state
-    m.expressibility_streamed(min(S, 2 * block * world), block, want_Q=True, resident_blocks=1)
+    m.expressibility_streamed(min(S, max(17, 2 * block * world)), block, want_Q=True, resident_blocks=1)
     pyqc.gates.rng.bit_generator.state = np.random.default_rng(1).bit_generator.state
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    stats = {}
+    stats = {"profile": bool(os.environ.get("C5_PROFILE"))}
     t0 = time.perf_counter()
     e, Q = m.expressibility_streamed(S, block, want_Q=True, resident_blocks=resident, stats=stats)
     torch.cuda.synchronize()
@@ -62,6 +62,8 @@ def main():
             "generations_per_rank": gens, "generations_total": sum(gens),
             "broadcasts": int(gs[0][1].item()), "broadcast_bytes_total": int(gs[0][2].item()),
             "Q_values_per_rank": [int(x[3].item()) for x in gs],
+            "phase_seconds_rank0": {k: round(stats[k], 3) for k in ("t_rows", "t_colgen", "t_bcast", "t_hist")}
+            if stats.get("profile") else None,
             "pairs_per_s": pairs / float(dt.item()),
             "generations_per_s_all_ranks": sum(gens) / float(dt.item())}), flush=True)
     if world > 1:

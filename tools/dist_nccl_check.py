@@ -35,6 +35,15 @@ def main():
     st = qc.run_batch(ang[lo:hi])
     e = pdist.sharded_expressibility(st, S, 2.0 ** 10)
     qm, qs = pdist.gathered_mean_std(engine.meyer_wallach(st), S)
+    # the block-streamed form (column blocks broadcast over NVLink from their owner, the next
+    # owned column generated ahead on a side stream): one round, and several rounds
+    streamed = []
+    for rb in (None, 1):
+        stt = {}
+        es = pdist.streamed_expressibility(
+            lambda a, b: qc.program.run(ang[a:b], init=qc.initial_state.tensor), S, 211, 2.0 ** 10,
+            resident_blocks=rb, stats=stt)
+        streamed.append((es, stt["rounds"], stt["broadcasts"], stt["prefetched"]))
     if rank == 0:
         full = qc.run_batch(ang)
         pairs = S * (S - 1) // 2
@@ -44,6 +53,9 @@ def main():
         out["expr_sharded"], out["expr_single"] = e, e1
         out["expr_equal"] = bool(e == e1)
         out["mw_equal"] = bool(qm == np.mean(q1) and qs == np.std(q1))
+        out["streamed"] = [{"expr": x[0], "rounds": x[1], "broadcasts": x[2], "prefetched": x[3]}
+                           for x in streamed]
+        out["streamed_equal"] = bool(all(x[0] == e1 for x in streamed))
 
     # QFIM + EQD, TFIM 12q x 4 layers, 257 parameter sets
     S2 = 257
@@ -54,7 +66,8 @@ def main():
         F = qc2.qfim_batch(ang2)
         eq1 = engine.count_greater(engine.eigvalsh(F), 1e-10)
         out["eqd_equal"] = bool(torch.equal(eq.cpu(), eq1.cpu()))
-        out["ok"] = bool(out["expr_equal"] and out["mw_equal"] and out["eqd_equal"])
+        out["ok"] = bool(out["expr_equal"] and out["mw_equal"] and out["eqd_equal"] and
+                         out["streamed_equal"])
         print(json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()
