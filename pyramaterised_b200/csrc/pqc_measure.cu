@@ -942,8 +942,13 @@ __global__ void __launch_bounds__(256, 1) k_fid_block(const c128* __restrict__ A
     for (int e = tid; e < FB_ROWS * FB_KC; e += 256) {
       const int r = e / FB_KC, k = e % FB_KC;
       const c128* src;
-      if (r < FB_TA) src = A + min(a0 + r, SA - 1) * D;
-      else src = B + min(b0 + (r - FB_TA), SB - 1) * D;
+      if (r < FB_TA) {
+        if (a0 + r >= SA) continue;                // ragged tile: the row's products are discarded
+        src = A + (a0 + r) * D;
+      } else {
+        if (b0 + (r - FB_TA) >= SB) continue;
+        src = B + (b0 + (r - FB_TA)) * D;
+      }
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
                        (unsigned)__cvta_generic_to_shared(dst + (size_t)e * 16)), "l"(src + kk + k) : "memory");
     }
@@ -954,6 +959,9 @@ __global__ void __launch_bounds__(256, 1) k_fid_block(const c128* __restrict__ A
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) re[i][j] = im[i][j] = 0.0;
+  for (int e = tid; e < 2 * FB_STAGE_BYTES / 16; e += 256)      // rows a ragged tile never loads
+    reinterpret_cast<double2*>(fb_sm)[e] = make_double2(0.0, 0.0);
+  __syncthreads();
   if (nchunk > 0) load_stage(0, 0);
   for (int c = 0; c < nchunk; ++c) {
     if (c + 1 < nchunk) {

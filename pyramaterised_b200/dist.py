@@ -266,11 +266,22 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
         r0, r1 = rnd * per_round, min(nb, (rnd + 1) * per_round)
         rows = {}
         tq = tick(None, 0.0)
-        for i in range(r0, r1):
-            if i % world != rank:
-                continue
+        # this rank's row blocks of the round live in ONE buffer (ascending block index), so a
+        # column meets all the rows before it in a single pair-kernel call that reads every
+        # resident state once
+        mine = [i for i in range(r0, r1) if i % world == rank]
+        n_mine = sum(bounds(i)[1] - bounds(i)[0] for i in mine)
+        rows_all, row_off, off = None, {}, 0
+        for i in mine:
             lo, hi = bounds(i)
-            rows[i] = run_block(lo, hi)
+            blk = run_block(lo, hi)
+            if rows_all is None:
+                rows_all = torch.empty((n_mine, blk.shape[1]), dtype=blk.dtype, device=blk.device)
+            rows_all[off:off + hi - lo].copy_(blk)
+            del blk
+            rows[i] = rows_all[off:off + hi - lo]
+            row_off[i] = off
+            off += hi - lo
             st["generations"] += hi - lo
             dev = rows[i].device
             if per_block is not None and not (rnd == start_round and i <= start_col):
@@ -329,8 +340,7 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
                     B = run_block(lo, hi)
                     st["generations"] += hi - lo
             else:
-                ref = next(iter(rows.values())) if rows else None
-                D = ref.shape[1] if ref is not None else (state_dim or int(hilbert_dim))
+                D = rows_all.shape[1] if rows_all is not None else (state_dim or int(hilbert_dim))
                 B = torch.empty((hi - lo, D), dtype=torch.complex128, device=dev)
             tq = tick("t_colgen", tq)
             prefetch()        # before the broadcast: the side stream runs while this rank waits for it
@@ -339,14 +349,15 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
                 st["broadcasts"] += 1
                 st["broadcast_bytes"] += int(B.numel() * B.element_size())
             tq = tick("t_bcast", tq)
-            for i, A in rows.items():
-                if i < j:
-                    hist += pair_hist(A, B, False, bins)
-                elif i == j and A.shape[0] > 1:
-                    hist += pair_hist(A, A, True, bins)
+            before = [i for i in mine if i < j]
+            if before:                             # a prefix of rows_all: one call
+                last = before[-1]
+                n_before = row_off[last] + rows[last].shape[0]
+                hist += pair_hist(rows_all[:n_before], B, False, bins)
+            if j in rows and rows[j].shape[0] > 1:
+                hist += pair_hist(rows[j], rows[j], True, bins)
             tick("t_hist", tq)
-            if j not in rows:
-                del B
+            B = None                               # a view of rows_all would keep the round's buffer alive
             if ck:
                 torch.save({"hist": hist.cpu(), "round": rnd, "col": j, "n_total": n_total,
                             "block": block, "world": world, "per_round": per_round, "bins": bins},
@@ -355,6 +366,7 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
             if progress is not None:
                 progress(rnd, j, n_rounds, nb)
         rows.clear()
+        rows_all = None
         start_col = -1
         st["rounds"] += 1
     if hist is None:                      # nothing to do on this rank: still joins the all-reduce
