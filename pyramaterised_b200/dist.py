@@ -321,34 +321,48 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
             st["generations"] += b - a
             st["prefetched"] += 1
 
-        for j in range(r0, nb):
-            if rnd == start_round and j <= start_col:
-                continue                           # finished before the checkpoint was written
+        def fetch(j):
+            """Start making column j available on this rank: the owner's copy (a resident row, the
+            prefetched block, or generated now), an empty buffer elsewhere, and the broadcast from
+            the owner as an ASYNC collective -- it runs beside the pair kernels of the column before."""
             lo, hi = bounds(j)
             owner = j % world
-            tq = tick(None, 0.0)
             if j in rows:
-                B = rows[j]
+                Bj = rows[j]
             elif owner == rank:
                 if j in pending:
-                    B, ev = pending.pop(j)
+                    Bj, ev = pending.pop(j)
                     if ev is not None:
                         torch.cuda.current_stream().wait_event(ev)
                 else:
                     if j in todo:
                         todo.remove(j)
-                    B = run_block(lo, hi)
+                    Bj = run_block(lo, hi)
                     st["generations"] += hi - lo
             else:
                 D = rows_all.shape[1] if rows_all is not None else (state_dim or int(hilbert_dim))
-                B = torch.empty((hi - lo, D), dtype=torch.complex128, device=dev)
-            tq = tick("t_colgen", tq)
-            prefetch()        # before the broadcast: the side stream runs while this rank waits for it
+                Bj = torch.empty((hi - lo, D), dtype=torch.complex128, device=dev)
+            work = None
             if world > 1:
-                _bcast_states(B, owner)
+                work = dist.broadcast(_as_real(Bj), src=owner, async_op=True)
                 st["broadcasts"] += 1
-                st["broadcast_bytes"] += int(B.numel() * B.element_size())
+                st["broadcast_bytes"] += int(Bj.numel() * Bj.element_size())
+            return Bj, work
+
+        cols = [j for j in range(r0, nb) if not (rnd == start_round and j <= start_col)]
+        tq = tick(None, 0.0)
+        prefetch()
+        nxt = fetch(cols[0]) if cols else None
+        for ci, j in enumerate(cols):
+            B, work = nxt
+            nxt = None
+            prefetch()        # the side stream generates this rank's next column meanwhile
+            tq = tick("t_colgen", tq)
+            if work is not None:
+                work.wait()
             tq = tick("t_bcast", tq)
+            if ci + 1 < len(cols):
+                nxt = fetch(cols[ci + 1])          # in flight while column j is histogrammed
             before = [i for i in mine if i < j]
             if before:                             # a prefix of rows_all: one call
                 last = before[-1]
@@ -356,7 +370,7 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
                 hist += pair_hist(rows_all[:n_before], B, False, bins)
             if j in rows and rows[j].shape[0] > 1:
                 hist += pair_hist(rows[j], rows[j], True, bins)
-            tick("t_hist", tq)
+            tq = tick("t_hist", tq)
             B = None                               # a view of rows_all would keep the round's buffer alive
             if ck:
                 torch.save({"hist": hist.cpu(), "round": rnd, "col": j, "n_total": n_total,
@@ -365,6 +379,7 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
                 os.replace(ck + ".tmp", ck)
             if progress is not None:
                 progress(rnd, j, n_rounds, nb)
+        nxt = None
         rows.clear()
         rows_all = None
         start_col = -1

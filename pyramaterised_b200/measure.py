@@ -180,7 +180,7 @@ class Measurements:
                     torch.cuda.memory_allocated()
             else:
                 free = 1 << 62
-            fit = int(0.8 * free // (block * 16 * N)) - 3        # + a travelling, a prefetched and a fresh block
+            fit = int(0.85 * free // (block * 16 * N)) - 4       # + two travelling, a prefetched and a fresh block
             resident_blocks = max(1, min(share, fit))
         Q = {}
         qfile = f"{checkpoint}.rank{rank}.Q.json" if checkpoint and want_Q else None
