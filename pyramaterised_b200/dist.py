@@ -234,7 +234,10 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
 
     st = {"generations": 0, "broadcasts": 0, "broadcast_bytes": 0, "rounds": 0, "resumed": 0,
           "prefetched": 0}
-    side = None
+    side = comm = None
+    rows_all = None
+    recv = [None, None]
+    n_recv = 0
     import time
     prof = bool(stats is not None and stats.get("profile"))
     for k in ("t_rows", "t_colgen", "t_bcast", "t_hist"):
@@ -271,12 +274,15 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
         # resident state once
         mine = [i for i in range(r0, r1) if i % world == rank]
         n_mine = sum(bounds(i)[1] - bounds(i)[0] for i in mine)
-        rows_all, row_off, off = None, {}, 0
+        row_off, off = {}, 0
         for i in mine:
             lo, hi = bounds(i)
             blk = run_block(lo, hi)
             if rows_all is None:
-                rows_all = torch.empty((n_mine, blk.shape[1]), dtype=blk.dtype, device=blk.device)
+                # allocated once for the whole run (every round reuses it: no 100 GB free / malloc
+                # cycles for the caching allocator to fragment)
+                rows_all = torch.empty((max(n_mine, resident_blocks * block), blk.shape[1]),
+                                       dtype=blk.dtype, device=blk.device)
             rows_all[off:off + hi - lo].copy_(blk)
             del blk
             rows[i] = rows_all[off:off + hi - lo]
@@ -300,6 +306,7 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
         cuda = dev.type == "cuda"
         if cuda and side is None:
             side = torch.cuda.Stream(device=dev)
+            comm = torch.cuda.Stream(device=dev)
         pending = {}
 
         def prefetch():
@@ -327,39 +334,58 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
             the owner as an ASYNC collective -- it runs beside the pair kernels of the column before."""
             lo, hi = bounds(j)
             owner = j % world
+            ev = None
             if j in rows:
                 Bj = rows[j]
             elif owner == rank:
                 if j in pending:
-                    Bj, ev = pending.pop(j)
-                    if ev is not None:
-                        torch.cuda.current_stream().wait_event(ev)
+                    Bj, ev = pending.pop(j)        # the broadcast waits for ev, not the main stream
                 else:
                     if j in todo:
                         todo.remove(j)
                     Bj = run_block(lo, hi)
                     st["generations"] += hi - lo
             else:
+                # two receive buffers used in turn (column j + 2 lands where column j was)
+                nonlocal n_recv
                 D = rows_all.shape[1] if rows_all is not None else (state_dim or int(hilbert_dim))
-                Bj = torch.empty((hi - lo, D), dtype=torch.complex128, device=dev)
+                k = n_recv % 2
+                n_recv += 1
+                if recv[k] is None:
+                    recv[k] = torch.empty((block, D), dtype=torch.complex128, device=dev)
+                Bj = recv[k][:hi - lo]
             work = None
             if world > 1:
-                work = dist.broadcast(_as_real(Bj), src=owner, async_op=True)
+                if cuda:
+                    # issued from a communication stream: it waits for what the main stream has
+                    # queued so far (the buffer's earlier life, the generation event), while the
+                    # main stream goes on to histogram the column before
+                    main = torch.cuda.current_stream()
+                    comm.wait_stream(main)
+                    if ev is not None:
+                        comm.wait_event(ev)
+                    with torch.cuda.stream(comm):
+                        work = dist.broadcast(_as_real(Bj), src=owner, async_op=True)
+                    Bj.record_stream(comm)
+                else:
+                    work = dist.broadcast(_as_real(Bj), src=owner, async_op=True)
                 st["broadcasts"] += 1
                 st["broadcast_bytes"] += int(Bj.numel() * Bj.element_size())
-            return Bj, work
+            return Bj, work, ev
 
         cols = [j for j in range(r0, nb) if not (rnd == start_round and j <= start_col)]
         tq = tick(None, 0.0)
         prefetch()
         nxt = fetch(cols[0]) if cols else None
         for ci, j in enumerate(cols):
-            B, work = nxt
+            B, work, ev = nxt
             nxt = None
             prefetch()        # the side stream generates this rank's next column meanwhile
             tq = tick("t_colgen", tq)
             if work is not None:
                 work.wait()
+            elif ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
             tq = tick("t_bcast", tq)
             if ci + 1 < len(cols):
                 nxt = fetch(cols[ci + 1])          # in flight while column j is histogrammed
@@ -381,7 +407,6 @@ def streamed_expressibility(run_block, n_total, block, hilbert_dim, pair_hist=_e
                 progress(rnd, j, n_rounds, nb)
         nxt = None
         rows.clear()
-        rows_all = None
         start_col = -1
         st["rounds"] += 1
     if hist is None:                      # nothing to do on this rank: still joins the all-reduce
