@@ -100,7 +100,13 @@ def as_angles(angles, P, dev=None):
 
 class Program:
     """A lowered gate program (pqc_program handle).  ops: sequence of
-    (kind, q0, q1, param, param2, group, scale, offset)."""
+    (kind, q0, q1, param, param2, group, scale, offset).
+
+    A Program is bound to the CUDA device of its first launch (the library refuses another
+    one) and keeps per-program scratch -- the per-sample trig table, the QFIM workspace -- so it
+    is NOT thread-safe and must not run on two streams at once: callers that overlap work
+    (dist.streamed_expressibility's side stream) order the launches of one Program with stream
+    waits.  release_workspace() frees the QFIM workspace (up to QFIM_WORK_BYTES)."""
 
     def __init__(self, n_qubits, n_params, ops):
         lib = _lib.load()               # planning is host-only; the device is needed to run
@@ -123,6 +129,10 @@ class Program:
     @property
     def dim(self):
         return 1 << self.n
+
+    def release_workspace(self):
+        """Free the live-vector workspace Program.qfim keeps between calls."""
+        self._work = None
 
     def describe(self):
         """The execution plan, one line per stage (host-only)."""

@@ -238,3 +238,38 @@ def test_arbgate_host_surface():
     assert qc.n_true_params == 3 and qc.n_params == 6          # quirk Q1 bookkeeping unchanged
     prog = qc.program
     assert [s[0] for s in prog.segs] == ["ops", "dense", "ops"] and prog.P == 3
+
+
+def test_front_planner_plans_and_plan_choice():
+    """The light-cone planner (pqc_front.cu), host only.  NPQC: the odd qubits (one first-layer
+    rotation each, then only CZ partners: cheap unblockers) are cleared in light sweeps first, so
+    the even qubits' chains run with all four register slots busy and every CZ merged into its
+    rotation -- 16q x 16 layers in 2 passes and ~4 layer ops per layer instead of 11.  Plan choice
+    for PQC.run: front plan for CNOT-chain and NPQC circuits, block plan for TFIM / XXZ."""
+    import re
+    import pyramaterised_b200 as pyqc
+
+    def front(kind, n, p):
+        qc = pyqc.templates.generate_circuit(kind, n, p, shuffle=False)
+        lines = qc.program.describe().split("\n")
+        head = [l for l in lines if l.startswith("FRONT plan")]
+        ops = []
+        for l in lines:
+            if l.startswith("FRONT PASS"):
+                for _, o in re.findall(r"\[rb ([0-9,]+) pre\d+ post\d+:([0-9 ]*)\]", l):
+                    ops += o.split()
+        passes = sum(l.startswith("FRONT PASS") for l in lines)
+        return head[0], passes, ops, qc
+
+    head, passes, ops, qc = front("NPQC", 16, 16)
+    assert head.endswith("used for PQC.run: 1") and passes == 2 and qc.program.n_passes == 2
+    layer_ops = sum(o in ("35", "36", "37", "38") for o in ops)
+    assert layer_ops <= 80, layer_ops                     # 185 before the unblocker sweeps
+    assert "8" not in ops                                 # no CZ left between two register bits
+    head, passes, ops, qc = front("NPQC", 28, 20)
+    assert passes <= 6 and sum(o in ("37", "38") for o in ops) <= 200
+    head, passes, _, qc = front("generic_HE", 16, 16)
+    assert head.endswith("used for PQC.run: 1") and qc.program.n_passes == passes
+    for kind in ("TFIM", "XXZ"):
+        head, passes, _, qc = front(kind, 16, 16)
+        assert head.endswith("used for PQC.run: 0") and qc.program.n_passes > passes
