@@ -181,10 +181,11 @@ struct SeqPlan {
   uint32_t wo[FAST_MAX_WT][PQC_MAX_QUBITS - 12];
 };
 
-// "Tile pipe" (k_tile_pipe, pqc_pipe.cu): the persistent, TMA-fed form of the pass kernels.
+// "Tile pipe" (k_tile_pipe, pqc_pipe.cu): the persistent, async-copy-fed form of the pass kernels.
 // One CTA per SM walks over (vector, tile) work items; tiles arrive in a ring of TP_NBUF
-// shared-memory buffers by bulk async copies (cp.async.bulk + mbarrier) issued ahead of the two
-// consumer groups, so HBM loads never wait for a free register file.  A pass is a list of
+// shared-memory buffers by per-thread 16-byte async copies (cp.async, completion counted on one
+// mbarrier per slot) issued ahead of the two consumer groups, so HBM loads never wait for a free
+// register file.  A pass is a list of
 // sweeps with RUNTIME geometry: any 4 of the 12 tile positions in registers, thread bits on the
 // other 8, shared-memory slots an affine function of the logical tile index.  X / CNOT are pure
 // relabelings of that index (they change the planner's slot tables, not the kernel).

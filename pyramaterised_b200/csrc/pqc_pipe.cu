@@ -1,4 +1,4 @@
-// pqc_pipe.cu -- k_tile_pipe: the persistent, TMA-fed pass kernel (gate application of
+// pqc_pipe.cu -- k_tile_pipe: the persistent, async-copy-fed pass kernel (gate application of
 // circuit.py:118-125 and the derivative passes of circuit.py:149-192 for n >= 12 qubits).
 //
 // Why it exists.  k_layer_pass / k_layer_seq load a 4096-amplitude tile from HBM straight into
@@ -20,8 +20,10 @@
 // A sweep's geometry is data, not code: any 4 of the 12 tile positions are the register bits, the
 // other 8 are thread bits, and the shared-memory slot of a logical tile index is an affine map
 // chosen by the planner (the XOR swizzle of the per-tile kernels).  X / CNOT are relabelings of the logical index and only change those tables.
-// Arithmetic and op order per amplitude are those of k_layer_pass / k_layer_seq: results are
-// bitwise identical (tests/test_gpu_parity.py compares the paths).
+// For the plans of the per-tile kernels (PQC_PIPE=1) arithmetic and op order per amplitude are
+// those of k_layer_pass / k_layer_seq: results are bitwise identical (tests/test_gpu_parity.py
+// compares the paths).  The front planner's own plans (pqc_front.cu) additionally use the 4-slot
+// R_y / R_z layer ops, the merged ry-CZ-ry rotation and the pending Z frame defined below.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
