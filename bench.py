@@ -350,7 +350,12 @@ def run_b200(a):
     kp = by.get(kern, {"ms": 0.0, "launches": 0, "bytes": 0.0})
     achieved = kp["bytes"] / (kp["ms"] / 1e3) / 1e9 if kp["ms"] > 0 else 0.0
     alg_per_launch = kp["bytes"] / max(1, kp["launches"])
-    exchange = exchange_leg(a, dev, rank, world) if world > 1 else None
+    exchange = None
+    if world > 1:
+        try:
+            exchange = exchange_leg(a, dev, rank, world)
+        except Exception as e:            # the headline line must still be printed
+            exchange = {"error": f"{type(e).__name__}: {e}"[:300]}
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps,
