@@ -273,3 +273,23 @@ def test_front_planner_plans_and_plan_choice():
     for kind in ("TFIM", "XXZ"):
         head, passes, _, qc = front(kind, 16, 16)
         assert head.endswith("used for PQC.run: 0") and qc.program.n_passes > passes
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver runs beside ours): one JSON line with the
+    contract's keys, at a size a CPU finishes instantly; it must not need a GPU or the CUDA library."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--qubits", "6",
+                        "--layers", "2", "--steps", "2", "--warmup", "1"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
