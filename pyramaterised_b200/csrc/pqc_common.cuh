@@ -219,6 +219,7 @@ struct TPOp {              // 16 bytes
                            // RZ: t[1] = global bit;  CZ: t[0], t[1] = tile positions | 0xffff, t[2], t[3] = global bits
                            // CNOT: t[0] = control tile position | 0xffff, t[1] = control global bit
   uint8_t wt, nterms, spawn, pad;   // ZZSUM / GEN: linear-form table, term count; GEN: spawn index
+                                    // LAYER_RY4: pad = 1 when some slot carries a partner byte
 };
 struct TPSweep {
   // thread part, per nibble of the thread index: byte offset of the slot (low 16 bits) and

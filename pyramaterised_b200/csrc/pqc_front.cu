@@ -777,6 +777,7 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
               packs[q].sub |= (uint8_t)(code << (2 * k));
               if (is_merged) {
                 const std::pair<double, int>& mg = merged[i];
+                packs[q].pad = 1;                  // the kernel's partner-aware path
                 packs[q].t[k] = (uint16_t)trig_pair(o, mg.first);
                 const uint8_t pb = partner_byte(mg.second);
                 if (k == 0) packs[q].a = pb;

@@ -1169,8 +1169,9 @@ __global__ void __launch_bounds__(256) k_kl_terms(const long long* __restrict__ 
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < B; i += (long long)gridDim.x * 256) {
     const double x = (double)hist[i] / tc;
     const double y = (N - 1.0) * pow(1.0 - bin_mid(i, B, step), N - 2.0) / th;
-    double t;
-    if (x > 0.0 && y > 0.0) t = x * log(x / y) - x + y;
+    double t;                                  // scipy.special.kl_div, NaN first
+    if (isnan(x) || isnan(y)) t = NAN;         // e.g. every Haar weight underflowed: 0 / 0
+    else if (x > 0.0 && y > 0.0) t = x * log(x / y) - x + y;
     else if (x == 0.0 && y >= 0.0) t = y;
     else t = INFINITY;
     kl += t;

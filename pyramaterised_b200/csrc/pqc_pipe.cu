@@ -144,7 +144,20 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
     }                                                                              \
     if ((fz >> K) & 1u) C.x = -C.x;                                                \
   }
-      TP_RY_SLOT(0, op.a, c0) TP_RY_SLOT(1, op.b, c1) TP_RY_SLOT(2, op.wt, c2) TP_RY_SLOT(3, op.nterms, c3)
+      if (op.pad) {                               // some slot is a merged ry-CZ-ry rotation
+        TP_RY_SLOT(0, op.a, c0) TP_RY_SLOT(1, op.b, c1) TP_RY_SLOT(2, op.wt, c2) TP_RY_SLOT(3, op.nterms, c3)
+      } else {                                    // plain layer: four predicated table reads
+        if (sk & 0x03) c0 = trig[op.t[0]];
+        if (sk & 0x0c) c1 = trig[op.t[1]];
+        if (sk & 0x30) c2 = trig[op.t[2]];
+        if (sk & 0xc0) c3 = trig[op.t[3]];
+        if (fz) {
+          if (fz & 1u) c0.x = -c0.x;
+          if (fz & 2u) c1.x = -c1.x;
+          if (fz & 4u) c2.x = -c2.x;
+          if (fz & 8u) c3.x = -c3.x;
+        }
+      }
 #undef TP_RY_SLOT
       op_ry_t<0>(a, c0.x);
       op_ry_t<1>(a, c1.x);

@@ -171,6 +171,20 @@ def test_histogram_edge_semantics():
         engine.hist_f64(torch.zeros(4, dtype=torch.float64, device="cuda"), 0)
 
 
+def test_kl_haar_degenerate_cases_match_scipy():
+    """expr() where the Haar weights (N-1)(1-F)^(N-2) underflow (config 5: N = 2^28): with every
+    weight 0 the reference divides 0 / 0 and scipy.special.kl_div propagates NaN; at the full-size
+    bin count the first bin survives and KL = 0; an empty PQC bin against a positive Haar weight
+    contributes the weight."""
+    for bins, total, N in ((3928, 523776, 2.0 ** 28), (374962, 49995000, 2.0 ** 28), (60, 1000, 16.0)):
+        counts = np.zeros(bins, dtype=np.int64)
+        counts[0] = total
+        got = float(engine.kl_haar(torch.as_tensor(counts, device="cuda"), N).item())
+        with np.errstate(all="ignore"):
+            want = orc.expr_from_counts(counts, N)
+        assert (np.isnan(want) and np.isnan(got)) or abs(got - want) <= 1e-12 * max(1.0, abs(want)), (bins, got, want)
+
+
 def test_efficient_measurements(golden):
     qc = pyqc.templates.generate_circuit("generic_HE", 4, 2)
     m = pyqc.measure.Measurements(qc)
@@ -424,7 +438,8 @@ def test_front_plan_matches_block_plan_and_oracle(kind, n, p, S, monkeypatch):
 
 
 @pytest.mark.parametrize("kind,n,p", [("XXZ", 16, 16), ("generic_HE", 16, 16), ("NPQC", 16, 16),
-                                      ("NPQC", 20, 20), ("NPQC", 22, 20)])
+                                      ("NPQC", 20, 20), ("NPQC", 22, 20), ("generic_HE", 20, 8),
+                                      ("XXZ", 20, 8), ("TFIM", 20, 8), ("qg_circuit", 18, 4)])
 def test_full_depth_states_vs_oracle(kind, n, p):
     """Full-depth circuits of BASELINE configs 3 / 5 on the default plan (front planner) against the
     oracle: row 0 of a small batch, every amplitude to 1e-10."""
