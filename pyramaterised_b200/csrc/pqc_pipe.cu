@@ -499,17 +499,25 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
         for (int j = 0; j < 16; ++j) dp[gb ^ XSEL4R(j, g0, g1, g2, g3)] = a[j];
         break;
       }
+      // the sweep's slot masks are read again instead of being kept live across the ops: five
+      // registers fewer under the 128-register cap, fewer spills (hardware-efficient 16q x 16:
+      // 36.0 -> 34.0 ms, XXZ 16q x 16 on this kernel: 44.0 -> 40.8 ms).  Also measured and dropped
+      // (profiles/r2_final_summary.md): reading the next op ahead of the arithmetic (+25 - 60 %:
+      // spills), a sentinel op instead of the loop's end index (+4 - 9 %)
+      const uint32_t tw2 = sw.tt[0][lo] ^ sw.tt[1][hi];
+      const uint32_t sb2 = tw2 & 0xffffu;
+      const uint32_t u0 = sw.rs[0], u1 = sw.rs[1], u2 = sw.rs[2], u3 = sw.rs[3];
       if (npost) {
-        const uint32_t lb = sb ^ TP_LIN4(v, r0, r1, r2, r3);
-        const uint32_t l0 = TP_LIN4(col[0], r0, r1, r2, r3), l1 = TP_LIN4(col[1], r0, r1, r2, r3),
-                       l2 = TP_LIN4(col[2], r0, r1, r2, r3), l3 = TP_LIN4(col[3], r0, r1, r2, r3);
+        const uint32_t lb = sb2 ^ TP_LIN4(v, u0, u1, u2, u3);
+        const uint32_t l0 = TP_LIN4(col[0], u0, u1, u2, u3), l1 = TP_LIN4(col[1], u0, u1, u2, u3),
+                       l2 = TP_LIN4(col[2], u0, u1, u2, u3), l3 = TP_LIN4(col[3], u0, u1, u2, u3);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           *reinterpret_cast<c128*>(buf + (lb ^ XSEL4R(j, l0, l1, l2, l3))) = a[j];
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          *reinterpret_cast<c128*>(buf + (sb ^ XSEL4R(j, r0, r1, r2, r3))) = a[j];
+          *reinterpret_cast<c128*>(buf + (sb2 ^ XSEL4R(j, u0, u1, u2, u3))) = a[j];
       }
       tp_group_bar(grp);
     }
