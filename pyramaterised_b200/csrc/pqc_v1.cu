@@ -2306,6 +2306,11 @@ __global__ void __launch_bounds__(XS_NT, 2) k_xsum_gather(const GatherArgs A) {
   }
 }
 
+// A thread-block-cluster form of this kernel (the partner chunks of up to four far bits read from
+// the peer CTAs' shared memory instead of L2) was measured and dropped: bit-identical results, but
+// the headline step lost 1.8 % at cluster size 2 and 14 % at 16 -- DSMEM reads are slower than the L2
+// hits they replace (profiles/r2_xsum_cluster.md).
+
 // standalone Gram columns: one CTA per (sample, row j, partner); writes the sum into tile 0 of
 // the partial array and zeroes the other tiles so the reducer stays uniform.
 __global__ void __launch_bounds__(256) k_multi_dots(const c128* __restrict__ buf, int n,
@@ -3095,20 +3100,17 @@ int pqc_v1_derivatives(const pqc_program* prog, const double* d_angles, long lon
         }
         const long long grid = S << (n - g.cb);
         if (grid > 0x7fffffffLL) PQC_FAIL(-1, "gather grid too large");
-        static bool gather_attr = false;
-        if (!gather_attr) {
+        static PqcDeviceOnce gather_attr;
+        if (gather_attr.first())
           PQC_CUDA(cudaFuncSetAttribute(k_tile_gather, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         80 * 1024));
-          gather_attr = true;
-        }
         bool all_pure = n >= 12 && g.cb == 12;
         for (int k = 0; k < g.nparams; ++k) all_pure = all_pure && g.purex[k];
         if (all_pure) {
-          static bool xs_attr = false;
-          if (!xs_attr) {
+          static PqcDeviceOnce xs_attr;
+          if (xs_attr.first()) {
             PQC_CUDA(cudaFuncSetAttribute(k_xsum_gather, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           80 * 1024));
-            xs_attr = true;
           }
           k_xsum_gather<<<(unsigned)grid, XS_NT, 4096 * sizeof(c128), st>>>(g);
         } else {
