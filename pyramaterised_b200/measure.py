@@ -396,10 +396,17 @@ class Measurements:
         return (energy, traj, magics, ents, gkps)
 
     # ---- additive batch entry points ---------------------------------------------------------------------
-    def qfim_batch(self, angles, cutoff_eigvals=None):
+    def qfim_batch(self, angles, cutoff_eigvals=None, want_eigvals=False):
         """QFIM [S,P,P] (device) for every row of angles; with a cutoff also the effective
-        quantum dimensions [S] (int32, device)."""
+        quantum dimensions [S] (int32, device), and with `want_eigvals` the ascending spectra
+        [S,P] they were counted from (get_eigenvalues, measure.py:73-75)."""
         F = self.QC.qfim_batch(angles)
-        if cutoff_eigvals is None:
+        if cutoff_eigvals is None and not want_eigvals:
             return F
-        return F, engine.count_greater(engine.eigvalsh(F), cutoff_eigvals)
+        w = engine.eigvalsh(F)
+        out = (F,)
+        if cutoff_eigvals is not None:
+            out += (engine.count_greater(w, cutoff_eigvals),)
+        if want_eigvals:
+            out += (w,)
+        return out
