@@ -5,6 +5,7 @@ Additive batch entry points (`run_batch`, `qfim_batch`) expose the sample axis t
 reference loops over in Python (measure.py:132,247,356,407).
 """
 import numpy as np
+import torch
 
 from . import engine
 from .gates import *            # noqa: F401,F403  (the reference re-exports gates through circuit)
@@ -212,10 +213,33 @@ class PQC():
             g.flip_pauli()
 
     # ---- derivative states (circuit.py:149-192) ----------------------------------------------------
+    def _gradient_buffer_literal(self):
+        """circuit.py:149-192 followed gate by gate: for every parameterised gate the circuit is
+        re-run with that gate replaced by `derivative() * gate`.  The slow path, taken only when a
+        gate's derivative is not a sum of Pauli generators the engine can spawn (a
+        shared_parameter block whose members do not commute, gates.py:458-466): P x G small
+        gate-program launches instead of one derivative pipeline."""
+        if any(g.param_count == 2 for g in self.gates):
+            raise NotImplementedError("two-parameter gates together with a non-commuting "
+                                      "shared_parameter block are not lowered")
+        rows = [self.initial_state]
+        for g in self.gates:
+            rows[0] = g * rows[0]
+        for g_on in (g for g in self.gates if g.param_count > 0):
+            deriv = g_on.derivative()
+            st = self.initial_state
+            for g in self.gates:
+                st = g * st
+                if g is g_on:
+                    st = deriv * st                 # (deriv * gate) * state, circuit.py:164-168
+            rows.append(st)
+        return torch.stack([r.tensor.reshape(-1) for r in rows])
+
     def _gradient_buffer(self):
-        if not self.program.grad_supported or not self._derivatives_exact():
-            raise NotImplementedError("derivative states for this gate set (non-commuting "
-                                      "shared_parameter) are not lowered yet")
+        if self.program.grad_supported and not self._derivatives_exact():
+            return self._gradient_buffer_literal()
+        if not self.program.grad_supported:
+            raise NotImplementedError("derivative states for this gate set are not lowered yet")
         # quirk Q2 (circuit.py:186-189): for a two-parameter gate the reference re-finds the
         # gate with an index into the PARAMETERISED list; that is the intended gate only when
         # every earlier gate is parameterised.  Anything else is fenced off, not imitated.
@@ -267,8 +291,20 @@ class PQC():
     # ---- fused batch QFIM (additive) -----------------------------------------------------------------
     def qfim_batch(self, angles, want_states=False, max_work_bytes=None):
         """angles [S,P] -> QFIM [S,P,P] (device), as update_state + get_QFI per row."""
-        if not self.program.grad_supported or not self._derivatives_exact():
+        if not self.program.grad_supported:
             raise NotImplementedError("QFIM for this gate set is not lowered yet")
+        if not self._derivatives_exact():
+            # literal derivative states row by row (see _gradient_buffer_literal)
+            from . import engine
+            a = np.asarray(angles.cpu() if hasattr(angles, "cpu") else angles, dtype=np.float64)
+            Fs, sts = [], []
+            for row in a.reshape(-1, self.n_true_params):
+                self.set_params(list(row))
+                buf = self._gradient_buffer_literal()
+                Fs.append(engine.qfim_from_grads(buf[:1], buf[1:].unsqueeze(0))[0])
+                sts.append(buf[0])
+            F = torch.stack(Fs)
+            return (F, torch.stack(sts)) if want_states else F
         return self.program.qfim(angles, init=self.initial_state.tensor, want_states=want_states,
                                  max_work_bytes=max_work_bytes)
 

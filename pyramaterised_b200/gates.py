@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from . import qobj as qt                              # the reference exposes `qt` (gates.py:1)
-from .qobj import Composite, Operator, PauliSum, State
+from .qobj import Composite, Operator, OpSum, PauliSum, State
 
 rng = np.random.default_rng(1)                        # gates.py:10 -- same global stream
 
@@ -92,9 +92,13 @@ class Gate:
         return (b.operation if isinstance(b, Gate) else b) * self.operation
 
     def __add__(self, b):
-        raise NotImplementedError("sums of unitaries are not represented; use derivative()")
+        # gates.py:75-79: `self.operation + b.operation` -- a sum of unitaries stays a term list
+        return OpSum([self.operation, b.operation if isinstance(b, Gate) else b])
 
-    __radd__ = __add__
+    def __radd__(self, b):
+        if isinstance(b, (int, float)) and b == 0:       # sum() starts from 0
+            return OpSum([self.operation])
+        return OpSum([b.operation if isinstance(b, Gate) else b, self.operation])
 
     def set_theta(self, theta):
         return
@@ -460,12 +464,22 @@ class shared_parameter(PRot):
         return all(_pauli_commute(a, b) for i, a in enumerate(gens) for b in gens[i + 1:])
 
     def derivative(self):
-        deriv = 0
-        for g in self.layer:
-            deriv = deriv + g.derivative()
-        if not self._sum_of_generators_is_exact():
-            raise NotImplementedError("non-commuting shared_parameter derivative")
-        return deriv
+        if self._sum_of_generators_is_exact():
+            deriv = 0
+            for g in self.layer:
+                deriv = deriv + g.derivative()
+            return deriv
+        # gates.py:458-466, literally: sum_k prod(layer with member k -> D_k * U_k, reversed) times
+        # the ELEMENT-WISE conjugate of the block (take_derivative multiplies the block back in;
+        # conj is the inverse only when the block's matrix is symmetric -- reproduced, not fixed).
+        # A sum of products of gate programs: an OpSum, applied term by term (PQC's literal
+        # derivative path, circuit.py:149-172).
+        terms = []
+        for count, g in enumerate(self.layer):
+            new_layer = list(self.layer)
+            new_layer[count] = g.derivative() * g
+            terms.append(prod(new_layer[::-1]))
+        return OpSum(terms) * self.operation.conj()
 
     def flip_pauli(self):
         for g in self.layer:

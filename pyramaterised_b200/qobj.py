@@ -510,6 +510,58 @@ class Operator:
         return f"Operator(n={self.n}, {[_lib.OP_NAMES[o[0]] for o in self.ops]})"
 
 
+class OpSum:
+    """Sum of operator-like terms (Operator / PauliSum / Composite / DenseOp): what
+    `Gate.__add__` / `__radd__` denote (gates.py:75-85, `self.operation + b.operation`).  Unitaries
+    are kept as gate programs, so their sum stays a list of terms: applied to a state term by
+    term, dense (`full()`) only on request."""
+
+    type = "oper"
+
+    def __init__(self, terms):
+        self.terms = []
+        for t in terms:
+            self.terms += t.terms if isinstance(t, OpSum) else [t]
+
+    @property
+    def dims(self):
+        return self.terms[0].dims
+
+    def __add__(self, o):
+        if _is_scalar(o) and o == 0:          # sum() starts from the integer 0
+            return self
+        if hasattr(o, "operation") and not isinstance(o, (State, OpSum)):
+            o = o.operation
+        if isinstance(o, (OpSum, Operator, PauliSum, Composite, DenseOp)):
+            return OpSum([self, o])
+        return NotImplemented
+
+    __radd__ = lambda self, o: self if (_is_scalar(o) and o == 0) else OpSum([o, self]) \
+        if isinstance(o, (Operator, PauliSum, Composite, DenseOp)) else NotImplemented
+
+    def __mul__(self, o):
+        if isinstance(o, State):
+            out = None
+            for t in self.terms:
+                if isinstance(t, DenseOp):
+                    m = torch.as_tensor(t._m, device=o.tensor.device)
+                    v = State(m @ o.tensor.reshape(-1), o.dims)
+                else:
+                    v = t * o
+                out = v if out is None else out + v
+            return out
+        if isinstance(o, (Operator, PauliSum, Composite)):
+            return OpSum([Composite([t]) * o if not isinstance(t, Composite) else t * o
+                          for t in self.terms])
+        return NotImplemented
+
+    def full(self):
+        return sum(t.full() for t in self.terms)
+
+    def __repr__(self):
+        return "OpSum(" + " + ".join(repr(t) for t in self.terms) + ")"
+
+
 class Composite:
     """Product of Operator / PauliSum factors, leftmost acts last."""
 
@@ -533,3 +585,11 @@ class Composite:
         if _is_scalar(o) and o == 1:
             return self
         return NotImplemented
+
+    def full(self):
+        """Dense matrix (small n): the product of the factors' matrices."""
+        out = None
+        for f in self.factors:
+            m = f.full()
+            out = m if out is None else out @ m
+        return out

@@ -25,6 +25,12 @@ def golden_r2():
     return np.load(os.path.join(ROOT, "tests", "golden", "ref_golden_r2.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_r3():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_golden_r3.npz"))
+
+
 def pytest_collection_modifyitems(config, items):
     """gpu-marked tests are skipped (not failed) on a box without CUDA."""
     try:

@@ -87,10 +87,6 @@ def test_quirk_q2_is_fenced_not_imitated():
     qc.update_state([0.3, 0.4, 0.5])
     with pytest.raises(NotImplementedError):
         qc.get_gradients()
-    bad = pyqc.PQC(3)
-    bad.add_layer([pyqc.shared_parameter([pyqc.R_x(0, 3), pyqc.R_z(0, 3)], 3, commute=False)])
-    with pytest.raises(NotImplementedError):
-        bad.get_gradients()
 
 
 def test_reference_known_answers(golden):
@@ -991,3 +987,47 @@ def test_dense_apply_large_register_is_unitary():
     q0 = pyqc.PQC(n)
     q0.add_layer([pyqc.R_y(i, n) for i in range(n)])
     assert np.abs((qb.run_batch(Z) - q0.run_batch(A[:, :n])).cpu().numpy()).max() < 1e-12
+
+
+def test_noncommuting_shared_parameter_vs_reference(golden_r3):
+    """shared_parameter(commute=False) whose members do not commute (gates.py:458-466: the sum of
+    products times the element-wise conjugate of the block): states, cost, every derivative state,
+    QFIM and EQD against the unmodified reference (tests/golden/make_golden_r3.py) and the oracle;
+    the batched QFIM entry point takes the same literal path."""
+    import cases_r3
+    from helpers import specs_from_circuit
+    for k, ang in enumerate(cases_r3.NONCOMM3_ANGLES):
+        qc = cases_r3.build_noncommuting3(pyqc)
+        m = pyqc.measure.Measurements(qc)
+        st = qc.update_state(list(ang))
+        assert np.abs(st.numpy() - golden_r3[f"noncomm3/{k}/state"]).max() < ATOL
+        assert abs(qc.cost(list(ang)) - float(golden_r3[f"noncomm3/{k}/cost"])) < ATOL
+        gr = np.stack([g.numpy() for g in qc.get_gradients()])
+        assert np.abs(gr - golden_r3[f"noncomm3/{k}/grads"]).max() < ATOL
+        specs = specs_from_circuit(qc)
+        assert np.abs(gr - orc.gradients(specs, 3, np.array([ang]), None)[0]).max() < ATOL
+        F = m.get_QFI()
+        ref = golden_r3[f"noncomm3/{k}/qfi"]
+        assert np.abs(F - ref).max() < RTOL * max(1.0, np.abs(ref).max())
+        assert m.get_effective_quantum_dimension(1e-12) == int(golden_r3[f"noncomm3/{k}/eqd"])
+        # the derivative of one gate, as the reference API hands it out (circuit.py:149-172)
+        g5 = [g for g in qc.gates if g.param_count > 0][5]
+        assert np.abs(qc.take_derivative(g5).numpy() - golden_r3[f"noncomm3/{k}/grads"][5]).max() < ATOL
+    qc = cases_r3.build_noncommuting3(pyqc)
+    Fb, sb = qc.qfim_batch(np.array(cases_r3.NONCOMM3_ANGLES), want_states=True)
+    for k in range(2):
+        ref = golden_r3[f"noncomm3/{k}/qfi"]
+        assert np.abs(Fb[k].cpu().numpy() - ref).max() < RTOL * max(1.0, np.abs(ref).max())
+        assert np.abs(sb[k].cpu().numpy() - golden_r3[f"noncomm3/{k}/state"]).max() < ATOL
+
+
+def test_gate_sums_vs_reference(golden_r3):
+    """Gate.__add__ / __radd__ (gates.py:75-85): sums of gate operators, dense and applied."""
+    import cases_r3
+    N, a, b, c = cases_r3.build_sum_gates(pyqc)
+    assert np.abs((a + b).full() - golden_r3["sum/a_plus_b"]).max() < 1e-14
+    assert np.abs(((a + b) + c).full() - golden_r3["sum/a_plus_b_plus_c"]).max() < 1e-14
+    assert np.abs((a.operation + c).full() - golden_r3["sum/radd"]).max() < 1e-14
+    assert np.abs(sum([a, b]).full() - golden_r3["sum/a_plus_b"]).max() < 1e-14
+    st = pyqc.State(torch.as_tensor(golden_r3["sum/state_in"], device="cuda"))
+    assert np.abs(((a + b) * st).numpy() - golden_r3["sum/applied"]).max() < ATOL

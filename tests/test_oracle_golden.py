@@ -156,3 +156,27 @@ def test_magic_12q(golden):
     assert abs(orc.renyi_fwht(st[0], 2.0) - r2) < RTOL * abs(r2)
     assert abs(orc.gkp(st[0]) - g) < RTOL * abs(g)
     assert abs(orc.single_Q(st[0], 12) - float(golden["magic12/Q"])) < ATOL
+
+
+def test_noncommuting_shared_parameter_branch(golden_r3):
+    """gates.py:458-466 with members that do not commute (and non-symmetric R_y members, so the
+    element-wise conjugate of the block is not its inverse): the oracle's restatement against the
+    reference-generated fixtures of tests/golden/make_golden_r3.py."""
+    import cases_r3
+    specs = [("R_y", 0), ("R_y", 1), ("R_y", 2), ("CHAIN", "CNOT"),
+             ("shared_parameter", [("R_x", 0), ("R_z", 0)], False),
+             ("shared_parameter", [("R_y", 0), ("R_y", 1)], False),
+             ("CHAIN", "CPHASE"),
+             ("shared_parameter", [("R_zz", 0, 1), ("R_x", 1), ("R_y", 2)], False),
+             ("R_x", 2)]
+    ang = np.array(cases_r3.NONCOMM3_ANGLES)
+    st = orc.run(specs, 3, ang, None)
+    gr = orc.gradients(specs, 3, ang, None)
+    for k in range(len(ang)):
+        assert np.abs(st[k] - golden_r3[f"noncomm3/{k}/state"]).max() < ATOL
+        assert np.abs(gr[k] - golden_r3[f"noncomm3/{k}/grads"]).max() < ATOL
+        F = orc.qfi(st[k], gr[k])
+        ref = golden_r3[f"noncomm3/{k}/qfi"]
+        assert np.abs(F - ref).max() < RTOL * max(1.0, np.abs(ref).max())
+        assert orc.eqd(F, 1e-12) == int(golden_r3[f"noncomm3/{k}/eqd"])
+        assert abs(orc.cost_zz(st[k:k + 1])[0] - golden_r3[f"noncomm3/{k}/cost"]) < ATOL
