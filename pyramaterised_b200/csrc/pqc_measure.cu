@@ -387,6 +387,104 @@ static int mw_tiles(const c128* d_states, long long S, int n, double* d_Q, doubl
   return rc;
 }
 
+// ---------------------------------------------------------------------------------
+// Meyer-Wallach for n <= 11 (BASELINE configs 1 and 2: 4 and 10 qubits, up to 1e5 states): one
+// CTA of 128 threads per state.  The state is read ONCE into shared memory; every thread then
+// accumulates (r00, Re r01, Im r01) of four qubits at a time over its share of the amplitude
+// pairs, the 16 values of a group are reduced over the warp by the fixed halving exchange of
+// k_mw_tiles and over the four warps in order.  Output in k_mw_tiles' partial layout (48 values
+// per state: group g = bits 4g .. 4g+3 at 16 g + 3 k, the norm at 12), finished by
+// k_mw_tiles_fin -- bitwise reproducible.  (k_mw_accumulate, which this replaces for small n,
+// re-read the state per qubit and ran four block reductions per qubit: 3.3 ms per 1e5 states of
+// 10 qubits.)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_mw_small(const c128* __restrict__ states, int n,
+                                                  double* __restrict__ part) {
+  extern __shared__ __align__(16) c128 ms_sm[];
+  __shared__ double wred[3][4][16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = 1 << n, half = D >> 1;
+  const c128* psi = states + ((long long)blockIdx.x << n);
+  double nr = 0.0;
+  for (int i = tid; i < D; i += 128) {
+    const c128 v = psi[i];
+    ms_sm[i] = v;
+    nr = fma(v.x, v.x, fma(v.y, v.y, nr));
+  }
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.0;
+    if (4 * g < n) {                                   // uniform over the grid
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int b = 4 * g + k;
+        if (b < n) {
+          const int lowmask = (1 << b) - 1;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          for (int p = tid; p < half; p += 128) {
+            const int x = ((p & ~lowmask) << 1) | (p & lowmask);
+            const c128 a0 = ms_sm[x], a1 = ms_sm[x | (1 << b)];
+            s0 = fma(a0.x, a0.x, fma(a0.y, a0.y, s0));
+            s1 = fma(a0.x, a1.x, fma(a0.y, a1.y, s1));      // a0 * conj(a1)
+            s2 = fma(a0.y, a1.x, fma(-a0.x, a1.y, s2));
+          }
+          v[3 * k] = s0; v[3 * k + 1] = s1; v[3 * k + 2] = s2;
+        }
+      }
+      if (g == 0) v[12] = nr;
+    }
+    const double r = mw_reduce16(v, lane);             // lane 2 i holds value i of this warp
+    if ((lane & 1) == 0) wred[g][warp][lane >> 1] = r;
+  }
+  __syncthreads();
+  if (tid < 48) {
+    const int g = tid >> 4, i = tid & 15;
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) t += wred[g][w][i];
+    part[(long long)blockIdx.x * 48 + tid] = t;
+  }
+}
+
+static int mw_small(const c128* d_states, long long S, int n, double* d_Q, double* d_acc,
+                    cudaStream_t st) {
+  if (S > 0x7fffffffLL) PQC_FAIL(-1, "Meyer-Wallach grid too large; split the batch");
+  MWFin fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.npass = 1;
+  fin.cps = 1;
+  for (int b = 0; b < n; ++b) {
+    fin.src_pass[b] = 0;
+    fin.src_slot[b] = (b >> 2) * 16 + 3 * (b & 3);
+  }
+  double* part = nullptr;
+  PQC_CUDA(cudaMallocAsync(&part, sizeof(double) * 48 * (size_t)S, st));
+  int rc = 0;
+  k_mw_small<<<(unsigned)S, 128, sizeof(c128) << n, st>>>(d_states, n, part);
+  ++g_pqc_launches;
+  if (cudaGetLastError() != cudaSuccess) rc = -2;
+  if (rc == 0) {
+    k_mw_tiles_fin<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(part, S, n, fin, d_Q, d_acc);
+    ++g_pqc_launches;
+    if (cudaGetLastError() != cudaSuccess) rc = -2;
+  }
+  cudaFreeAsync(part, st);
+  if (rc) pqc_set_error("Meyer-Wallach small-state kernel launch failed");
+  return rc;
+}
+
+// which Meyer-Wallach path: n >= 12 the tile kernel, n <= 11 the one-CTA-per-state kernel;
+// PQC_MW=generic keeps k_mw_accumulate (the independent cross-check of the tests)
+static int mw_dispatch(const c128* d_states, long long S, int n, double* d_Q, double* d_acc,
+                       cudaStream_t st, bool* handled) {
+  *handled = mw_tiles_enabled();
+  if (!*handled) return 0;
+  return n >= 12 ? mw_tiles(d_states, S, n, d_Q, d_acc, st) : mw_small(d_states, S, n, d_Q, d_acc, st);
+}
+
 static int mw_accumulate(const c128* d_states, long long S, int n, double* d_acc, cudaStream_t st) {
   const int chunk_log2 = std::min(n, 14);
   const long long grid = S << (n - chunk_log2);
@@ -402,7 +500,11 @@ extern "C" int pqc_meyer_wallach(const pqc_c128* d_states, int64_t S, int n, dou
   if (S <= 0) return 0;
   if (n < 1 || n > PQC_MAX_QUBITS) PQC_FAIL(-1, "bad qubit count");
   cudaStream_t st = (cudaStream_t)stream;
-  if (n > 14 && mw_tiles_enabled()) return mw_tiles((const c128*)d_states, S, n, d_Q, nullptr, st);
+  {
+    bool handled = false;
+    const int rc = mw_dispatch((const c128*)d_states, S, n, d_Q, nullptr, st, &handled);
+    if (handled) return rc;
+  }
   double* acc = nullptr;
   PQC_CUDA(cudaMallocAsync(&acc, sizeof(double) * 4 * n * S, st));
   int rc = mw_accumulate((const c128*)d_states, S, n, acc, st);
@@ -430,9 +532,9 @@ extern "C" int pqc_ptrace_1q(const pqc_c128* d_state, int n, int qubit, pqc_c128
   cudaStream_t st = (cudaStream_t)stream;
   double* acc = nullptr;
   PQC_CUDA(cudaMallocAsync(&acc, sizeof(double) * 4 * n, st));
-  int rc = (n > 14 && mw_tiles_enabled())
-               ? mw_tiles((const c128*)d_state, 1, n, nullptr, acc, st)
-               : mw_accumulate((const c128*)d_state, 1, n, acc, st);
+  bool handled = false;
+  int rc = mw_dispatch((const c128*)d_state, 1, n, nullptr, acc, st, &handled);
+  if (!handled) rc = mw_accumulate((const c128*)d_state, 1, n, acc, st);
   if (rc == 0) {
     k_rho_from_acc<<<1, 1, 0, st>>>(acc, n, qubit, (c128*)d_rho);
     ++g_pqc_launches;

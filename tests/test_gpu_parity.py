@@ -449,11 +449,13 @@ def test_full_depth_states_vs_oracle(kind, n, p):
     assert abs(float(engine.meyer_wallach(st[:1])[0].item()) - orc.single_Q(ref[0], n)) < ATOL
 
 
-@pytest.mark.parametrize("n,S", [(15, 3), (16, 5), (19, 2), (20, 1), (23, 1), (24, 1)])
+@pytest.mark.parametrize("n,S", [(3, 7), (4, 1000), (7, 5), (10, 300), (11, 3), (12, 9), (13, 2),
+                                 (14, 3), (15, 3), (16, 5), (19, 2), (20, 1), (23, 1), (24, 1)])
 def test_meyer_wallach_tile_kernel_matches_generic_and_oracle(n, S, monkeypatch):
-    """n > 14: k_mw_tiles (all 12 tile bits per read, 8 more per further pass, fixed-order
-    reductions) against k_mw_accumulate (PQC_MW=generic), the oracle, ptrace and itself run twice
-    (bitwise reproducible: no floating-point atomics)."""
+    """n >= 12: k_mw_tiles (all 12 tile bits per read, 8 more per further pass), n <= 11:
+    k_mw_small (one CTA per state, one read) -- both with fixed-order reductions -- against
+    k_mw_accumulate (PQC_MW=generic), the oracle, ptrace and themselves run twice (bitwise
+    reproducible: no floating-point atomics)."""
     qc = pyqc.templates.generate_circuit("generic_HE", n, 2)
     ang = np.random.default_rng(n).random((S, qc.n_true_params)) * 2 * np.pi
     st = qc.run_batch(ang)
@@ -469,6 +471,7 @@ def test_meyer_wallach_tile_kernel_matches_generic_and_oracle(n, S, monkeypatch)
     assert np.abs(rho1 - rho0).max() < 1e-12
     if n <= 20:
         assert abs(float(Q1[0].item()) - orc.single_Q(st[0].cpu().numpy(), n)) < ATOL
+        assert abs(float(Q1[S - 1].item()) - orc.single_Q(st[S - 1].cpu().numpy(), n)) < ATOL
 
 
 def test_ragged_and_empty_batches():
