@@ -200,6 +200,11 @@ struct SeqPlan {
                                      // CZ with a bit that is constant for the thread (see below)
 #define PQC_K_CZF 39                 // CZ(register bit, thread-constant bit): a pending Z "frame"
 #define PQC_K_ZFLUSH 40              // apply the pending Z frame now
+#define PQC_K_RZZ1 41                // one R_zz on two register bits: a = ka * 4 + kb, t[0] = (cos, sin) of
+                                     // the half angle; amplitude x (c - i s) where the bits agree, (c + i s) else
+#define PQC_K_RZZ2 42                // two same-angle R_zz on disjoint register-bit pairs (all four bits):
+                                     // a = 0 (01|23), 1 (02|13), 2 (03|12), t[0] = (cos, sin) of the FULL
+                                     // angle; both pairs aligned: x (c - i s), both anti-aligned: x (c + i s)
 // Z frame (k_tile_pipe): CZ between a register bit k and a bit that is constant for the thread is
 // Z^b on bit k.  Z anticommutes with the X / Y rotations and commutes with everything diagonal,
 // so instead of touching 16 amplitudes it flips a per-thread flag; later rx / ry / xy rotations

@@ -858,6 +858,37 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
                 mem.push_back(L[y]);
                 usedz[y] = 1;
               }
+              // one or two bonds that sit entirely on the register bits (the brick-wall diamonds
+              // of the XXZ template, two thirds of its R_zz groups): a direct phase on the
+              // thread's 16 amplitudes -- 64 / 32 FP64 instructions instead of a table-lookup op
+              // (per amplitude LOP3 + POPC + LDS.128 + a complex product, ~165 in all)
+              {
+                static const bool no_rzzr = getenv("PQC_FRONT_NORZZR") != nullptr;
+                bool regs = !no_rzzr && mem.size() <= 2;
+                for (int m : mem) regs = regs && kof[F.ops[m].b0] >= 0 && kof[F.ops[m].b1] >= 0;
+                if (regs && mem.size() == 2 && (F.ops[mem[0]].support & F.ops[mem[1]].support)) regs = false;
+                if (regs) {
+                  const FOp& o0 = F.ops[mem[0]];
+                  const int ka = std::min(kof[o0.b0], kof[o0.b1]), kb = std::max(kof[o0.b0], kof[o0.b1]);
+                  TPOp t;
+                  memset(&t, 0, sizeof(t));
+                  t.b = 0xff;
+                  if (mem.size() == 1) {
+                    t.kind = PQC_K_RZZ1;
+                    t.a = (uint8_t)(ka * 4 + kb);
+                    t.t[0] = (uint16_t)trig_of(1, o0);
+                  } else {
+                    // the pair that holds register bit 0 names the pairing: 01|23, 02|13, 03|12
+                    const FOp& o1 = F.ops[mem[1]];
+                    const int partner0 = ka == 0 ? kb : (kof[o1.b0] == 0 ? kof[o1.b1] : kof[o1.b0]);
+                    t.kind = PQC_K_RZZ2;
+                    t.a = (uint8_t)(partner0 - 1);
+                    t.t[0] = (uint16_t)trig_of(2, o0);
+                  }
+                  if (!push(t)) FRONT_FAIL(18);
+                  continue;
+                }
+              }
               if (nwt >= TP_MAX_WT) FRONT_FAIL(17);
               uint32_t wt[33];
               memset(wt, 0, sizeof(wt));

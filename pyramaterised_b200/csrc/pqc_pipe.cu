@@ -81,6 +81,36 @@ __device__ __forceinline__ void op_rz_t(c128 (&a)[16], double t) {
   }
 }
 
+// R_zz on the register bits KA < KB: exp(-i theta/2 z_a z_b), (c, s) = (cos, sin)(theta / 2)
+template <int KA, int KB>
+__device__ __forceinline__ void op_rzz1(c128 (&a)[16], double c, double s) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const double sj = (((j >> KA) ^ (j >> KB)) & 1) ? s : -s;
+    const c128 v = a[j];
+    a[j] = make_double2(fma(-sj, v.y, c * v.x), fma(sj, v.x, c * v.y));
+  }
+}
+// two same-angle R_zz on the disjoint register-bit pairs (KA, KB) and (the other two bits): the
+// phase is exp(-i theta) where both pairs are aligned, exp(+i theta) where both are anti-aligned
+// and 1 where they differ; (c, s) = (cos, sin)(theta)
+template <int KA, int KB>
+__device__ __forceinline__ void op_rzz2(c128 (&a)[16], double c, double s) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int p0 = ((j >> KA) ^ (j >> KB)) & 1;
+    const int rest = 15 & ~((1 << KA) | (1 << KB));
+    int p1 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if ((rest >> k) & 1) p1 ^= (j >> k) & 1;
+    if (p0 != p1) continue;
+    const double sj = p0 ? s : -s;
+    const c128 v = a[j];
+    a[j] = make_double2(fma(-sj, v.y, c * v.x), fma(sj, v.x, c * v.y));
+  }
+}
+
 __device__ __forceinline__ uint32_t tp_partner_bit(uint32_t pb, uint32_t lidx, uint32_t tbase) {
   return (pb & 0x80u) ? ((tbase >> (pb & 0x7fu)) & 1u) : ((lidx >> pb) & 1u);
 }
@@ -209,6 +239,21 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
         case 7: op_xy<1, 3>(a, cs.x, cs.y); break;
         default: op_xy<2, 3>(a, cs.x, cs.y); break;
       }
+    } else if (kind == PQC_K_RZZ1) {
+      const double2 cs = trig[op.t[0]];
+      switch (op.a) {
+        case 1: op_rzz1<0, 1>(a, cs.x, cs.y); break;
+        case 2: op_rzz1<0, 2>(a, cs.x, cs.y); break;
+        case 3: op_rzz1<0, 3>(a, cs.x, cs.y); break;
+        case 6: op_rzz1<1, 2>(a, cs.x, cs.y); break;
+        case 7: op_rzz1<1, 3>(a, cs.x, cs.y); break;
+        default: op_rzz1<2, 3>(a, cs.x, cs.y); break;
+      }
+    } else if (kind == PQC_K_RZZ2) {
+      const double2 cs = trig[op.t[0]];
+      if (op.a == 0) op_rzz2<0, 1>(a, cs.x, cs.y);
+      else if (op.a == 1) op_rzz2<0, 2>(a, cs.x, cs.y);
+      else op_rzz2<0, 3>(a, cs.x, cs.y);
     } else if (kind == PQC_K_ZZSUM || kind == PQC_K_GEN) {
       // w(x) = w(tile) ^ w(thread part) ^ w(register value j); wn holds w per tile nibble value
       const uint32_t(*wn)[16] = P->wn[op.wt];

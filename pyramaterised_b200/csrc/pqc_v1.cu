@@ -23,24 +23,34 @@
 #include "pqc_common.cuh"
 #include "pqc_ops.cuh"
 
+#ifndef PQC_FRONT_SEQ_MAX_QUBITS
+#define PQC_FRONT_SEQ_MAX_QUBITS 22    // XXZ-type circuits: the front plan up to here (see pqc_use_front)
+#endif
+
 // Which plan runs PQC.run.  The front plan (pqc_front.cu, few deep passes on k_tile_pipe) wins
 // wherever the block plan would run passes on the generic interpreter (CNOT-chain circuits:
-// 2.2x) or k_layer_seq passes with runs of R_z / CZ (NPQC: 1.6x).  The block plan stays when
-// every one of its passes is a layer pass (TFIM: k_layer_pass' compile-time geometry, 1.9x) or a
-// layer-sequence pass without diagonal runs (XXZ: 43 light passes at 4.3 TB/s beat 10 passes of
-// 9 sweeps each by 9 - 20 %); measured in profiles/r2_front_vs_block.jsonl.
+// 2.2x), k_layer_seq passes with runs of R_z / CZ (NPQC: 1.6x - 4x), and -- since the R_zz bonds
+// that sit on the register bits are direct phases instead of table-lookup ops (PQC_K_RZZ1 / 2) --
+// the XXZ template's layer-sequence passes up to 22 qubits (12q x 16: 6.0 against 8.5 ms per 8192
+// states, 14q: 16.0 / 19.3 ms per 4096, 16q: 35.7 / 43.9 ms per 2048, 18q x 8: 21.9 / 23.8 ms per
+// 512, 20q x 8: 50.6 / 55.2 ms per 256; at 24q x 4 the 19 light passes win, 33.5 / 35.6 ms per 16:
+// profiles/r2_rzz_register_ops.md).  The block plan stays when every one of its passes is a
+// layer pass (TFIM: k_layer_pass' compile-time geometry, 1.7x).
 // PQC_FRONT=0 / 1 forces the choice (read per call so tests can compare the plans).
 bool pqc_use_front(const pqc_program* prog) {
   if (!prog->front_ok || prog->front_run.empty()) return false;
   const char* e = getenv("PQC_FRONT");
   if (e && strcmp(e, "0") == 0) return false;
   if (e && strcmp(e, "1") == 0) return true;
-  bool all_light = !prog->v1_run.empty();
+  bool all_fast = !prog->v1_run.empty(), all_light = all_fast;
   for (int pi : prog->v1_run) {
     const V1Pass& ps = prog->v1_passes[pi];
+    all_fast = all_fast && ps.fast_ok;
     all_light = all_light && (ps.fast_ok || (ps.seq_ok && !ps.seq.has_diag));
   }
-  return !all_light;
+  if (all_fast) return false;
+  if (all_light && prog->n > PQC_FRONT_SEQ_MAX_QUBITS) return false;
+  return true;
 }
 
 bool pqc_use_v0() {

@@ -405,7 +405,8 @@ def test_tile_pipe_kernel_matches_per_tile_kernels_bitwise(kind, n, p, S, monkey
 FRONT_CASES = [("XXZ", 16, 3, 5), ("XXZ", 13, 4, 3), ("generic_HE", 16, 3, 5), ("generic_HE", 12, 4, 3),
                ("NPQC", 16, 5, 5), ("NPQC", 17, 3, 2), ("TFIM", 16, 3, 5), ("TFIM_modified", 14, 2, 3),
                ("qg_circuit", 13, 2, 3), ("Circuit_2", 12, 2, 3), ("clifford", 12, 2, 3),
-               ("Circuit_9", 12, 2, 3), ("y_CPHASE", 13, 2, 3), ("XXZ", 20, 2, 1)]
+               ("Circuit_9", 12, 2, 3), ("y_CPHASE", 13, 2, 3), ("XXZ", 20, 2, 1), ("XXZ", 16, 16, 2),
+               ("XXZ", 14, 6, 3), ("TFIM", 14, 5, 2)]
 
 
 @pytest.mark.parametrize("kind,n,p,S", FRONT_CASES)

@@ -1,10 +1,17 @@
 #!/bin/bash
-# Round 2: the front planner on k_tile_pipe -- parity, then gate-apply throughput by template layers.
-tag=${1:-r2f}
+# front-plan parity + gate-apply timings per plan.  Usage: bash tools/gpu_r2_front.sh TAG
+tag=${1:-r4e}
 out=gpurun_out/$tag; mkdir -p $out
-timeout 1200 python -m pytest tests -m gpu -q -x -k "front_plan or full_depth or tile_pipe" > $out/pytest.log 2>&1; tail -15 $out/pytest.log
-cfgs="c3:XXZ:16:16:2048 c3:generic_HE:16:16:2048 c3:NPQC:16:16:4096 c3:TFIM:16:16:4096 c3:NPQC:24:16:16 c3:NPQC:28:8:2 c3:NPQC:28:20:2 c3:XXZ:20:8:256"
-for fr in 1 0; do
-  PQC_FRONT=$fr timeout 600 python tools/bench_configs.py $cfgs > $out/apply_front$fr.jsonl 2> $out/apply_front$fr.err
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "front_plan or full_depth or tile_pipe" > $out/pytest.log 2>&1; tail -3 $out/pytest.log
+cfgs="c3:XXZ:16:16:2048 c3:XXZ:20:8:256 c3:generic_HE:16:16:2048 c3:NPQC:16:16:4096 c3:TFIM:16:16:4096"
+PQC_FRONT=1 timeout 300 python tools/bench_configs.py $cfgs > $out/apply_front.jsonl 2> $out/apply.err
+PQC_FRONT=1 PQC_FRONT_NORZZR=1 timeout 300 python tools/bench_configs.py c3:XXZ:16:16:2048 c3:XXZ:20:8:256 > $out/apply_front_norzzr.jsonl 2>> $out/apply.err
+PQC_FRONT=0 timeout 300 python tools/bench_configs.py c3:XXZ:16:16:2048 c3:XXZ:20:8:256 > $out/apply_block.jsonl 2>> $out/apply.err
+for f in apply_front apply_front_norzzr apply_block; do echo $f; python - $out/$f.jsonl <<'PY'
+import json, sys
+for l in open(sys.argv[1]):
+    j = json.loads(l)
+    print(" ", j["config"], "ms", round(j["ms"], 2), "passes", j["passes"], "by-layers GB/s", round(j["algorithmic_GBps_layers"]))
+PY
 done
-cat $out/apply_front1.jsonl; echo; cat $out/apply_front0.jsonl; tail -3 $out/apply_front1.err
+tail -3 $out/apply.err
