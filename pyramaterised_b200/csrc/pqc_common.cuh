@@ -226,6 +226,17 @@ struct TPOp {              // 16 bytes
   uint8_t wt, nterms, spawn, pad;   // ZZSUM / GEN: linear-form table, term count; GEN: spawn index
                                     // LAYER_RY4: pad = 1 when some slot carries a partner byte
 };
+#define TP_MAX_INJ 6
+// X / CNOT relabeling folded into a sweep's load or store, worked out by the planner: register
+// index j lives at slot  base ^ XOR_{k in j} l[k] ^ XOR_i (control bit of injection i ? inj[i].lm : 0).
+// An injection is a CNOT whose control bit is constant for the thread (a thread bit of the tile or
+// a bit of the tile's offset); more than TP_MAX_INJ distinct controls: the planner gives the pass up.
+struct TPAff {
+  uint16_t l[4];
+  uint16_t base;
+  uint8_t ninj, pad;
+  struct { uint8_t src, pad; uint16_t lm; } inj[TP_MAX_INJ];   // src: a partner byte
+};
 struct TPSweep {
   // thread part, per nibble of the thread index: byte offset of the slot (low 16 bits) and
   // logical tile index (high 16 bits); word = tt[0][tid & 15] ^ tt[1][tid >> 4]
@@ -237,6 +248,7 @@ struct TPSweep {
   // (the last npost ops) of the sweep: targets are register bits, so a thread only permutes its
   // own 16 slots
   uint8_t npre, npost, pad[2];
+  TPAff pre, post;
 };
 struct PipePlan {
   int nsw, nops, ntrig, nwt;
@@ -248,6 +260,7 @@ struct PipePlan {
   uint16_t ld_sr[4];
   uint32_t st_t[2][16];    // last sweep, direct store: amplitude offset of the thread part
   uint32_t st_r[4];        //   and of the register bits
+  uint32_t st_q[4], st_base, st_gm[TP_MAX_INJ];   // the last sweep's store relabeling (TPAff) as amplitude masks
   uint32_t wn[TP_MAX_WT][3][16];
   uint32_t wo[TP_MAX_WT][PQC_MAX_QUBITS - 12];
   TPSweep sw[TP_MAX_SWEEPS];

@@ -698,6 +698,66 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
         ps.op_ids.insert(ps.op_ids.end(), F.ops[i].ids.begin(), F.ops[i].ids.end());
       }
       sw.npre = (uint8_t)sim.pre.size();
+      // the relabeling of ops [b, e) as the kernel's tp_affine would work it out per thread (reverse:
+      // folded into the load, i.e. the inverse order), but once, here: col / v_const by simulation,
+      // every CNOT with a thread-fixed control as an injection carried through the later ops
+      auto build_aff = [&](int b, int e, bool reverse, TPAff& af, bool global) -> bool {
+        uint32_t col[4] = {1u, 2u, 4u, 8u}, vc = 0u, m[TP_MAX_INJ];
+        uint8_t src[TP_MAX_INJ];
+        int ninj = 0;
+        bool ok = true;
+        for (int q = 0; q < e - b; ++q) {
+          const TPOp& pm = pp.ops[reverse ? e - 1 - q : b + q];
+          const int kt = pm.b;
+          if (pm.kind == PQC_OP_X) {
+            vc ^= 1u << kt;
+          } else if (pm.a != 0xff) {
+            const int kc = pm.a;
+            for (int c = 0; c < 4; ++c) col[c] ^= ((col[c] >> kc) & 1u) << kt;
+            vc ^= ((vc >> kc) & 1u) << kt;
+            for (int i2 = 0; i2 < ninj; ++i2) m[i2] ^= ((m[i2] >> kc) & 1u) << kt;
+          } else {
+            const uint8_t sb8 = pm.t[0] != 0xffff ? (uint8_t)pm.t[0] : (uint8_t)(0x80 | pm.t[1]);
+            int at = -1;
+            for (int i2 = 0; i2 < ninj; ++i2)
+              if (src[i2] == sb8) at = i2;
+            if (at >= 0) {
+              m[at] ^= 1u << kt;
+            } else if (ninj < TP_MAX_INJ) {
+              src[ninj] = sb8;
+              m[ninj++] = 1u << kt;
+            } else {
+              ok = false;
+            }
+          }
+        }
+        memset(&af, 0, sizeof(af));
+        if (!ok) return false;
+        auto lin16 = [&](uint32_t x) {
+          uint32_t r = 0;
+          for (int k = 0; k < 4; ++k) if ((x >> k) & 1u) r ^= sw.rs[k];
+          return (uint16_t)r;
+        };
+        auto lin32 = [&](uint32_t x) {
+          uint32_t r = 0;
+          for (int k = 0; k < 4; ++k) if ((x >> k) & 1u) r ^= 1u << tb[rpos[k]];
+          return r;
+        };
+        for (int c = 0; c < 4; ++c) af.l[c] = lin16(col[c]);
+        af.base = lin16(vc);
+        af.ninj = (uint8_t)ninj;
+        for (int i2 = 0; i2 < ninj; ++i2) {
+          af.inj[i2].src = src[i2];
+          af.inj[i2].lm = lin16(m[i2]);
+        }
+        if (global) {
+          for (int c = 0; c < 4; ++c) pp.st_q[c] = lin32(col[c]);
+          pp.st_base = lin32(vc);
+          for (int i2 = 0; i2 < ninj; ++i2) pp.st_gm[i2] = lin32(m[i2]);
+        }
+        return true;
+      };
+      if (sw.npre && !build_aff(sw.op_begin, sw.op_begin + sw.npre, true, sw.pre, false)) FRONT_FAIL(21);
       // ---- body: levels of mutually commuting ops
       {
         // peephole: ry(fixed alpha) -> CZ(q, thread-constant bit) -> ry on one register qubit q
@@ -940,6 +1000,7 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
       }
       sw.npost = (uint8_t)sim.post.size();
       sw.op_end = (uint16_t)nops;
+      if (sw.npost && !build_aff(nops - sw.npost, nops, false, sw.post, last)) FRONT_FAIL(22);
     }
     if (ntrig > TP_MAX_TRIG) FRONT_FAIL(20);
     pp.nops = nops;

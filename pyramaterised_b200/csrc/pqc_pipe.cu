@@ -369,34 +369,9 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
 #undef TP_RESCALE
 }
 
-#define TP_LIN4(x, a0, a1, a2, a3) \
-  ((((x)&1u) ? (a0) : 0u) ^ (((x)&2u) ? (a1) : 0u) ^ (((x)&4u) ? (a2) : 0u) ^ (((x)&8u) ? (a3) : 0u))
-
-// X / CNOT index permutations ops[begin, end) of a sweep as an affine map of the 4-bit register
-// index: label(j) = XOR_{k in j} col[k] ^ v (k_sweep_pass' `affine`).  reverse: the inverse order,
-// for permutations folded into the load.
-__device__ __forceinline__ void tp_affine(const PipePlan* P, int begin, int end, bool reverse,
-                                          uint32_t lidx, uint32_t tbase, uint32_t (&col)[4],
-                                          uint32_t& v) {
-  col[0] = 1u; col[1] = 2u; col[2] = 4u; col[3] = 8u;
-  v = 0u;
-  for (int q = 0; q < end - begin; ++q) {
-    const TPOp pm = P->ops[reverse ? end - 1 - q : begin + q];
-    const int kt = pm.b;
-    if (pm.kind == PQC_OP_X) {
-      v ^= 1u << kt;
-    } else if (pm.a != 0xff) {               // CNOT, control in registers
-      const int kc = pm.a;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) col[c] ^= ((col[c] >> kc) & 1u) << kt;
-      v ^= ((v >> kc) & 1u) << kt;
-    } else {                                 // CNOT, control fixed for this thread
-      const uint32_t cb = pm.t[0] != 0xffff ? ((lidx >> pm.t[0]) & 1u) : ((tbase >> pm.t[1]) & 1u);
-      v ^= cb << kt;
-    }
-  }
-}
-
+// X / CNOT index permutations of a sweep are affine maps of the 4-bit register index, label(j) =
+// XOR_{k in j} col[k] ^ v (k_sweep_pass' `affine`); the front planner works them out once per sweep
+// (TPAff, pqc_front.cu) and the kernel only XORs slot masks.
 template <bool GEN>
 __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
   extern __shared__ __align__(128) unsigned char tp_sm[];
@@ -505,11 +480,12 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
       const int npre = sw.npre, npost = sw.npost, ob = sw.op_begin, oe = sw.op_end;
       const bool last = s + 1 == nsw;
       if (npre) {
-        uint32_t col[4], v;
-        tp_affine(P, ob, ob + npre, true, lidx, tbase, col, v);
-        const uint32_t lb = sb ^ TP_LIN4(v, r0, r1, r2, r3);
-        const uint32_t l0 = TP_LIN4(col[0], r0, r1, r2, r3), l1 = TP_LIN4(col[1], r0, r1, r2, r3),
-                       l2 = TP_LIN4(col[2], r0, r1, r2, r3), l3 = TP_LIN4(col[3], r0, r1, r2, r3);
+        // planner-made relabeling: four slot masks, a base and one conditional XOR per CNOT whose
+        // control is fixed for the thread
+        uint32_t lb = sb ^ sw.pre.base;
+        for (int i = 0; i < sw.pre.ninj; ++i)
+          if (tp_partner_bit(sw.pre.inj[i].src, lidx, tbase)) lb ^= sw.pre.inj[i].lm;
+        const uint32_t l0 = sw.pre.l[0], l1 = sw.pre.l[1], l2 = sw.pre.l[2], l3 = sw.pre.l[3];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           a[j] = *reinterpret_cast<const c128*>(buf + (lb ^ XSEL4R(j, l0, l1, l2, l3)));
@@ -526,18 +502,17 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
         tp_cp_async_commit();
       }
       tp_ops<GEN>(a, P, sw, ob + npre, oe - npost, trig, lidx, tbase, tile, tiles_log2, gen, A, fscale);
-      uint32_t col[4] = {1u, 2u, 4u, 8u}, v = 0u;
-      if (npost) tp_affine(P, oe - npost, oe, false, lidx, tbase, col, v);
       if (last) {
         if (fscale != 1.0) op_scale(a, fscale);
         const uint32_t amp = tbase | P->st_t[0][lo] | P->st_t[1][hi];
         uint32_t g0 = P->st_r[0], g1 = P->st_r[1], g2 = P->st_r[2], g3 = P->st_r[3];
         uint32_t gb = amp;
         if (npost) {
-          gb = amp ^ TP_LIN4(v, g0, g1, g2, g3);
-          const uint32_t q0 = TP_LIN4(col[0], g0, g1, g2, g3), q1 = TP_LIN4(col[1], g0, g1, g2, g3),
-                         q2 = TP_LIN4(col[2], g0, g1, g2, g3), q3 = TP_LIN4(col[3], g0, g1, g2, g3);
-          g0 = q0; g1 = q1; g2 = q2; g3 = q3;
+          gb = amp ^ P->st_base;
+          const uint32_t lidx2 = (sw.tt[0][lo] ^ sw.tt[1][hi]) >> 16;   // re-read, not kept live
+          for (int i = 0; i < sw.post.ninj; ++i)
+            if (tp_partner_bit(sw.post.inj[i].src, lidx2, tbase)) gb ^= P->st_gm[i];
+          g0 = P->st_q[0]; g1 = P->st_q[1]; g2 = P->st_q[2]; g3 = P->st_q[3];
         }
         c128* dp = A.dst + (((long long)sample * A.slots_total + dst_slot) << A.n);
 #pragma unroll
@@ -553,9 +528,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
       const uint32_t sb2 = tw2 & 0xffffu;
       const uint32_t u0 = sw.rs[0], u1 = sw.rs[1], u2 = sw.rs[2], u3 = sw.rs[3];
       if (npost) {
-        const uint32_t lb = sb2 ^ TP_LIN4(v, u0, u1, u2, u3);
-        const uint32_t l0 = TP_LIN4(col[0], u0, u1, u2, u3), l1 = TP_LIN4(col[1], u0, u1, u2, u3),
-                       l2 = TP_LIN4(col[2], u0, u1, u2, u3), l3 = TP_LIN4(col[3], u0, u1, u2, u3);
+        uint32_t lb = sb2 ^ sw.post.base;
+        const uint32_t lidx2 = tw2 >> 16;
+        for (int i = 0; i < sw.post.ninj; ++i)
+          if (tp_partner_bit(sw.post.inj[i].src, lidx2, tbase)) lb ^= sw.post.inj[i].lm;
+        const uint32_t l0 = sw.post.l[0], l1 = sw.post.l[1], l2 = sw.post.l[2], l3 = sw.post.l[3];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           *reinterpret_cast<c128*>(buf + (lb ^ XSEL4R(j, l0, l1, l2, l3))) = a[j];

@@ -475,6 +475,25 @@ def test_meyer_wallach_tile_kernel_matches_generic_and_oracle(n, S, monkeypatch)
         assert abs(float(Q1[S - 1].item()) - orc.single_Q(st[S - 1].cpu().numpy(), n)) < ATOL
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 11, 12, 13])
+def test_meyer_wallach_on_random_states_every_small_size(n):
+    """Haar-like random states (not circuit outputs: every amplitude generic, unnormalised rows too)
+    at the sizes where the kernels change hands (k_mw_small up to 11 qubits, the tile kernel from
+    12): Q and every reduced density matrix against the oracle (measure.py:226-237)."""
+    g = np.random.default_rng(100 + n)
+    S = 37
+    st = g.normal(size=(S, 2 ** n)) + 1j * g.normal(size=(S, 2 ** n))
+    st /= np.linalg.norm(st, axis=1, keepdims=True)
+    d = torch.as_tensor(st, device="cuda")
+    Q = engine.meyer_wallach(d).cpu().numpy()
+    ref = np.array([orc.single_Q(s, n) for s in st])
+    assert np.abs(Q - ref).max() < 1e-12
+    for q in (0, n - 1):
+        m = st[5].reshape(2 ** q, 2, 2 ** (n - q - 1)).transpose(1, 0, 2).reshape(2, -1)
+        rho = engine.ptrace_1q(d[5], q).cpu().numpy().reshape(2, 2)
+        assert np.abs(rho - m @ m.conj().T).max() < 1e-12
+
+
 def test_ragged_and_empty_batches():
     """Batch edges: a QFIM batch that does not fill its last 256-set chunk, a single row, an
     empty batch; every row must equal the one-row call bit for bit (fixed summation orders)."""
