@@ -372,6 +372,18 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
 // X / CNOT index permutations of a sweep are affine maps of the 4-bit register index, label(j) =
 // XOR_{k in j} col[k] ^ v (k_sweep_pass' `affine`); the front planner works them out once per sweep
 // (TPAff, pqc_front.cu) and the kernel only XORs slot masks.
+
+// base slot (or amplitude) mask of a relabeled load / store: the constant part plus one XOR per CNOT
+// whose control bit is fixed for this thread.  Deliberately NOT inlined: inlined, the extra live values
+// change k_tile_pipe's register allocation under the 128-register cap and the XXZ passes (which never
+// come here) run 3 % slower; as a call the hardware-efficient passes keep 6 of the 8 % this table form
+// gains over walking the ops per thread (gpurun_out/r6b, profiles/r2_relabel_tables.md).
+__device__ __noinline__ uint32_t tp_aff_base(const TPAff* af, uint32_t lidx, uint32_t tbase) {
+  uint32_t x = af->base;
+  for (int i = 0; i < af->ninj; ++i)
+    if (tp_partner_bit(af->inj[i].src, lidx, tbase)) x ^= af->inj[i].lm;
+  return x;
+}
 template <bool GEN>
 __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
   extern __shared__ __align__(128) unsigned char tp_sm[];
@@ -482,9 +494,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
       if (npre) {
         // planner-made relabeling: four slot masks, a base and one conditional XOR per CNOT whose
         // control is fixed for the thread
-        uint32_t lb = sb ^ sw.pre.base;
-        for (int i = 0; i < sw.pre.ninj; ++i)
-          if (tp_partner_bit(sw.pre.inj[i].src, lidx, tbase)) lb ^= sw.pre.inj[i].lm;
+        const uint32_t lb = sb ^ tp_aff_base(&sw.pre, lidx, tbase);
         const uint32_t l0 = sw.pre.l[0], l1 = sw.pre.l[1], l2 = sw.pre.l[2], l3 = sw.pre.l[3];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -528,10 +538,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
       const uint32_t sb2 = tw2 & 0xffffu;
       const uint32_t u0 = sw.rs[0], u1 = sw.rs[1], u2 = sw.rs[2], u3 = sw.rs[3];
       if (npost) {
-        uint32_t lb = sb2 ^ sw.post.base;
-        const uint32_t lidx2 = tw2 >> 16;
-        for (int i = 0; i < sw.post.ninj; ++i)
-          if (tp_partner_bit(sw.post.inj[i].src, lidx2, tbase)) lb ^= sw.post.inj[i].lm;
+        const uint32_t lb = sb2 ^ tp_aff_base(&sw.post, tw2 >> 16, tbase);
         const uint32_t l0 = sw.post.l[0], l1 = sw.post.l[1], l2 = sw.post.l[2], l3 = sw.post.l[3];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
