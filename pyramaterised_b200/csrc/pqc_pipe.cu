@@ -31,6 +31,27 @@
 #include "pqc_ops.cuh"
 
 #define TP_THREADS 512
+// Op-set specialisation: k_tile_pipe is an interpreter at the 128-register cap, and its speed is set
+// by how ptxas lays out the op loop (profiles/r2_relabel_tables.md) -- so the kernel is compiled once
+// per FAMILY of op kinds, each instance carrying only the branches its passes can reach (and the Z
+// frame / the relabeling code only where they can occur).  The launcher picks the smallest set
+// that covers a pass' ops; TP_ALL is the catch-all (and the only one with in-pass spawns).
+#define TP_O_RY4 1
+#define TP_O_RY4PAD 2      // merged ry-CZ-ry slots (partner bytes): needs the Z frame
+#define TP_O_RZ4 4
+#define TP_O_RX4 8
+#define TP_O_CZF 16        // needs the Z frame
+#define TP_O_RXY 32
+#define TP_O_ZZSUM 64      // ZZSUM / GEN table phases
+#define TP_O_DIAG 128      // runs of R_z / CZ
+#define TP_O_REAL4 256
+#define TP_O_RZZ 512       // RZZ1 / RZZ2
+#define TP_O_PERM 1024     // X / CNOT relabelings at the sweep ends
+#define TP_ALL 2047
+#define TP_SET_XXZ (TP_O_RXY | TP_O_ZZSUM | TP_O_RZZ)
+#define TP_SET_HE (TP_O_RY4 | TP_O_RZ4 | TP_O_REAL4 | TP_O_PERM)
+#define TP_SET_NPQC (TP_O_RY4 | TP_O_RY4PAD | TP_O_RZ4 | TP_O_CZF | TP_O_DIAG | TP_O_REAL4)
+#define TP_HAS_FZ(OPS) (((OPS) & (TP_O_RY4PAD | TP_O_CZF)) != 0)
 #define TP_TILE_BYTES 65536
 #define TP_TRIG_BYTES (TP_MAX_TRIG * 16)
 #define TP_SMEM_TILES (TP_NBUF * TP_TILE_BYTES)
@@ -134,7 +155,7 @@ __device__ __forceinline__ void tp_zflush(c128 (&a)[16], uint32_t& fz) {
 // The 4-slot layer ops run all four slots unconditionally (identity parameters for absent gates):
 // straight-line code with an even number of register-set hand-overs, so the compiler needs no
 // register moves at the interpreter's merge point (a lone conditional rotation costs 32 moves).
-template <bool GEN>
+template <bool GEN, int OPS>
 __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const TPSweep& sw, int ob,
                                        int oe, const double2* trig, uint32_t lidx, uint32_t tbase,
                                        uint32_t tile, int tiles_log2, int gen, const PipeArgs& A,
@@ -156,7 +177,7 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
   for (int oi = ob; oi < oe; ++oi) {
     const TPOp op = P->ops[oi];
     const int kind = op.kind;
-    if (kind == PQC_K_LAYER_RY4) {
+    if ((OPS & TP_O_RY4) && kind == PQC_K_LAYER_RY4) {
       const int sk = op.sub;
       double2 c0 = ident, c1 = ident, c2 = ident, c3 = ident;
 #define TP_RY_SLOT(K, PB, C)                                                       \
@@ -174,14 +195,14 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
     }                                                                              \
     if ((fz >> K) & 1u) C.x = -C.x;                                                \
   }
-      if (op.pad) {                               // some slot is a merged ry-CZ-ry rotation
+      if ((OPS & TP_O_RY4PAD) && op.pad) {        // some slot is a merged ry-CZ-ry rotation
         TP_RY_SLOT(0, op.a, c0) TP_RY_SLOT(1, op.b, c1) TP_RY_SLOT(2, op.wt, c2) TP_RY_SLOT(3, op.nterms, c3)
       } else {                                    // plain layer: four predicated table reads
         if (sk & 0x03) c0 = trig[op.t[0]];
         if (sk & 0x0c) c1 = trig[op.t[1]];
         if (sk & 0x30) c2 = trig[op.t[2]];
         if (sk & 0xc0) c3 = trig[op.t[3]];
-        if (fz) {
+        if (TP_HAS_FZ(OPS) && fz) {
           if (fz & 1u) c0.x = -c0.x;
           if (fz & 2u) c1.x = -c1.x;
           if (fz & 4u) c2.x = -c2.x;
@@ -195,7 +216,7 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
       op_ry_t<3>(a, c3.x);
       fscale *= (c0.y * c1.y) * (c2.y * c3.y);
       TP_RESCALE()
-    } else if (kind == PQC_K_LAYER_RZ4) {
+    } else if ((OPS & TP_O_RZ4) && kind == PQC_K_LAYER_RZ4) {
       const int sk = op.sub;
       double2 c0 = ident, c1 = ident, c2 = ident, c3 = ident;
       if (sk & 0x03) c0 = trig[op.t[0]];
@@ -208,29 +229,33 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
       op_rz_t<3>(a, c3.x);
       fscale *= (c0.y * c1.y) * (c2.y * c3.y);
       TP_RESCALE()
-    } else if (kind == PQC_K_LAYER_RX4) {
+    } else if ((OPS & TP_O_RX4) && kind == PQC_K_LAYER_RX4) {
       const int sk = op.sub;
       double2 c0 = ident, c1 = ident, c2 = ident, c3 = ident;
       if (sk & 0x03) c0 = trig[op.t[0]];
       if (sk & 0x0c) c1 = trig[op.t[1]];
       if (sk & 0x30) c2 = trig[op.t[2]];
       if (sk & 0xc0) c3 = trig[op.t[3]];
-      if (fz & 1u) c0.x = -c0.x;
-      if (fz & 2u) c1.x = -c1.x;
-      if (fz & 4u) c2.x = -c2.x;
-      if (fz & 8u) c3.x = -c3.x;
+      if (TP_HAS_FZ(OPS)) {
+        if (fz & 1u) c0.x = -c0.x;
+        if (fz & 2u) c1.x = -c1.x;
+        if (fz & 4u) c2.x = -c2.x;
+        if (fz & 8u) c3.x = -c3.x;
+      }
       op_rx_t<0>(a, c0.x);
       op_rx_t<1>(a, c1.x);
       op_rx_t<2>(a, c2.x);
       op_rx_t<3>(a, c3.x);
       fscale *= (c0.y * c1.y) * (c2.y * c3.y);
       TP_RESCALE()
-    } else if (kind == PQC_K_CZF) {
+    } else if ((OPS & TP_O_CZF) && kind == PQC_K_CZF) {
       fz ^= tp_partner_bit(op.b, lidx, tbase) << op.a;
-    } else if (kind == PQC_K_RXY) {
+    } else if ((OPS & TP_O_RXY) && kind == PQC_K_RXY) {
       double2 cs = trig[op.t[0]];
-      const int ka = op.a >> 2, kb = op.a & 3;
-      if (((fz >> ka) ^ (fz >> kb)) & 1u) cs.y = -cs.y;
+      if (TP_HAS_FZ(OPS)) {
+        const int ka = op.a >> 2, kb = op.a & 3;
+        if (((fz >> ka) ^ (fz >> kb)) & 1u) cs.y = -cs.y;
+      }
       switch (op.a) {
         case 1: op_xy<0, 1>(a, cs.x, cs.y); break;
         case 2: op_xy<0, 2>(a, cs.x, cs.y); break;
@@ -239,7 +264,7 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
         case 7: op_xy<1, 3>(a, cs.x, cs.y); break;
         default: op_xy<2, 3>(a, cs.x, cs.y); break;
       }
-    } else if (kind == PQC_K_RZZ1) {
+    } else if ((OPS & TP_O_RZZ) && kind == PQC_K_RZZ1) {
       const double2 cs = trig[op.t[0]];
       switch (op.a) {
         case 1: op_rzz1<0, 1>(a, cs.x, cs.y); break;
@@ -249,12 +274,12 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
         case 7: op_rzz1<1, 3>(a, cs.x, cs.y); break;
         default: op_rzz1<2, 3>(a, cs.x, cs.y); break;
       }
-    } else if (kind == PQC_K_RZZ2) {
+    } else if ((OPS & TP_O_RZZ) && kind == PQC_K_RZZ2) {
       const double2 cs = trig[op.t[0]];
       if (op.a == 0) op_rzz2<0, 1>(a, cs.x, cs.y);
       else if (op.a == 1) op_rzz2<0, 2>(a, cs.x, cs.y);
       else op_rzz2<0, 3>(a, cs.x, cs.y);
-    } else if (kind == PQC_K_ZZSUM || kind == PQC_K_GEN) {
+    } else if ((OPS & TP_O_ZZSUM) && (kind == PQC_K_ZZSUM || kind == PQC_K_GEN)) {
       // w(x) = w(tile) ^ w(thread part) ^ w(register value j); wn holds w per tile nibble value
       const uint32_t(*wn)[16] = P->wn[op.wt];
       uint32_t w0 = wn[0][lidx & 15u] ^ wn[1][(lidx >> 4) & 15u] ^ wn[2][lidx >> 8];
@@ -282,7 +307,7 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
           a[j] = make_double2(v.x * fr - v.y * fi, v.y * fr + v.x * fi);
         }
       }
-    } else if (kind == PQC_OP_RZ || kind == PQC_OP_CZ) {
+    } else if ((OPS & TP_O_DIAG) && (kind == PQC_OP_RZ || kind == PQC_OP_CZ)) {
       // ---- a run of diagonal ops: accumulate, then apply once (as k_layer_seq)
       double tc = 1.0, ts = 0.0;                  // thread-level phase (tc + i ts)
       double pc[4] = {1.0, 1.0, 1.0, 1.0}, pn[4] = {0.0, 0.0, 0.0, 0.0};   // bit k = 1: (pc + i pn)
@@ -345,9 +370,9 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
           a[j] = make_double2(tp_flip(a[j].x, m), tp_flip(a[j].y, m));
         }
       }
-    } else if (kind == PQC_K_LAYER_REAL4) {
+    } else if ((OPS & TP_O_REAL4) && kind == PQC_K_LAYER_REAL4) {
       // ry / Hadamard mix (initial layers): H does not commute with a pending Z frame
-      if (fz) tp_zflush(a, fz);
+      if (TP_HAS_FZ(OPS) && fz) tp_zflush(a, fz);
       const int sk = op.sub;
       double f = 1.0;
 #define TP_REAL_SLOT(K)                                                    \
@@ -360,12 +385,12 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
 #undef TP_REAL_SLOT
       fscale *= f;
       TP_RESCALE()
-    } else if (kind == PQC_K_ZFLUSH) {
+    } else if (TP_HAS_FZ(OPS) && kind == PQC_K_ZFLUSH) {
       if (fz) tp_zflush(a, fz);
     }
   }
-  if (fz) tp_zflush(a, fz);
-  if (lscale != 1.0) op_scale(a, lscale);
+  if (TP_HAS_FZ(OPS) && fz) tp_zflush(a, fz);
+  if ((OPS & TP_O_RY4PAD) && lscale != 1.0) op_scale(a, lscale);
 #undef TP_RESCALE
 }
 
@@ -384,7 +409,7 @@ __device__ __noinline__ uint32_t tp_aff_base(const TPAff* af, uint32_t lidx, uin
     if (tp_partner_bit(af->inj[i].src, lidx, tbase)) x ^= af->inj[i].lm;
   return x;
 }
-template <bool GEN>
+template <bool GEN, int OPS>
 __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
   extern __shared__ __align__(128) unsigned char tp_sm[];
   double2* trigs = reinterpret_cast<double2*>(tp_sm + TP_SMEM_TILES);
@@ -491,7 +516,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
       const uint32_t r0 = sw.rs[0], r1 = sw.rs[1], r2 = sw.rs[2], r3 = sw.rs[3];
       const int npre = sw.npre, npost = sw.npost, ob = sw.op_begin, oe = sw.op_end;
       const bool last = s + 1 == nsw;
-      if (npre) {
+      if ((OPS & TP_O_PERM) && npre) {
         // planner-made relabeling: four slot masks, a base and one conditional XOR per CNOT whose
         // control is fixed for the thread
         const uint32_t lb = sb ^ tp_aff_base(&sw.pre, lidx, tbase);
@@ -511,13 +536,13 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
         if (k + TP_NBUF < nk) load_tile(k + TP_NBUF);
         tp_cp_async_commit();
       }
-      tp_ops<GEN>(a, P, sw, ob + npre, oe - npost, trig, lidx, tbase, tile, tiles_log2, gen, A, fscale);
+      tp_ops<GEN, OPS>(a, P, sw, ob + npre, oe - npost, trig, lidx, tbase, tile, tiles_log2, gen, A, fscale);
       if (last) {
         if (fscale != 1.0) op_scale(a, fscale);
         const uint32_t amp = tbase | P->st_t[0][lo] | P->st_t[1][hi];
         uint32_t g0 = P->st_r[0], g1 = P->st_r[1], g2 = P->st_r[2], g3 = P->st_r[3];
         uint32_t gb = amp;
-        if (npost) {
+        if ((OPS & TP_O_PERM) && npost) {
           gb = amp ^ P->st_base;
           const uint32_t lidx2 = (sw.tt[0][lo] ^ sw.tt[1][hi]) >> 16;   // re-read, not kept live
           for (int i = 0; i < sw.post.ninj; ++i)
@@ -537,7 +562,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_tile_pipe(const PipeArgs A) {
       const uint32_t tw2 = sw.tt[0][lo] ^ sw.tt[1][hi];
       const uint32_t sb2 = tw2 & 0xffffu;
       const uint32_t u0 = sw.rs[0], u1 = sw.rs[1], u2 = sw.rs[2], u3 = sw.rs[3];
-      if (npost) {
+      if ((OPS & TP_O_PERM) && npost) {
         const uint32_t lb = sb2 ^ tp_aff_base(&sw.post, tw2 >> 16, tbase);
         const uint32_t l0 = sw.post.l[0], l1 = sw.post.l[1], l2 = sw.post.l[2], l3 = sw.post.l[3];
 #pragma unroll
@@ -716,8 +741,31 @@ bool pqc_pipe_build(const V1Pass& ps, int n, PipePlan& pp) {
   return true;
 }
 
+// the op kinds (and sweep-end relabelings) a plan uses, as a TP_O_* mask
+static int tp_plan_ops(const PipePlan& pp) {
+  int m = 0;
+  for (int i = 0; i < pp.nops; ++i) {
+    const TPOp& o = pp.ops[i];
+    switch (o.kind) {
+      case PQC_K_LAYER_RY4: m |= TP_O_RY4 | (o.pad ? TP_O_RY4PAD : 0); break;
+      case PQC_K_LAYER_RZ4: m |= TP_O_RZ4; break;
+      case PQC_K_LAYER_RX4: m |= TP_O_RX4; break;
+      case PQC_K_CZF: case PQC_K_ZFLUSH: m |= TP_O_CZF; break;
+      case PQC_K_RXY: m |= TP_O_RXY; break;
+      case PQC_K_ZZSUM: case PQC_K_GEN: m |= TP_O_ZZSUM; break;
+      case PQC_OP_RZ: case PQC_OP_CZ: m |= TP_O_DIAG; break;
+      case PQC_K_LAYER_REAL4: m |= TP_O_REAL4; break;
+      case PQC_K_RZZ1: case PQC_K_RZZ2: m |= TP_O_RZZ; break;
+      case PQC_OP_X: case PQC_OP_CNOT: m |= TP_O_PERM; break;
+      default: m |= TP_ALL; break;
+    }
+  }
+  for (int s2 = 0; s2 < pp.nsw; ++s2)
+    if (pp.sw[s2].npre || pp.sw[s2].npost) m |= TP_O_PERM;
+  return m;
+}
+
 int pqc_pipe_launch(const PipeArgs& a, const PipePlan& hplan, cudaStream_t st) {
-  (void)hplan;
   int dev = 0;
   PQC_CUDA(cudaGetDevice(&dev));
   static int sms[64] = {0};
@@ -725,19 +773,28 @@ int pqc_pipe_launch(const PipeArgs& a, const PipePlan& hplan, cudaStream_t st) {
   if (dev < 0 || dev >= 64) PQC_FAIL(-1, "device index out of range");
   if (!attr[dev]) {
     PQC_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
-    PQC_CUDA(cudaFuncSetAttribute(k_tile_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)TP_SMEM_TOTAL));
-    PQC_CUDA(cudaFuncSetAttribute(k_tile_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)TP_SMEM_TOTAL));
+#define TP_ATTR(K) PQC_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_TOTAL))
+    TP_ATTR((k_tile_pipe<false, TP_ALL>));
+    TP_ATTR((k_tile_pipe<true, TP_ALL>));
+    TP_ATTR((k_tile_pipe<false, TP_SET_XXZ>));
+    TP_ATTR((k_tile_pipe<false, TP_SET_HE>));
+    TP_ATTR((k_tile_pipe<false, TP_SET_NPQC>));
+#undef TP_ATTR
     attr[dev] = true;
   }
   const long long total = a.n_items << (a.n - 12);
   if (total <= 0) return 0;
   if (total > 0x7fffffffLL) PQC_FAIL(-1, "pass grid too large; split the batch");
   const unsigned grid = (unsigned)std::min<long long>(total, sms[dev]);
+  // the smallest compiled op set that covers this plan (PQC_PIPE_OPSET=all: always the catch-all)
+  static const bool all_only = getenv("PQC_PIPE_OPSET") && strcmp(getenv("PQC_PIPE_OPSET"), "all") == 0;
+  const int need = tp_plan_ops(hplan);
   const int h = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st, PQC_PROF_TILE_PIPE);
-  if (a.nspawn > 0) k_tile_pipe<true><<<grid, TP_THREADS, TP_SMEM_TOTAL, st>>>(a);
-  else k_tile_pipe<false><<<grid, TP_THREADS, TP_SMEM_TOTAL, st>>>(a);
+  if (a.nspawn > 0) k_tile_pipe<true, TP_ALL><<<grid, TP_THREADS, TP_SMEM_TOTAL, st>>>(a);
+  else if (!all_only && !(need & ~TP_SET_XXZ)) k_tile_pipe<false, TP_SET_XXZ><<<grid, TP_THREADS, TP_SMEM_TOTAL, st>>>(a);
+  else if (!all_only && !(need & ~TP_SET_HE)) k_tile_pipe<false, TP_SET_HE><<<grid, TP_THREADS, TP_SMEM_TOTAL, st>>>(a);
+  else if (!all_only && !(need & ~TP_SET_NPQC)) k_tile_pipe<false, TP_SET_NPQC><<<grid, TP_THREADS, TP_SMEM_TOTAL, st>>>(a);
+  else k_tile_pipe<false, TP_ALL><<<grid, TP_THREADS, TP_SMEM_TOTAL, st>>>(a);
   pqc_prof_launch_end(h, st);
   PQC_LAUNCH_CHECK();
   return 0;
