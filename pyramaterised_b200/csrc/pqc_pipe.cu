@@ -49,7 +49,7 @@
 #define TP_O_PERM 1024     // X / CNOT relabelings at the sweep ends
 #define TP_ALL 2047
 #define TP_SET_XXZ (TP_O_RXY | TP_O_ZZSUM | TP_O_RZZ)
-#define TP_SET_HE (TP_O_RY4 | TP_O_RZ4 | TP_O_REAL4 | TP_O_PERM)
+#define TP_SET_HE (TP_O_RY4 | TP_O_RZ4 | TP_O_PERM)
 #define TP_SET_NPQC (TP_O_RY4 | TP_O_RY4PAD | TP_O_RZ4 | TP_O_CZF | TP_O_DIAG | TP_O_REAL4)
 #define TP_HAS_FZ(OPS) (((OPS) & (TP_O_RY4PAD | TP_O_CZF)) != 0)
 #define TP_TILE_BYTES 65536
@@ -399,11 +399,11 @@ __device__ __forceinline__ void tp_ops(c128 (&a)[16], const PipePlan* P, const T
 // (TPAff, pqc_front.cu) and the kernel only XORs slot masks.
 
 // base slot (or amplitude) mask of a relabeled load / store: the constant part plus one XOR per CNOT
-// whose control bit is fixed for this thread.  Deliberately NOT inlined: inlined, the extra live values
-// change k_tile_pipe's register allocation under the 128-register cap and the XXZ passes (which never
-// come here) run 3 % slower; as a call the hardware-efficient passes keep 6 of the 8 % this table form
-// gains over walking the ops per thread (gpurun_out/r6b, profiles/r2_relabel_tables.md).
-__device__ __noinline__ uint32_t tp_aff_base(const TPAff* af, uint32_t lidx, uint32_t tbase) {
+// whose control bit is fixed for this thread.  (While the kernel was one monolithic interpreter this
+// had to be a non-inlined call: inlined, it changed the register allocation and slowed the XXZ passes,
+// which never come here, by 3 %.  With one kernel instance per op family the families no longer share
+// an allocation, and inlined it is worth 7 % on the CNOT-chain instance: profiles/r2_relabel_tables.md.)
+__device__ __forceinline__ uint32_t tp_aff_base(const TPAff* af, uint32_t lidx, uint32_t tbase) {
   uint32_t x = af->base;
   for (int i = 0; i < af->ninj; ++i)
     if (tp_partner_bit(af->inj[i].src, lidx, tbase)) x ^= af->inj[i].lm;
