@@ -23,34 +23,25 @@
 #include "pqc_common.cuh"
 #include "pqc_ops.cuh"
 
-#ifndef PQC_FRONT_SEQ_MAX_QUBITS
-#define PQC_FRONT_SEQ_MAX_QUBITS 22    // XXZ-type circuits: the front plan up to here (see pqc_use_front)
-#endif
 
 // Which plan runs PQC.run.  The front plan (pqc_front.cu, few deep passes on k_tile_pipe) wins
 // wherever the block plan would run passes on the generic interpreter (CNOT-chain circuits:
-// 2.2x), k_layer_seq passes with runs of R_z / CZ (NPQC: 1.6x - 4x), and -- since the R_zz bonds
-// that sit on the register bits are direct phases instead of table-lookup ops (PQC_K_RZZ1 / 2) --
-// the XXZ template's layer-sequence passes up to 22 qubits (12q x 16: 6.0 against 8.5 ms per 8192
-// states, 14q: 16.0 / 19.3 ms per 4096, 16q: 35.7 / 43.9 ms per 2048, 18q x 8: 21.9 / 23.8 ms per
-// 512, 20q x 8: 50.6 / 55.2 ms per 256; at 24q x 4 the 19 light passes win, 33.5 / 35.6 ms per 16:
-// profiles/r2_rzz_register_ops.md).  The block plan stays when every one of its passes is a
-// layer pass (TFIM: k_layer_pass' compile-time geometry, 1.7x).
+// 2.8x), k_layer_seq passes with runs of R_z / CZ (NPQC: 1.6x - 4x), and -- since the register-bond
+// R_zz are direct phases and k_tile_pipe has an instance of its own for the XXZ op family -- the XXZ
+// template's layer-sequence passes at every size measured (12q x 16: 4.7 against 8.5 ms per 8192
+// states, 16q x 16: 27.5 / 43.9 ms per 2048, 20q x 8: 37.1 / 55.2 ms per 256, 24q x 4: 26.3 / 33.5 ms
+// per 16, 28q x 2: 35.8 / 41.0 ms per 2: profiles/r2_rzz_register_ops.md, r2_relabel_tables.md).
+// The block plan stays when every one of its passes is a layer pass (TFIM: k_layer_pass'
+// compile-time geometry, 1.7x).
 // PQC_FRONT=0 / 1 forces the choice (read per call so tests can compare the plans).
 bool pqc_use_front(const pqc_program* prog) {
   if (!prog->front_ok || prog->front_run.empty()) return false;
   const char* e = getenv("PQC_FRONT");
   if (e && strcmp(e, "0") == 0) return false;
   if (e && strcmp(e, "1") == 0) return true;
-  bool all_fast = !prog->v1_run.empty(), all_light = all_fast;
-  for (int pi : prog->v1_run) {
-    const V1Pass& ps = prog->v1_passes[pi];
-    all_fast = all_fast && ps.fast_ok;
-    all_light = all_light && (ps.fast_ok || (ps.seq_ok && !ps.seq.has_diag));
-  }
-  if (all_fast) return false;
-  if (all_light && prog->n > PQC_FRONT_SEQ_MAX_QUBITS) return false;
-  return true;
+  bool all_fast = !prog->v1_run.empty();
+  for (int pi : prog->v1_run) all_fast = all_fast && prog->v1_passes[pi].fast_ok;
+  return !all_fast;
 }
 
 bool pqc_use_v0() {
