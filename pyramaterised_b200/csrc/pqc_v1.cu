@@ -1823,7 +1823,7 @@ struct SeqArgs {
 // thread-level phase T, one phase per register bit (bit = 1 takes the conjugate), a 16-bit sign
 // mask -- and applied together: at most 16 complex multiplications per touched register bit
 // whatever the number of gates.  `base` = the thread's tile-local index (register bits zero).
-template <bool GEN, bool DIAG, int RN, int NX, int NY>
+template <bool GEN, bool DIAG, bool LAYERS, int RN, int NX, int NY>
 __device__ __forceinline__ void seq_ops(c128 (&a)[16], const SeqArgs& A, int slot, int vx, int vy,
                                         const double2* trig, const uint32_t (*s_wn)[3][16],
                                         const uint32_t* s_wb, int gen, double& fscale,
@@ -1906,7 +1906,7 @@ __device__ __forceinline__ void seq_ops(c128 (&a)[16], const SeqArgs& A, int slo
         case 7: op_xy<1, 3>(a, cs.x, cs.y); break;
         default: op_xy<2, 3>(a, cs.x, cs.y); break;
       }
-    } else if (kind == PQC_K_LAYER_RX4) {
+    } else if (LAYERS && kind == PQC_K_LAYER_RX4) {
       const int sk = op.subk;
       double2 c0 = make_double2(0.0, 1.0), c1 = c0, c2 = c0, c3 = c0;
       if (sk & 0xff) c0 = trig[op.t[0]];
@@ -1918,7 +1918,7 @@ __device__ __forceinline__ void seq_ops(c128 (&a)[16], const SeqArgs& A, int slo
       op_rx_t<2>(a, c2.x);
       op_rx_t<3>(a, c3.x);
       fscale *= (c0.y * c1.y) * (c2.y * c3.y);
-    } else if (kind == PQC_K_LAYER_REAL4) {
+    } else if (LAYERS && kind == PQC_K_LAYER_REAL4) {
       const int sk = op.subk;
       double f = 1.0;
 #define SEQ_REAL_SLOT(K)                                                   \
@@ -1958,7 +1958,9 @@ __device__ __forceinline__ void seq_ops(c128 (&a)[16], const SeqArgs& A, int slo
   }
 }
 
-template <bool GEN, bool DIAG>
+// LAYERS = false: the pass has no 4-slot rotation layer ops (every pass of the XXZ template): their
+// branches are compiled out of the op loop (the same reasoning as k_tile_pipe's op sets)
+template <bool GEN, bool DIAG, bool LAYERS>
 __global__ void __launch_bounds__(256, 2) k_layer_seq(const SeqArgs A) {
   extern __shared__ __align__(16) c128 lp_sm[];
   double2* trig = reinterpret_cast<double2*>(lp_sm + 4096);
@@ -2057,11 +2059,11 @@ __global__ void __launch_bounds__(256, 2) k_layer_seq(const SeqArgs A) {
       }
     }
     if (g == 0)
-      seq_ops<GEN, DIAG, 2, 0, 1>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale, (uint32_t)tid, tbase);
+      seq_ops<GEN, DIAG, LAYERS, 2, 0, 1>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale, (uint32_t)tid, tbase);
     else if (g == 1)
-      seq_ops<GEN, DIAG, 0, 1, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale, (uint32_t)tid << 4, tbase);
+      seq_ops<GEN, DIAG, LAYERS, 0, 1, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale, (uint32_t)tid << 4, tbase);
     else
-      seq_ops<GEN, DIAG, 1, 0, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale,
+      seq_ops<GEN, DIAG, LAYERS, 1, 0, 2>(a, A, s, lo, hi, trig, s_wn, s_wb, gen, fscale,
                             (uint32_t)lo | ((uint32_t)hi << 8), tbase);
     if (s + 1 == nsw && g != 1 && !A.staged) break;   // the registers go straight to global memory
     if (s + 1 == nsw && fscale != 1.0) op_scale(a, fscale);
@@ -2862,18 +2864,30 @@ static int launch_v1(const V1Args& a_in, cudaStream_t st) {
     }
     static PqcDeviceOnce qattr_once;
     if (qattr_once.first()) {
-      PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+#define SEQ_ATTR(G, D, L) PQC_CUDA(cudaFuncSetAttribute(k_layer_seq<G, D, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024))
+      SEQ_ATTR(false, false, true); SEQ_ATTR(true, false, true); SEQ_ATTR(false, true, true); SEQ_ATTR(true, true, true);
+      SEQ_ATTR(false, false, false); SEQ_ATTR(true, false, false);
+#undef SEQ_ATTR
     }
     const size_t qsmem = 4096 * sizeof(c128) + (size_t)a.ntrig * sizeof(double2);
     const int hq = pqc_prof_launch_begin((double)a.n_items * 2.0 * sizeof(c128) * (double)(1ll << a.n), st, PQC_PROF_LAYER_SEQ);
     const bool sp = a.nspawn > 0, dg = f.plan.has_diag != 0;
-    if (sp && dg) k_layer_seq<true, true><<<(unsigned)grid, 256, qsmem, st>>>(f);
-    else if (sp) k_layer_seq<true, false><<<(unsigned)grid, 256, qsmem, st>>>(f);
-    else if (dg) k_layer_seq<false, true><<<(unsigned)grid, 256, qsmem, st>>>(f);
-    else k_layer_seq<false, false><<<(unsigned)grid, 256, qsmem, st>>>(f);
+    bool layers = false;                         // any 4-slot rotation layer op in the pass?
+    {
+      const SeqPlan& q = a.hpass->seq;
+      int tot = 0;
+      for (int i = 0; i < q.nsw; ++i) tot = std::max(tot, q.off[i] + q.nops[i]);
+      for (int i = 0; i < tot; ++i)
+        layers = layers || q.ops[i].kind == PQC_K_LAYER_RX4 || q.ops[i].kind == PQC_K_LAYER_REAL4;
+      static const bool force = getenv("PQC_SEQ_LAYERS") != nullptr;      // A/B: always the full op set
+      layers = layers || force;
+    }
+    if (sp && dg) k_layer_seq<true, true, true><<<(unsigned)grid, 256, qsmem, st>>>(f);
+    else if (dg) k_layer_seq<false, true, true><<<(unsigned)grid, 256, qsmem, st>>>(f);
+    else if (sp && layers) k_layer_seq<true, false, true><<<(unsigned)grid, 256, qsmem, st>>>(f);
+    else if (sp) k_layer_seq<true, false, false><<<(unsigned)grid, 256, qsmem, st>>>(f);
+    else if (layers) k_layer_seq<false, false, true><<<(unsigned)grid, 256, qsmem, st>>>(f);
+    else k_layer_seq<false, false, false><<<(unsigned)grid, 256, qsmem, st>>>(f);
     pqc_prof_launch_end(hq, st);
     PQC_LAUNCH_CHECK();
     return 0;
