@@ -31,17 +31,26 @@
 // template's layer-sequence passes at every size measured (12q x 16: 4.7 against 8.5 ms per 8192
 // states, 16q x 16: 27.5 / 43.9 ms per 2048, 20q x 8: 37.1 / 55.2 ms per 256, 24q x 4: 26.3 / 33.5 ms
 // per 16, 28q x 2: 35.8 / 41.0 ms per 2: profiles/r2_rzz_register_ops.md, r2_relabel_tables.md).
-// The block plan stays when every one of its passes is a layer pass (TFIM: k_layer_pass'
-// compile-time geometry, 1.7x).
+// The block plan stays for circuits without XY rotations whose passes are all layer passes or
+// plain layer-sequence passes (TFIM: k_layer_pass' compile-time geometry, 1.7x).
 // PQC_FRONT=0 / 1 forces the choice (read per call so tests can compare the plans).
 bool pqc_use_front(const pqc_program* prog) {
   if (!prog->front_ok || prog->front_run.empty()) return false;
   const char* e = getenv("PQC_FRONT");
   if (e && strcmp(e, "0") == 0) return false;
   if (e && strcmp(e, "1") == 0) return true;
-  bool all_fast = !prog->v1_run.empty();
-  for (int pi : prog->v1_run) all_fast = all_fast && prog->v1_passes[pi].fast_ok;
-  return !all_fast;
+  // layer passes (compile-time geometry) and layer-sequence passes without R_z / CZ runs are the
+  // light block-plan passes: they keep TFIM-type circuits (at 18+ qubits some of their passes need
+  // another sweep order and run on k_layer_seq; the front plan is 1.7x slower on TFIM at 16 qubits).
+  // A circuit with XY pair rotations (the XXZ type) takes the front plan although its passes are light.
+  bool all_light = !prog->v1_run.empty();
+  for (int pi : prog->v1_run) {
+    const V1Pass& ps = prog->v1_passes[pi];
+    all_light = all_light && (ps.fast_ok || (ps.seq_ok && !ps.seq.has_diag));
+  }
+  bool has_xy = false;
+  for (const pqc_op& o : prog->ops) has_xy = has_xy || o.kind == PQC_OP_RXX || o.kind == PQC_OP_RYY;
+  return !all_light || has_xy;
 }
 
 bool pqc_use_v0() {
