@@ -100,6 +100,16 @@ class Gate:
             return OpSum([self.operation])
         return OpSum([b.operation if isinstance(b, Gate) else b, self.operation])
 
+    def get_op(self):
+        """The reference's per-class matrix builder (gates.py:122-123, 226-232, 303-304 ...): here
+        every gate's operator is the symbolic form of its primitive ops."""
+        return self.operation
+
+    def set_properties(self):
+        """gates.py:125-127, 160-173, 510-512: picks the QuTiP gate function and Pauli of a subclass;
+        here those are class attributes (`_kind`, `_axis`), nothing to set."""
+        return None
+
     def set_theta(self, theta):
         return
 
@@ -557,6 +567,84 @@ class RR_block(shared_parameter):
 
 
 # %% fSim ----------------------------------------------------------------------------------------------
+def _expand_2toN(m4, N, control, target):
+    """qutip's gate_expand_2toN on a host matrix: the 4 x 4 `m4` (first factor = `control`) on qubits
+    control / target of an N-qubit register, qubit 0 most significant (gates.py:595-597)."""
+    if N < 2 or control == target or not (0 <= control < N and 0 <= target < N):
+        raise ValueError("control and target must be two different qubits of the register")
+    if N > 12:
+        raise MemoryError("dense form is only provided for N <= 12")
+    D = 1 << N
+    b = np.arange(D)
+    sc, st = N - 1 - control, N - 1 - target
+    col4 = 2 * ((b >> sc) & 1) + ((b >> st) & 1)
+    rest = b & ~((1 << sc) | (1 << st))
+    out = np.zeros((D, D), dtype=np.complex128)
+    for r4 in range(4):
+        rows = rest | ((r4 >> 1) << sc) | ((r4 & 1) << st)
+        out[rows, b] = m4[r4, col4]
+    return out
+
+
+def _fsim_matrix(theta, phi, which):
+    """The 4 x 4 matrices of gates.py:598-606 (which = 0), 619-627 (1: "d/dtheta") and 640-648
+    (2: "d/dphi") exactly as written there -- the |00> entry of both derivative matrices stays 1 and
+    d/dtheta keeps exp(-i phi) (quirk Q3 of SURVEY.md)."""
+    c, s, e = np.cos(theta), np.sin(theta), np.exp(-1j * phi)
+    m = np.zeros((4, 4), dtype=np.complex128)
+    m[0, 0] = 1
+    if which == 1:
+        m[1, 1] = m[2, 2] = -s
+        m[1, 2] = m[2, 1] = -1j * c
+    else:
+        m[1, 1] = m[2, 2] = c
+        m[1, 2] = m[2, 1] = -1j * s
+    m[3, 3] = -1j * e if which == 2 else e
+    return m
+
+
+def _two_qubit_dense(m4, N, control, target):
+    if (control == 1 and target == 0) and N is None:          # gates.py:591-592
+        N = 2
+    if N is None:
+        return qt.DenseOp(m4, [[2, 2], [2, 2]])
+    return qt.DenseOp(_expand_2toN(m4, N, control, target), [[2] * N, [2] * N])
+
+
+def fsim_gate(theta, phi, N=None, control=0, target=1):
+    """gates.py:588-606.  On a register (N given) the gate is the symbolic one-op Operator -- it acts
+    on device states at any N and `.full()` gives the matrix; without N the bare 4 x 4 matrix."""
+    if (control == 1 and target == 0) and N is None:
+        N = 2
+    if N is None:
+        return qt.DenseOp(_fsim_matrix(theta, phi, 0), [[2, 2], [2, 2]])
+    return Operator(N, [_op(_lib.OP_FSIM, control, target, scale=phi, offset=theta)])
+
+
+def fsim_gate_d_theta(theta, phi, N=None, control=0, target=1):
+    """gates.py:609-627 (dense: N <= 12; derivative STATES at any N come from PQC.get_gradients)."""
+    return _two_qubit_dense(_fsim_matrix(theta, phi, 1), N, control, target)
+
+
+def fsim_gate_d_phi(theta, phi, N=None, control=0, target=1):
+    """gates.py:630-648"""
+    return _two_qubit_dense(_fsim_matrix(theta, phi, 2), N, control, target)
+
+
+def fixed_fsim_gate(theta, N=None, control=0, target=1):
+    """gates.py:700-716: fSim with phi = 0."""
+    if (control == 1 and target == 0) and N is None:
+        N = 2
+    if N is None:
+        return qt.DenseOp(_fsim_matrix(theta, 0.0, 0), [[2, 2], [2, 2]])
+    return Operator(N, [_op(_lib.OP_FIXED_FSIM, control, target, offset=theta)])
+
+
+def fixed_fsim_gate_d_theta(theta, N=None, control=0, target=1):
+    """gates.py:719-737"""
+    return _two_qubit_dense(_fsim_matrix(theta, 0.0, 1), N, control, target)
+
+
 class fSim(PRot):
     """Two-parameter fSim(theta, phi) (gates.py:588-606,651-697)."""
 
@@ -580,10 +668,19 @@ class fSim(PRot):
         return [_op(_lib.OP_FSIM, self.q1, self.q2, scale=self.phi, offset=self.theta)]
 
     def derivative(self):
-        raise NotImplementedError("fSim has no symbolic derivative operator; derivative STATES "
-                                  "(quirk-Q3 matrices) come from PQC.get_gradients / take_derivative")
+        # the reference's fSim inherits PRot.derivative (gates.py:133-139), which reads a `fock`
+        # attribute fSim.__init__ never sets (gates.py:652-660): an AttributeError there as well
+        raise AttributeError("fSim has no single derivative (no `fock` generator, as in the reference); "
+                             "use parameterised_derivative(1 | 2)")
 
-    parameterised_derivative = lambda self, param: self.derivative()
+    def parameterised_derivative(self, param):
+        """gates.py:680-693: param 1 -> 'd/dtheta', 2 -> 'd/dphi' as dense operators (N <= 12; the
+        derivative STATES of PQC.get_gradients / take_derivative come from the op's kernels)."""
+        if param == 1:
+            return fsim_gate_d_theta(self.theta, self.phi, N=self.q_N, control=self.q1, target=self.q2)
+        if param == 2:
+            return fsim_gate_d_phi(self.theta, self.phi, N=self.q_N, control=self.q1, target=self.q2)
+        raise ValueError("fSim has parameters 1 (theta) and 2 (phi)")
 
     def flip_pauli(self):
         pass
@@ -610,8 +707,9 @@ class fixed_fSim(PRot):
         return [_op(_lib.OP_FIXED_FSIM, self.q1, self.q2, offset=self.theta)]
 
     def derivative(self):
-        raise NotImplementedError("fixed_fSim has no symbolic derivative operator; derivative "
-                                  "STATES come from PQC.get_gradients / take_derivative")
+        """gates.py:753-756 as a dense operator (N <= 12; derivative STATES at any N come from
+        PQC.get_gradients / take_derivative)."""
+        return fixed_fsim_gate_d_theta(self.theta, N=self.q_N, control=self.q1, target=self.q2)
 
     def flip_pauli(self):
         pass

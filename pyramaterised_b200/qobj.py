@@ -68,6 +68,13 @@ class DenseOp:
             return DenseOp(self._m @ o._m, self.dims)
         if _is_scalar(o):
             return DenseOp(self._m * o, self.dims)
+        if isinstance(o, State):
+            # dense operator on a ket (what `ARBGATE * state` is in the reference, gates.py:63-67):
+            # one row-major matrix-vector product in the library (csrc/pqc_dense.cu)
+            if self._m.shape[1] != o.tensor.numel():
+                raise TypeError("incompatible dimensions")
+            M = torch.from_numpy(np.ascontiguousarray(self._m)).to(o.tensor.device)
+            return State(engine.dense_apply(o.tensor.reshape(1, -1), M)[0], o.dims)
         return NotImplemented
 
     __rmul__ = lambda self, o: DenseOp(self._m * o, self.dims) if _is_scalar(o) else NotImplemented

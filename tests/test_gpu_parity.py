@@ -607,6 +607,38 @@ def test_operator_algebra_and_state_surface(golden):
     assert np.abs(d.numpy() - orc.apply_1q(out.numpy()[None], N, 1, -0.5j * orc.SY)[0]).max() < ATOL
 
 
+def test_dense_operators_act_on_states():
+    """`ARBGATE * state` (gates.py:63-67 with the dense operation of gates.py:416-420) and the dense
+    fSim derivative operators of gates.py:609-648, 719-737 acting on device kets; fsim_gate on a
+    register as a symbolic operator whose dense form is the embedded 4 x 4 matrix."""
+    import scipy.linalg
+    G = pyqc.gates
+    N, th, ph = 3, 0.37, 1.21
+    rng = np.random.default_rng(11)
+    v = rng.standard_normal(1 << N) + 1j * rng.standard_normal(1 << N)
+    v /= np.linalg.norm(v)
+    psi = pyqc.State(v)
+    H = pyqc.templates.TFIM_hamiltonian(N, 0.8, 0.1)
+    g = pyqc.ARBGATE(H)
+    g.set_theta(0.6)
+    out = g * psi
+    assert out.dims == psi.dims
+    assert np.abs(out.numpy().reshape(-1) - scipy.linalg.expm(-0.6j * H.full()) @ v).max() < ATOL
+    for d, fn in ((1, G.fsim_gate_d_theta), (2, G.fsim_gate_d_phi)):
+        got = fn(th, ph, N=N, control=2, target=0) * psi
+        want = orc.apply_2q(v[None].copy(), N, 2, 0, orc.fsim_matrix(th, ph, d))[0]
+        assert np.abs(got.numpy().reshape(-1) - want).max() < ATOL
+    U = G.fsim_gate(th, ph, N=N, control=0, target=2).full()
+    assert np.abs(U - G._expand_2toN(orc.fsim_matrix(th, ph, 0), N, 0, 2)).max() < 1e-14
+    U = G.fixed_fsim_gate(th, N=N, control=1, target=2).full()
+    assert np.abs(U - G._expand_2toN(orc.fixed_fsim_matrix(th, 0), N, 1, 2)).max() < 1e-14
+    f = pyqc.fSim([0, 2], N)
+    f.set_theta(th)
+    f.set_phi(ph)
+    assert np.abs((f * psi).numpy().reshape(-1)
+                  - orc.apply_2q(v[None].copy(), N, 0, 2, orc.fsim_matrix(th, ph, 0))[0]).max() < ATOL
+
+
 def test_fidelity_dmma_matches_fma_and_numpy(monkeypatch):
     """The FP64 tensor-core pair-fidelity kernel against the CUDA-core one and numpy, on
     ragged sizes, rectangular and triangular blocks, with identical integer histograms."""

@@ -240,6 +240,54 @@ def test_arbgate_host_surface():
     assert [s[0] for s in prog.segs] == ["ops", "dense", "ops"] and prog.P == 3
 
 
+def test_fsim_matrix_functions_and_get_op_surface():
+    """The module-level fSim matrices of gates.py:588-648, 700-737 (quirk-Q3 entries included), their
+    embedding on a register (qutip's gate_expand_2toN, qubit 0 most significant, first factor =
+    control) against the oracle's matrix-free two-qubit application, and the get_op / set_properties
+    surface every reference gate class has (gates.py:122-127)."""
+    G = pyqc.gates
+    th, ph = 0.37, 1.21
+    for d, fn in enumerate((G.fsim_gate, G.fsim_gate_d_theta, G.fsim_gate_d_phi)):
+        assert np.array_equal(fn(th, ph).full(), orc.fsim_matrix(th, ph, d))
+    assert np.array_equal(G.fixed_fsim_gate(th).full(), orc.fixed_fsim_matrix(th, 0))
+    assert np.array_equal(G.fixed_fsim_gate_d_theta(th).full(), orc.fixed_fsim_matrix(th, 1))
+    assert G.fsim_gate_d_phi(th, ph).dims == [[2, 2], [2, 2]]
+    # control = 1, target = 0 without N means N = 2 (gates.py:591-592)
+    assert G.fsim_gate_d_theta(th, ph, control=1, target=0).shape == (4, 4)
+    rng = np.random.default_rng(5)
+    for (N, c, t) in [(2, 1, 0), (3, 0, 2), (4, 3, 1), (5, 1, 2)]:
+        psi = rng.standard_normal((1, 1 << N)) + 1j * rng.standard_normal((1, 1 << N))
+        for d, fn in ((1, G.fsim_gate_d_theta), (2, G.fsim_gate_d_phi)):
+            M = fn(th, ph, N=N, control=c, target=t)
+            assert M.dims == [[2] * N, [2] * N]
+            want = orc.apply_2q(psi.copy(), N, c, t, orc.fsim_matrix(th, ph, d))[0]
+            assert np.abs(M.full() @ psi[0] - want).max() < 1e-14
+        M = G.fixed_fsim_gate_d_theta(th, N=N, control=c, target=t)
+        want = orc.apply_2q(psi.copy(), N, c, t, orc.fixed_fsim_matrix(th, 1))[0]
+        assert np.abs(M.full() @ psi[0] - want).max() < 1e-14
+    # on a register the gates themselves are one-op symbolic operators (any N)
+    op = G.fsim_gate(th, ph, N=20, control=3, target=4)
+    assert op.n == 20 and [o[0] for o in op.ops] == [_lib.OP_FSIM]
+    assert [o[0] for o in G.fixed_fsim_gate(th, N=20, control=3, target=4).ops] == [_lib.OP_FIXED_FSIM]
+    with pytest.raises(ValueError):
+        G.fsim_gate_d_phi(th, ph, N=3, control=1, target=1)
+    # gate objects: derivative operators as the reference returns them
+    f = pyqc.fSim([0, 2], 3)
+    f.set_theta(th)
+    f.set_phi(ph)
+    assert f.parameterised_derivative(1) == G.fsim_gate_d_theta(th, ph, N=3, control=0, target=2)
+    assert f.parameterised_derivative(2) == G.fsim_gate_d_phi(th, ph, N=3, control=0, target=2)
+    with pytest.raises(AttributeError):
+        f.derivative()
+    ff = pyqc.fixed_fSim([1, 0], 2)
+    ff.set_theta(th)
+    assert ff.derivative() == G.fixed_fsim_gate_d_theta(th, N=2, control=1, target=0)
+    for g in (pyqc.R_x(0, 2), pyqc.H(1, 2), pyqc.CNOT([0, 1], 2), pyqc.CHAIN(pyqc.CZ, 3),
+              pyqc.R_zz([0, 1], 2), f, ff):
+        assert g.set_properties() is None
+        assert g.get_op().ops == g.operation.ops
+
+
 def test_front_planner_plans_and_plan_choice():
     """The light-cone planner (pqc_front.cu), host only.  NPQC: the odd qubits (one first-layer
     rotation each, then only CZ partners: cheap unblockers) are cleared in light sweeps first, so
