@@ -125,6 +125,66 @@ def test_c_abi_exports_every_declared_symbol():
     assert b"n_qubits" in lib.pqc_last_error()
 
 
+def test_c_abi_from_a_plain_c_host(tmp_path):
+    """The boundary is a C ABI, not a Python one: include/pqc_b200.h compiles as pedantic C99 and a
+    C host linked against libpqc_b200.so plans a gate program (TFIM-like layer on 16 qubits: H, R_zz
+    ring, R_x -- gates.py:106-147,493-537) without a GPU, reads the plan back and gets the library's
+    error string on a bad call.  No compute entry point is called."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "host.c"
+    src.write_text(r"""
+#include "pqc_b200.h"
+#include <stdio.h>
+#include <string.h>
+int main(void) {
+  enum { N = 16 };
+  pqc_op ops[3 * N];
+  int k = 0, q;
+  pqc_program* prog = 0;
+  int64_t st[8];
+  static char text[1 << 16];
+  for (q = 0; q < N; ++q, ++k) {            /* Hadamard layer */
+    pqc_op o = {PQC_OP_H, 0, -1, -1, -1, 0, 1.0, 0.0};
+    o.q0 = q; o.group = k; ops[k] = o;
+  }
+  for (q = 0; q < N; ++q, ++k) {            /* R_zz ring sharing parameter 0 */
+    pqc_op o = {PQC_OP_RZZ, 0, 0, 0, -1, 0, 1.0, 0.0};
+    o.q0 = q; o.q1 = (q + 1) % N; o.group = N; ops[k] = o;
+  }
+  for (q = 0; q < N; ++q, ++k) {            /* R_x layer sharing parameter 1 */
+    pqc_op o = {PQC_OP_RX, 0, -1, 1, -1, 0, 1.0, 0.0};
+    o.q0 = q; o.group = N + 1; ops[k] = o;
+  }
+  if (pqc_abi_version() != 1) return 2;
+  if (pqc_program_create(N, 2, k, ops, &prog) != 0) { printf("create: %s\n", pqc_last_error()); return 3; }
+  if (pqc_program_stats(prog, st) != 0) return 4;
+  if (pqc_program_describe(prog, text, sizeof text) < 0) return 5;
+  printf("n=%lld P=%lld ops=%lld passes=%lld grad=%lld\n", (long long)st[0], (long long)st[1],
+         (long long)st[2], (long long)st[3], (long long)st[5]);
+  printf("has_pass=%d\n", strstr(text, "PASS") != 0);
+  pqc_program_destroy(prog);
+  prog = 0;
+  if (pqc_program_create(0, 0, 0, 0, &prog) >= 0) return 6;
+  printf("err=%s\n", pqc_last_error());
+  return 0;
+}
+""")
+    exe = tmp_path / "host"
+    libdir = os.path.join(ROOT, "pyramaterised_b200")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror",
+                    "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lpqc_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.splitlines()
+    assert lines[0].startswith("n=16 P=2 ops=48 passes=") and lines[0].endswith("grad=1")
+    assert 1 <= int(re.search(r"passes=(\d+)", lines[0]).group(1)) <= 3
+    assert lines[1] == "has_pass=1" and "n_qubits" in lines[2]
+
+
 def test_no_cpu_fallback_and_no_oracle_import():
     import torch
     pkg = os.path.join(ROOT, "pyramaterised_b200")
