@@ -22,7 +22,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
+#include <queue>
 #include <tuple>
 
 #include "pqc_common.cuh"
@@ -113,6 +115,20 @@ struct Front {
   std::vector<uint64_t> desc;    // transitive successors of every op, N x dw bits
   int dw = 0;
   int cur_stamp = 0;
+  // worklist forms of the two simulations below (same results, cost proportional to what a
+  // simulation touches instead of to the whole pending list; PQC_FRONT_CHECK=1 runs both forms
+  // and aborts on any difference)
+  std::vector<std::vector<int>> succ;
+  std::vector<int> live;         // predecessors of an op that are not done yet
+  std::vector<int> cnt, cstamp;  // of those, the ones not taken in the current simulation (valid
+                                 // when cstamp == cur_stamp)
+  std::vector<int> cand_mark;    // == cand_id: member of the current pass' closure
+  int cand_id = 0;
+  std::vector<int> pfront;       // pending ops whose predecessors are all done (per pass)
+  std::vector<int> sfront;       // the same among the closure's not-done ops (per sweep choice)
+  bool worklist = true;          // false: weights are not all 1.0 (PQC_FRONT_ALPHA), sums would
+                                 // depend on the visiting order -- keep the scans
+  bool check = false;
 
   bool ready(int i) const {
     for (int p : preds[i])
@@ -120,8 +136,69 @@ struct Front {
     return true;
   }
 
-  // mixing ops + permutations the closure of `tile` can execute (any number of sweeps)
+  void mark_done(int i) {
+    if (done[i]) return;
+    done[i] = 1;
+    for (int j : succ[i]) --live[j];
+  }
+
+  // ops of `from` that are not done and whose predecessors are all done, in program order
+  void frontier_of(const std::vector<int>& from, std::vector<int>& out) const {
+    out.clear();
+    for (int i : from)
+      if (!done[i] && live[i] == 0) out.push_back(i);
+  }
+
+  // op i was taken by the current simulation: true when that was j's last missing predecessor
+  bool last_pred_taken(int j) {
+    if (cstamp[j] != cur_stamp) {
+      cstamp[j] = cur_stamp;
+      cnt[j] = live[j];
+    }
+    return --cnt[j] == 0;
+  }
+
+  // closure_weight_scan as a worklist from `pfront`: the closure is the least fixed point of
+  // "fits the tile and every predecessor is done or inside", whatever the visiting order; the
+  // weights are all 1.0 here, so the sum does not depend on the order either
+  double closure_weight_fast(uint32_t tile, std::vector<int>* out) {
+    ++cur_stamp;
+    double w = 0;
+    std::vector<int> work;
+    for (int i : pfront)
+      if (!((ops[i].mix | ops[i].tgt) & ~tile)) work.push_back(i);
+    while (!work.empty()) {
+      const int i = work.back();
+      work.pop_back();
+      const FOp& o = ops[i];
+      stamp[i] = cur_stamp;
+      if (o.mix || o.tgt) w += wgt[i];
+      if (out) out->push_back(i);
+      for (int j : succ[i])
+        if (last_pred_taken(j) && !((ops[j].mix | ops[j].tgt) & ~tile)) work.push_back(j);
+    }
+    return w;
+  }
+
   double closure_weight(uint32_t tile, const std::vector<int>& pending, std::vector<int>* out) {
+    if (!worklist) return closure_weight_scan(tile, pending, out);
+    if (!check) return closure_weight_fast(tile, out);
+    std::vector<int> a, b;
+    const double wa = closure_weight_scan(tile, pending, &a);
+    const double wb = closure_weight_fast(tile, &b);
+    std::sort(a.begin(), a.end());
+    std::sort(b.begin(), b.end());
+    if (wa != wb || a != b) {
+      fprintf(stderr, "front planner: closure worklist differs from the scan (%g / %g, %zu / %zu ops)\n",
+              wa, wb, a.size(), b.size());
+      abort();
+    }
+    if (out) out->insert(out->end(), b.begin(), b.end());
+    return wb;
+  }
+
+  // mixing ops + permutations the closure of `tile` can execute (any number of sweeps)
+  double closure_weight_scan(uint32_t tile, const std::vector<int>& pending, std::vector<int>* out) {
     ++cur_stamp;
     double w = 0;
     bool changed = true;
@@ -155,8 +232,8 @@ struct Front {
   // what one sweep with register bits R can execute: permutations first (folded into the load),
   // then every ready op whose mixing bits are register bits, then permutations (folded into the
   // store).  `cand` = the pass' closure, in program order.
-  void sim_sweep(uint32_t R, const std::vector<int>& cand, int op_room, int trig_room, int wt_room,
-                 SweepSim& S) {
+  void sim_sweep_scan(uint32_t R, const std::vector<int>& cand, int op_room, int trig_room,
+                      int wt_room, SweepSim& S) {
     ++cur_stamp;
     S.pre.clear(); S.body.clear(); S.post.clear();
     S.weight = 0;
@@ -223,6 +300,93 @@ struct Front {
     }
     S.ntrig = ntrig;
     S.ntables = (int)zzkeys.size();
+  }
+
+  // sim_sweep_scan from the ready frontier (`sfront`) instead of over the whole closure.  The scan
+  // visits the closure in program order and every predecessor of an op precedes it, so one round
+  // of a phase takes whatever the phase can take, in ascending op index; a min-heap over the
+  // ready ops pops in exactly that order (an op enters when its last predecessor is taken, and
+  // that predecessor has a smaller index), refusals (register set, room) are final within a
+  // phase, and the ready ops a phase refused are the next phase's start.  Same takes, same order,
+  // same room / level / table bookkeeping.
+  void sim_sweep_fast(uint32_t R, int op_room, int trig_room, int wt_room, SweepSim& S) {
+    ++cur_stamp;
+    S.pre.clear(); S.body.clear(); S.post.clear();
+    S.weight = 0;
+    int nops = 0, ntrig = 0;
+    std::vector<std::pair<int, int>> zzkeys;
+    auto level_of = [&](int i) {
+      int lv = 1;
+      for (int p : preds[i])
+        if (!done[p] && stamp[p] == cur_stamp && lvl[p] > 0) lv = std::max(lv, lvl[p] + 1);
+      return lv;
+    };
+    auto trig_need = [&](const FOp& o) {
+      if (o.kind == PQC_OP_RZZ) return 2;
+      if (o.kind == PQC_OP_H || o.kind == PQC_OP_CZ || o.kind == PQC_OP_IDENT || is_perm(o)) return 0;
+      return 1;
+    };
+    auto room = [&](int i, const FOp& o) {
+      if (nops + 1 > op_room) return false;
+      if (ntrig + trig_need(o) > trig_room) return false;
+      if (o.kind == PQC_OP_RZZ) {
+        const std::pair<int, int> key(o.param, level_of(i));
+        if (std::find(zzkeys.begin(), zzkeys.end(), key) == zzkeys.end() &&
+            (int)zzkeys.size() + 1 > wt_room)
+          return false;
+      }
+      return true;
+    };
+    std::priority_queue<int, std::vector<int>, std::greater<int>> heap;
+    std::vector<int> refused;
+    for (int i : sfront) heap.push(i);
+    for (int phase = 0; phase < 3; ++phase) {
+      std::vector<int>& where = phase == 0 ? S.pre : (phase == 1 ? S.body : S.post);
+      refused.clear();
+      while (!heap.empty()) {
+        const int i = heap.top();
+        heap.pop();
+        const FOp& o = ops[i];
+        bool ok;
+        if (is_perm(o)) ok = phase != 1 && !(o.tgt & ~R);
+        else ok = phase == 1 && !(o.mix & ~R);
+        if (!(ok && room(i, o))) {
+          refused.push_back(i);
+          continue;
+        }
+        lvl[i] = phase == 1 ? level_of(i) : 0;
+        stamp[i] = cur_stamp;
+        where.push_back(i);
+        ++nops;
+        ntrig += trig_need(o);
+        if (o.kind == PQC_OP_RZZ) {
+          const std::pair<int, int> key(o.param, lvl[i]);
+          if (std::find(zzkeys.begin(), zzkeys.end(), key) == zzkeys.end()) zzkeys.push_back(key);
+        }
+        if (o.mix || o.tgt) S.weight += wgt[i];
+        for (int j : succ[i])
+          if (last_pred_taken(j) && cand_mark[j] == cand_id) heap.push(j);
+      }
+      for (int i : refused) heap.push(i);
+    }
+    S.ntrig = ntrig;
+    S.ntables = (int)zzkeys.size();
+  }
+
+  void sim_sweep(uint32_t R, const std::vector<int>& cand, int op_room, int trig_room, int wt_room,
+                 SweepSim& S) {
+    if (!worklist) return sim_sweep_scan(R, cand, op_room, trig_room, wt_room, S);
+    if (!check) return sim_sweep_fast(R, op_room, trig_room, wt_room, S);
+    SweepSim T;
+    sim_sweep_scan(R, cand, op_room, trig_room, wt_room, T);
+    sim_sweep_fast(R, op_room, trig_room, wt_room, S);
+    if (T.pre != S.pre || T.body != S.body || T.post != S.post || T.weight != S.weight ||
+        T.ntrig != S.ntrig || T.ntables != S.ntables) {
+      fprintf(stderr, "front planner: sweep worklist differs from the scan (R = %x: %zu+%zu+%zu / "
+              "%zu+%zu+%zu ops)\n", R, T.pre.size(), T.body.size(), T.post.size(), S.pre.size(),
+              S.body.size(), S.post.size());
+      abort();
+    }
   }
 };
 
@@ -358,9 +522,17 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
     F.dw = W;
     F.desc.assign((size_t)N * W, 0);
     std::vector<uint64_t>& desc = F.desc;
-    std::vector<std::vector<int>> succ(N);
+    F.succ.assign(N, {});
+    std::vector<std::vector<int>>& succ = F.succ;
     for (int j = 0; j < N; ++j)
       for (int i : F.preds[j]) succ[i].push_back(j);
+    F.cand_mark.assign(N, 0);
+    F.live.assign(N, 0);
+    for (int j = 0; j < N; ++j) F.live[j] = (int)F.preds[j].size();
+    F.cnt.assign(N, 0);
+    F.cstamp.assign(N, 0);
+    F.worklist = alpha == 0.0;
+    F.check = getenv("PQC_FRONT_CHECK") != nullptr;
     F.wgt.assign(N, 1.0);
     for (int i = N - 1; i >= 0; --i) {
       uint64_t* di = &desc[(size_t)i * W];
@@ -386,6 +558,7 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
     if (++guard > 4096) FRONT_FAIL(5);
     // ---- tile: grow by closure gain per added bit (candidates: the missing bits of pending ops)
     uint32_t tile = low;
+    F.frontier_of(pending, F.pfront);
     // cheap unblockers first: a bit with at most two pending rotations that many ops on OTHER bits
     // wait for (NPQC's odd qubits: one first-layer rotation each, then only CZ partners).  With
     // them in the tile early the later passes run whole chains with every register slot busy and
@@ -443,6 +616,8 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
     std::vector<int> cand;
     F.closure_weight(tile, pending, &cand);
     std::sort(cand.begin(), cand.end());
+    ++F.cand_id;
+    for (int i : cand) F.cand_mark[i] = F.cand_id;
     int tb[12], lpos[32], nt = 0;
     for (int b = 0; b < 32; ++b) lpos[b] = -1;
     for (int b = 0; b < n; ++b)
@@ -502,6 +677,7 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
               for (int d = c + 1; d < m; ++d)
                 Rs.push_back((1u << ub[a]) | (1u << ub[b]) | (1u << ub[c]) | (1u << ub[d]));
       }
+      F.frontier_of(cand, F.sfront);
       for (uint32_t R : Rs) {
         F.sim_sweep(R, cand, TP_MAX_OPS - 4 - ops_used, TP_MAX_TRIG - 2 - trig_used,
                     TP_MAX_WT - wt_used, cur);
@@ -518,9 +694,9 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
         // (its geometry is irrelevant to them) instead of opening one of their own
         break;
       }
-      for (int i : best.pre) F.done[i] = 1;
-      for (int i : best.body) F.done[i] = 1;
-      for (int i : best.post) F.done[i] = 1;
+      for (int i : best.pre) F.mark_done(i);
+      for (int i : best.body) F.mark_done(i);
+      for (int i : best.post) F.mark_done(i);
       const int nz = best.ntables, ntr = best.ntrig;
       ops_used += best_total;
       trig_used += ntr;
@@ -543,7 +719,7 @@ static bool front_impl(pqc_program* prog, std::vector<TrigJob>& tjobs) {
           bool rdy = true;
           for (int p : F.preds[i]) if (!F.done[p]) rdy = false;
           if (!rdy) continue;
-          F.done[i] = 1;
+          F.mark_done(i);
           sweeps.back().sim.body.push_back(i);
           ++ops_used;
           trig_used += o.kind == PQC_OP_RZZ ? 2 : 1;

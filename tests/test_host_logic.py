@@ -389,6 +389,25 @@ def test_front_planner_plans_and_plan_choice():
     assert head.endswith("used for PQC.run: 1") and qc.program.n_passes == passes
 
 
+def test_front_planner_worklist_equals_scan_and_plans_fast(monkeypatch):
+    """The front planner simulates candidate tiles and sweeps thousands of times per pass.  Both
+    simulations run from the ready frontier (a worklist / a min-heap over ready ops) instead of
+    scanning the whole pending list; PQC_FRONT_CHECK=1 runs the original scans next to them at every
+    call and aborts the process on any difference.  Planning a deep 12-qubit CNOT-chain circuit
+    (1392 ops; 17 s with the scans, meet-in-the-middle sub-plans included) must stay interactive."""
+    import time
+    t0 = time.time()
+    assert "FRONT plan" in pyqc.templates.generate_circuit("qg_circuit", 12, 20).program.describe()
+    assert time.time() - t0 < 8.0
+    d6 = pyqc.templates.generate_circuit("qg_circuit", 12, 6).program.describe()
+    monkeypatch.setenv("PQC_FRONT_CHECK", "1")
+    assert pyqc.templates.generate_circuit("qg_circuit", 12, 6).program.describe() == d6
+    for kind, n, p in (("NPQC", 16, 16), ("XXZ", 16, 16), ("generic_HE", 16, 16), ("NPQC", 28, 20),
+                       ("Circuit_9", 14, 5), ("TFIM", 18, 4), ("clifford", 13, 8)):
+        kw = {"shuffle": False} if kind == "XXZ" else {}
+        assert "FRONT plan" in pyqc.templates.generate_circuit(kind, n, p, **kw).program.describe()
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the arm the driver runs beside ours): one JSON line with the
     contract's keys, at a size a CPU finishes instantly; it must not need a GPU or the CUDA library."""
